@@ -1,0 +1,159 @@
+/* ad4sm_b200.h -- C ABI of libad4sm_b200.so: the B200-native `makeϕrKt` hot path of AD4SM.jl.
+ *
+ * The reference (AD4SM.jl v0.0.7, pure Julia) has no FFI of its own; the boundary it offers is
+ * multiple dispatch on `Elements.makeϕrKt` / `Elements.makeϕrKt_d`.  Each entry point below names
+ * the reference method(s) it replaces; `ad4sm.jl_b200/julia/AD4SMB200.jl` re-defines those methods
+ * with `ccall` into this library.
+ *
+ * Conventions
+ *   - plain C types only; all arrays are caller-owned host memory unless a name ends in `_dev`.
+ *   - node ids and CSC indices are 1-based Int64, exactly as Julia holds them.
+ *   - `u` is the reference's `u::Matrix{Float64}` (dofs_per_node x n_nodes, column-major);
+ *     DOF id = (node-1)*dofs_per_node + comp   (elements.toolkit.jl:183,187).
+ *   - every function returns 0 on success and a negative AD4SM_E* code otherwise;
+ *     `ad4sm_last_error()` returns a thread-local message.  Nothing throws across the ABI.
+ *   - one in-flight call per plan.  There is NO CPU fallback: without a CUDA device every
+ *     compute entry point fails with AD4SM_ENODEV.
+ */
+#ifndef AD4SM_B200_H
+#define AD4SM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AD4SM_ABI_VERSION 1
+
+/* status codes */
+#define AD4SM_OK 0
+#define AD4SM_EINVAL (-1)  /* bad argument / unsupported element-material combination */
+#define AD4SM_ENODEV (-2)  /* no CUDA device / CUDA runtime error */
+#define AD4SM_ENOMEM (-3)
+#define AD4SM_ESTATE (-4)  /* call order (e.g. fetch before eval) */
+#define AD4SM_ENCCL (-5)
+
+/* element kinds: CEElem{D,P,M,T,N} (elements.jl:71-77), CPElem (elements.jl:104-111) */
+#define AD4SM_ELEM_CE 0
+#define AD4SM_ELEM_CP 1
+
+/* material kinds (elasticmaterials.jl:25-120, phasefieldmaterials.jl:5-16) */
+#define AD4SM_MAT_HOOKE 1        /* params: E, nu                flags: SMALL */
+#define AD4SM_MAT_HOOKE2D 2      /* params: E, nu                flags: SMALL, PLANE_STRESS */
+#define AD4SM_MAT_NEOHOOKE 3     /* params: C1, K   (K<0: incompressible / plane-stress form) */
+#define AD4SM_MAT_MOONEYRIVLIN 4 /* params: C1, C2, K */
+#define AD4SM_MAT_OGDEN 5        /* params: alpha, mu, K */
+#define AD4SM_MAT_PHASEFIELD 6   /* params[0..3]: base material, params[4..6]: l0, Gc, n; mat_base = base kind */
+
+/* material flags */
+#define AD4SM_F_SMALL 1u              /* `small=true`: E = sym(F)-I instead of Green-Lagrange */
+#define AD4SM_F_PLANE_STRESS 2u       /* Hooke2D{T,:plane_stress} */
+#define AD4SM_F_DHN 4u                /* PhaseField{M,:DHn} (default :ATn) */
+#define AD4SM_F_PF_GRAD_INTENDED 8u   /* d-phase: keep d/dd of l0^2|∇d|^2 (reference drops it, toolkit:159-166) */
+#define AD4SM_F_NH2D_EXT 16u          /* PhaseField{NeoHooke} on 2x2 F: plane-strain embedding (extension) */
+
+/* fields a plan can assemble for */
+#define AD4SM_FIELD_U 0 /* displacement dofs: dofs_per_node per node */
+#define AD4SM_FIELD_D 1 /* phase-field dofs: 1 per node (makeϕrKt_d) */
+
+/* One homogeneous group of elements: same element type parameters (kind, D, P, N) and the same
+ * material.  This is the SoA packing of a `Vector{CEElem}` / `Vector{CPElem}`
+ * (elements.jl:71-77,104-111); array layouts follow the reference's nesting order. */
+typedef struct ad4sm_batch {
+  int32_t elem_kind;      /* AD4SM_ELEM_* */
+  int32_t dim;            /* D: 2 or 3 */
+  int32_t n_gauss;        /* P */
+  int32_t n_elem_nodes;   /* N */
+  int32_t mat_kind;       /* AD4SM_MAT_* */
+  int32_t mat_base;       /* base material kind when mat_kind == PHASEFIELD, else 0 */
+  uint32_t mat_flags;     /* AD4SM_F_* */
+  int32_t reserved;
+  double mat_params[8];
+  int64_t n_elems;
+  const int64_t* nodes;      /* [n_elems][N]        elem.nodes, 1-based */
+  const double* gradN;       /* [n_elems][D][P][N]  elem.∇N[d][gp][a] */
+  const double* wgt;         /* [n_elems][P]        elem.wgt[gp] */
+  const double* Nval;        /* [n_elems][P][N]     elem.N[gp][a]   (CPElem; NULL for CEElem) */
+  const int64_t* orig_index; /* [n_elems] 0-based position of each element in `elems` (fixes the
+                                summation order); NULL = positions continue after the previous batch */
+} ad4sm_batch;
+
+typedef struct ad4sm_plan ad4sm_plan; /* opaque: device copies of the batches + CSC pattern + scatter maps */
+
+/* Pointers into plan-owned DEVICE memory holding the result of the last evaluation of `field`
+ * (valid until the next evaluation / plan destruction).  The pattern is the structural one;
+ * `n_zero` tells whether `dropzeros` would remove anything. */
+typedef struct ad4sm_device_view {
+  int64_t n_dof, nnz;
+  const double* phi_dev;    /* [1] */
+  const double* r_dev;      /* [n_dof] */
+  const double* nzval_dev;  /* [nnz]  structural CSC(=CSR, Kt is symmetric) values */
+  const int64_t* colptr_dev; /* [n_dof+1] 1-based */
+  const int64_t* rowval_dev; /* [nnz]     1-based */
+  const int64_t* n_zero_dev; /* [1] number of stored exact zeros in nzval */
+} ad4sm_device_view;
+
+int ad4sm_abi_version(void);
+const char* ad4sm_last_error(void);
+int ad4sm_device_count(int* count);
+
+/* Build a plan for `elems` (replaces the per-call boxing/allocation of _assemble_ϕrKt,
+ * elasticelements.jl:208-221, and the triplet/sparse machinery of elements.toolkit.jl:169-203).
+ * All batches must have the same N (the reference requires equal dofs/elem, elasticelements.jl:212-214).
+ * dofs_per_node = size(u,1) (>= D; extra rows of u are ignored by getF, toolkit:13, and yield
+ * structural zeros that dropzeros removes). `device` = CUDA ordinal, -1 = current. */
+int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_nodes, int32_t dofs_per_node,
+                      int32_t device, ad4sm_plan** plan_out);
+void ad4sm_plan_destroy(ad4sm_plan* plan);
+
+/* Structural CSC pattern of Kt (before dropzeros) for a field: sizes, then the arrays. */
+int ad4sm_plan_pattern_size(ad4sm_plan* plan, int32_t field, int64_t* n_dof, int64_t* nnz);
+int ad4sm_plan_pattern(ad4sm_plan* plan, int32_t field, int64_t* colptr /*[n_dof+1]*/, int64_t* rowval /*[nnz]*/);
+
+/* makeϕrKt(elems, u)  -- elasticelements.jl:356-358.  Writes ϕ and r (length(u)); leaves Kt on the
+ * device and reports nnz AFTER dropzeros so the caller can size the arrays for ad4sm_fetch_csc. */
+int ad4sm_eval(ad4sm_plan* plan, const double* u, double* phi, double* r, int64_t* nnz_out);
+
+/* makeϕr: ϕ and r only -- elements.toolkit.jl:204-215 applied to the element loop of :216-218. */
+int ad4sm_eval_phi_r(ad4sm_plan* plan, const double* u, double* phi, double* r);
+
+/* makeϕrKt(elems::Vector{<:CPElem}, u, d) -- phasefieldelements.jl:228-238 (d indexed by node). */
+int ad4sm_eval_pf_u(ad4sm_plan* plan, const double* u, const double* d, double* phi, double* r, int64_t* nnz_out);
+
+/* makeϕrKt_d(elems, u, d) / makeϕrKt_d(elems, u, d, ϕmax) -- phasefieldelements.jl:239-262.
+ * `hist`: NULL, or one pointer per batch to [n_elems][P][2] doubles (ϕmax[e][gp] tuples), updated
+ * in place like the reference mutates ϕmax (:180).  r has n_nodes entries. */
+int ad4sm_eval_pf_d(ad4sm_plan* plan, const double* u, const double* d, double* const* hist, double* phi, double* r,
+                    int64_t* nnz_out);
+
+/* SparseMatrixCSC arrays of the last evaluation, after dropzeros (toolkit:202).  Any pointer may be NULL. */
+int ad4sm_fetch_csc(ad4sm_plan* plan, int64_t* colptr, int64_t* rowval, double* nzval);
+
+/* ---- device-resident path (inputs/outputs stay in HBM; used by GPU-side callers and bench.py) ---- */
+int ad4sm_set_stream(ad4sm_plan* plan, void* cuda_stream); /* cudaStream_t; NULL = plan's own stream */
+/* mode: 0 = elastic (ad4sm_eval), 1 = PF u-phase, 2 = PF d-phase, 3 = elastic ϕ,r only.
+ * u_dev [dpn*n_nodes], d_dev [n_nodes] or NULL, hist_dev: NULL or concatenated [sum n_elems*P*2].
+ * Asynchronous on the plan's stream. */
+int ad4sm_eval_device(ad4sm_plan* plan, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev);
+int ad4sm_device_view_get(ad4sm_plan* plan, int32_t field, ad4sm_device_view* view);
+int ad4sm_sync(ad4sm_plan* plan);
+
+/* Per-kernel CUDA-event timing (bench.py roofline): enable, run evaluations, then read the
+ * accumulated milliseconds and launch counts per kernel class. */
+#define AD4SM_PROF_ELEMENT 0  /* K1 element energy/gradient/Hessian */
+#define AD4SM_PROF_ASSEMBLE 1 /* K2 segmented assembly of Kt and r */
+#define AD4SM_PROF_REDUCE 2   /* ϕ reduction */
+#define AD4SM_PROF_GATHER 3   /* u gather / misc */
+#define AD4SM_PROF_NCLASS 4
+int ad4sm_profile_enable(ad4sm_plan* plan, int32_t on);
+int ad4sm_profile_read(ad4sm_plan* plan, double ms[AD4SM_PROF_NCLASS], int64_t launches[AD4SM_PROF_NCLASS],
+                       int32_t reset);
+
+/* FP64 DFMA peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 entry). */
+int ad4sm_measure_fp64_peak(int32_t device, double* tflops, double* sm_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AD4SM_B200_H */
