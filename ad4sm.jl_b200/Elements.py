@@ -1,0 +1,652 @@
+"""Host-side mirror of `AD4SM.Elements` for the `makeϕrKt` path.
+
+Same names, argument meaning and error behaviour as the reference (file:line into /root/reference/src):
+  element data model   CEElem / CPElem                elements.jl:71-77, 104-111
+  constructors         Tria, Quad, QuadR, Tet04, Hex08, Hex08R            elasticelements.jl:35-96, 129-162, 197
+                       TriaP, QuadP, QuadPR, Hex08P, Hex08PR, Wdg06P, Tet04P   phasefieldelements.jl:9-145
+  hot path             makeϕrKt(elems, u)             elasticelements.jl:356-358
+                       makeϕrKt(elems, u, d)          phasefieldelements.jl:228-238
+                       makeϕrKt_d(elems, u, d[, ϕmax])  phasefieldelements.jl:239-262
+                       makeϕr(elems, u)               elements.toolkit.jl:204-215 over the loop of :216-218
+
+The constructors (model-build time, host, numpy) produce exactly the per-element data the reference
+stores -- physical shape-function gradients ∇N[d][gp][a], weights wgt[gp] = det(J)·w, and N[gp][a]
+for CPElem -- either one element at a time (reference signature) or vectorised over a whole mesh
+(`*_batch`).  All energy/gradient/Hessian evaluation and the assembly run on the GPU through the
+C ABI (`_capi.py` -> libad4sm_b200.so); nothing here computes them on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import Materials
+from . import _capi as capi
+
+__all__ = [
+    "CEElem", "CPElem", "ElemBatch", "SparseMatrixCSC", "Plan",
+    "Tria", "Quad", "QuadR", "Tet04", "Hex08", "Hex08R",
+    "TriaP", "QuadP", "QuadPR", "Hex08P", "Hex08PR", "Wdg06P", "Tet04P",
+    "makeϕrKt", "makeϕrKt_d", "makeϕr", "make_phi_r_Kt", "make_phi_r_Kt_d", "make_phi_r",
+]
+
+GP2 = ((-0.577350269189626, 1.0), (0.577350269189626, 1.0))  # elasticelements.jl:52-53,131 (truncated √3/3)
+GP1 = ((0.0, 1.0),)
+
+
+# ------------------------------------------------------------------------------------------------
+# data model
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ElemBatch:
+    """Structure-of-arrays packing of a homogeneous `Vector{CEElem}` / `Vector{CPElem}`: one element
+    type (kind, D, P, N) and one material.  Layouts follow the reference's nesting order."""
+    kind: str  # "CE" | "CP"
+    D: int
+    nodes: np.ndarray  # [ne][N] int64, 1-based
+    gradN: np.ndarray  # [ne][D][P][N]
+    wgt: np.ndarray  # [ne][P]
+    mat: object
+    Nval: np.ndarray | None = None  # [ne][P][N]  (CP)
+    V: np.ndarray | None = None  # [ne]
+    orig_index: np.ndarray | None = None  # [ne] position in `elems` (summation order); None = in order
+
+    def __post_init__(self):
+        self.nodes = np.ascontiguousarray(self.nodes, dtype=np.int64)
+        self.gradN = np.ascontiguousarray(self.gradN, dtype=np.float64)
+        self.wgt = np.ascontiguousarray(self.wgt, dtype=np.float64)
+        if self.Nval is not None:
+            self.Nval = np.ascontiguousarray(self.Nval, dtype=np.float64)
+        ne, N = self.nodes.shape
+        assert self.gradN.shape[0] == ne and self.gradN.shape[1] == self.D and self.gradN.shape[3] == N
+        assert self.wgt.shape == (ne, self.gradN.shape[2])
+
+    @property
+    def ne(self):
+        return self.nodes.shape[0]
+
+    @property
+    def N(self):
+        return self.nodes.shape[1]
+
+    @property
+    def P(self):
+        return self.wgt.shape[1]
+
+    def __len__(self):
+        return self.ne
+
+    def __getitem__(self, i):
+        cls = CEElem if self.kind == "CE" else CPElem
+        kw = dict(nodes=self.nodes[i].copy(), gradN=self.gradN[i], wgt=self.wgt[i],
+                  V=float(self.V[i]) if self.V is not None else float(self.wgt[i].sum()), mat=self.mat, D=self.D)
+        if self.kind == "CP":
+            kw["N"] = self.Nval[i]
+        return cls(**kw)
+
+
+@dataclass
+class CEElem:
+    """`CEElem{D,P,M,T,N}` (elements.jl:71-77).  `gradN[d][gp][a]` is the reference's `∇N`."""
+    nodes: np.ndarray
+    gradN: np.ndarray  # [D][P][N]
+    wgt: np.ndarray  # [P]
+    V: float
+    mat: object
+    D: int = 0
+    kind = "CE"
+
+    def __post_init__(self):
+        self.nodes = np.asarray(self.nodes, dtype=np.int64)
+        self.gradN = np.asarray(self.gradN, dtype=np.float64)
+        self.wgt = np.asarray(self.wgt, dtype=np.float64)
+        self.D = self.gradN.shape[0]
+
+    @property
+    def ᐁN(self):  # noqa: N802  (∇ itself is not an identifier character in Python)
+        return self.gradN
+
+    @property
+    def P(self):
+        return self.wgt.shape[0]
+
+    @property
+    def Nn(self):
+        return self.nodes.shape[0]
+
+
+@dataclass
+class CPElem(CEElem):
+    """`CPElem{D,P,M,T,N}` (elements.jl:104-111): adds the shape-function values `N[gp][a]`."""
+    N: np.ndarray = None  # [P][N]
+    kind = "CP"
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.N = np.asarray(self.N, dtype=np.float64)
+
+
+@dataclass
+class SparseMatrixCSC:
+    """Julia's `SparseMatrixCSC{Float64,Int64}`: 1-based `colptr`/`rowval`, rows ascending per column."""
+    m: int
+    n: int
+    colptr: np.ndarray
+    rowval: np.ndarray
+    nzval: np.ndarray
+
+    @property
+    def nnz(self):
+        return int(self.nzval.shape[0])
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.nzval, self.rowval - 1, self.colptr - 1), shape=(self.m, self.n))
+
+
+# ------------------------------------------------------------------------------------------------
+# constructors (vectorised over elements; the per-element reference signatures wrap them)
+# ------------------------------------------------------------------------------------------------
+def _shape_quad(xi, eta):  # elasticelements.jl:57; returns N [4], dN/dξ [2][4]
+    N = np.array([(1 - xi) * (1 - eta), (1 + xi) * (1 - eta), (1 + xi) * (1 + eta), (1 - xi) * (1 + eta)]) / 4
+    dN = np.array([[-(1 - eta), (1 - eta), (1 + eta), -(1 + eta)],
+                   [-(1 - xi), -(1 + xi), (1 + xi), (1 - xi)]]) / 4
+    return N, dN
+
+
+def _shape_hex(x, e, z):  # elasticelements.jl:134-137
+    sx = np.array([-1, 1, 1, -1, -1, 1, 1, -1.0])
+    se = np.array([-1, -1, 1, 1, -1, -1, 1, 1.0])
+    sz = np.array([-1, -1, -1, -1, 1, 1, 1, 1.0])
+    fx, fe, fz = 1 + sx * x, 1 + se * e, 1 + sz * z
+    N = fx * fe * fz / 8
+    dN = np.array([sx * fe * fz, fx * se * fz, fx * fe * sz]) / 8
+    return N, dN
+
+
+def _shape_wdg(x, e, z):  # phasefieldelements.jl:98-99
+    t = 1 - x - e
+    N = np.array([(1 - z) * t, (1 - z) * x, (1 - z) * e, (1 + z) * t, (1 + z) * x, (1 + z) * e]) / 2
+    dN = np.array([[-(1 - z), (1 - z), 0, -(1 + z), (1 + z), 0],
+                   [-(1 - z), 0, (1 - z), -(1 + z), 0, (1 + z)],
+                   [-t, -x, -e, t, x, e]]) / 2
+    return N, dN
+
+
+def _tensor_points(D, GP):
+    """Gauss points in storage order: `Nx[ii,jj(,kk)]` flattened column-major by `tuple(Nx...)`, i.e. the
+    ξ index runs fastest (elasticelements.jl:64-79, 144-161)."""
+    pts = []
+    if D == 2:
+        for (eta, we) in GP:
+            for (xi, wx) in GP:
+                pts.append(((xi, eta), wx * we))
+    else:
+        for (ze, wz) in GP:
+            for (eta, we) in GP:
+                for (xi, wx) in GP:
+                    pts.append(((xi, eta, ze), wx * we * wz))
+    return pts
+
+
+def _det(J):
+    """detJ (toolkit:33-36) over a stack of D x D matrices."""
+    if J.shape[-1] == 2:
+        return J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]
+    return (J[..., 0, 0] * (J[..., 1, 1] * J[..., 2, 2] - J[..., 1, 2] * J[..., 2, 1])
+            - J[..., 0, 1] * (J[..., 1, 0] * J[..., 2, 2] - J[..., 1, 2] * J[..., 2, 0])
+            + J[..., 0, 2] * (J[..., 1, 0] * J[..., 2, 1] - J[..., 1, 1] * J[..., 2, 0]))
+
+
+def _iso_batch(kind, D, shape, pts, conn, coords, mat, chunk=65536):
+    """Isoparametric constructor over all elements: J[j,i] = ∂x_i/∂ξ_j, ∇N = J \\ ∂N/∂ξ, wgt = det(J)·w
+    (elasticelements.jl:66-74, 148-157)."""
+    conn = np.ascontiguousarray(conn, dtype=np.int64)
+    coords = np.asarray(coords, dtype=np.float64)
+    ne, N = conn.shape
+    P = len(pts)
+    gradN = np.empty((ne, D, P, N))
+    wgt = np.empty((ne, P))
+    Nval = np.empty((ne, P, N)) if kind == "CP" else None
+    shp = [shape(*pt) for pt, _ in pts]
+    for s in range(0, ne, chunk):
+        sl = slice(s, min(ne, s + chunk))
+        X = coords[conn[sl] - 1][:, :, :D]  # [e][a][i]
+        for g, (pt, w) in enumerate(pts):
+            N0, dN = shp[g]
+            J = np.einsum("ja,eai->eji", dN, X)
+            gradN[sl, :, g, :] = np.linalg.solve(J, np.broadcast_to(dN, (J.shape[0],) + dN.shape))
+            wgt[sl, g] = _det(J) * w
+            if Nval is not None:
+                Nval[sl, g, :] = N0
+    return ElemBatch(kind, D, conn, gradN, wgt, mat, Nval, V=wgt.sum(axis=1))
+
+
+def _tria_batch(kind, conn, coords, mat):  # elasticelements.jl:38-46
+    conn = np.ascontiguousarray(conn, dtype=np.int64)
+    X = np.asarray(coords, dtype=np.float64)[conn - 1]
+    x1, x2, x3 = X[:, 0, 0], X[:, 1, 0], X[:, 2, 0]
+    y1, y2, y3 = X[:, 0, 1], X[:, 1, 1], X[:, 2, 1]
+    Delta = x1 * y2 - x2 * y1 - x1 * y3 + x3 * y1 + x2 * y3 - x3 * y2
+    Nx = np.stack([y2 - y3, y3 - y1, y1 - y2], axis=1) / Delta[:, None]
+    Ny = np.stack([x3 - x2, x1 - x3, x2 - x1], axis=1) / Delta[:, None]
+    A = np.abs(Delta) / 2
+    gradN = np.stack([Nx, Ny], axis=1)[:, :, None, :]
+    Nval = np.full((len(conn), 1, 3), 1 / 3) if kind == "CP" else None
+    return ElemBatch(kind, 2, conn, gradN, A[:, None], mat, Nval, V=A)
+
+
+def _tet_batch(kind, conn, coords, mat):  # elasticelements.jl:85-94 (wgt = V = det(A)/6, signed)
+    conn = np.ascontiguousarray(conn, dtype=np.int64)
+    X = np.asarray(coords, dtype=np.float64)[conn - 1]
+    A = np.ones((len(conn), 4, 4))
+    A[:, :, 1:4] = X[:, :, :3]
+    Cm = np.linalg.inv(A)
+    V = np.linalg.det(A) / 6
+    gradN = Cm[:, 1:4, :][:, :, None, :]
+    Nval = np.full((len(conn), 1, 4), 0.25) if kind == "CP" else None
+    return ElemBatch(kind, 3, conn, gradN, V[:, None], mat, Nval, V=V)
+
+
+_WDG_PTS = [((2 / 3, 1 / 6, 3 ** 0.5 / 3), 1 / 3), ((2 / 3, 1 / 6, -(3 ** 0.5) / 3), 1 / 3),
+            ((1 / 6, 2 / 3, 3 ** 0.5 / 3), 1 / 3), ((1 / 6, 2 / 3, -(3 ** 0.5) / 3), 1 / 3),
+            ((1 / 6, 1 / 6, 3 ** 0.5 / 3), 1 / 3), ((1 / 6, 1 / 6, -(3 ** 0.5) / 3), 1 / 3)]
+
+
+def Tria_batch(conn, coords, mat):
+    return _tria_batch("CE", conn, coords, mat)
+
+
+def TriaP_batch(conn, coords, mat):
+    return _tria_batch("CP", conn, coords, mat)
+
+
+def Quad_batch(conn, coords, mat, GP=GP2):
+    return _iso_batch("CE", 2, _shape_quad, _tensor_points(2, GP), conn, coords, mat)
+
+
+def QuadP_batch(conn, coords, mat, GP=GP2):
+    return _iso_batch("CP", 2, _shape_quad, _tensor_points(2, GP), conn, coords, mat)
+
+
+def Tet04_batch(conn, coords, mat):
+    return _tet_batch("CE", conn, coords, mat)
+
+
+def Tet04P_batch(conn, coords, mat):
+    return _tet_batch("CP", conn, coords, mat)
+
+
+def Hex08_batch(conn, coords, mat, GP=GP2):
+    return _iso_batch("CE", 3, _shape_hex, _tensor_points(3, GP), conn, coords, mat)
+
+
+def Hex08P_batch(conn, coords, mat, GP=GP2):
+    return _iso_batch("CP", 3, _shape_hex, _tensor_points(3, GP), conn, coords, mat)
+
+
+def Wdg06P_batch(conn, coords, mat):
+    return _iso_batch("CP", 3, _shape_wdg, _WDG_PTS, conn, coords, mat)
+
+
+def _single(batch_ctor, nodes, p0, **kw):
+    nodes = np.asarray(nodes, dtype=np.int64)
+    p0 = np.asarray(p0, dtype=np.float64)
+    b = batch_ctor(np.arange(1, len(nodes) + 1)[None, :], p0, **kw)
+    el = b[0]
+    el.nodes = nodes
+    return el
+
+
+def _default_mat(mat):
+    return Materials.Hooke(1.0, 0.3) if mat is None else mat
+
+
+# reference signatures: Ctor(nodes, p0; mat=..., GP=...)
+def Tria(nodes, p0, mat=None):
+    return _single(Tria_batch, nodes, p0, mat=_default_mat(mat))
+
+
+def Quad(nodes, p0, GP=GP2, mat=None):
+    return _single(Quad_batch, nodes, p0, mat=_default_mat(mat), GP=GP)
+
+
+def QuadR(nodes, p0, mat=None):
+    return Quad(nodes, p0, GP=GP1, mat=mat)
+
+
+def Tet04(nodes, p0, mat=None):
+    return _single(Tet04_batch, nodes, p0, mat=_default_mat(mat))
+
+
+def Hex08(nodes, p0, GP=GP2, mat=None):
+    return _single(Hex08_batch, nodes, p0, mat=_default_mat(mat), GP=GP)
+
+
+def Hex08R(nodes, p0, mat=None):
+    return Hex08(nodes, p0, GP=GP1, mat=mat)
+
+
+def TriaP(nodes, p0, mat=None):
+    return _single(TriaP_batch, nodes, p0, mat=_default_mat(mat))
+
+
+def QuadP(nodes, p0, GP=GP2, mat=None):
+    return _single(QuadP_batch, nodes, p0, mat=_default_mat(mat), GP=GP)
+
+
+def QuadPR(nodes, p0, mat=None):
+    return QuadP(nodes, p0, GP=GP1, mat=mat)
+
+
+def Hex08P(nodes, p0, GP=GP2, mat=None):
+    return _single(Hex08P_batch, nodes, p0, mat=_default_mat(mat), GP=GP)
+
+
+def Hex08PR(nodes, p0, mat=None):
+    return Hex08P(nodes, p0, GP=GP1, mat=mat)
+
+
+def Wdg06P(nodes, p0, mat=None):
+    return _single(Wdg06P_batch, nodes, p0, mat=_default_mat(mat))
+
+
+def Tet04P(nodes, p0, mat=None):
+    return _single(Tet04P_batch, nodes, p0, mat=_default_mat(mat))
+
+
+# ------------------------------------------------------------------------------------------------
+# packing `elems` -> batches
+# ------------------------------------------------------------------------------------------------
+def material_descriptor(mat, pf_grad_term="reference", nh2d_extension=False):
+    """(mat_kind, mat_base, mat_flags, params[8]) of include/ad4sm_b200.h from a Materials object."""
+    p = np.zeros(8)
+
+    def elastic(m):
+        q = np.zeros(4)
+        f = 0
+        if isinstance(m, Materials.Hooke):
+            k, q[:2] = capi.MAT_HOOKE, (m.E, m.nu)
+            f |= capi.F_SMALL if m.small else 0
+        elif isinstance(m, Materials.Hooke2D):
+            k, q[:2] = capi.MAT_HOOKE2D, (m.E, m.nu)
+            f |= (capi.F_SMALL if m.small else 0) | (capi.F_PLANE_STRESS if m.plane_stress else 0)
+        elif isinstance(m, Materials.NeoHooke):
+            k, q[:2] = capi.MAT_NEOHOOKE, (m.C1, m.K)
+        elif isinstance(m, Materials.MooneyRivlin):
+            k, q[:3] = capi.MAT_MOONEYRIVLIN, (m.C1, m.C2, m.K)
+        elif isinstance(m, Materials.Ogden):
+            k, q[:3] = capi.MAT_OGDEN, (m.alpha, m.mu, m.K)
+        else:
+            raise TypeError(f"MethodError: no method matching getϕ(F, ::{type(m).__name__})")
+        return k, q, f
+
+    if isinstance(mat, Materials.PhaseField):
+        base, q, f = elastic(mat.mat)
+        p[:4] = q
+        p[4:7] = (mat.l0, mat.Gc, mat.n)
+        f |= capi.F_DHN if mat.AT == "DHn" else 0
+        if pf_grad_term == "intended":
+            f |= capi.F_PF_GRAD_INTENDED
+        elif pf_grad_term != "reference":
+            raise ValueError("pf_grad_term must be 'reference' or 'intended'")
+        if nh2d_extension:
+            f |= capi.F_NH2D_EXT
+        return capi.MAT_PHASEFIELD, base, f, p
+    kind, q, f = elastic(mat)
+    p[:4] = q
+    return kind, 0, f, p
+
+
+def as_batches(elems):
+    """`elems` (a list of CEElem/CPElem, an ElemBatch, or a list of ElemBatch) -> list[ElemBatch].
+    Element objects are grouped by (kind, D, P, N, material); `orig_index` keeps the position in `elems`
+    so the assembly sums duplicates in `elems` order like the reference."""
+    if isinstance(elems, ElemBatch):
+        return [elems]
+    if len(elems) == 0:
+        raise AssertionError("makeϕrKt: `elems` is empty")  # elasticelements.jl:210
+    if all(isinstance(e, ElemBatch) for e in elems):
+        return list(elems)
+    groups = {}
+    for i, e in enumerate(elems):
+        if not isinstance(e, CEElem):
+            raise TypeError(f"MethodError: makeϕrKt does not accept {type(e).__name__}")
+        key = (e.kind, e.D, e.P, e.Nn, id(e.mat) if not getattr(e.mat, "__hash__", None) else e.mat)
+        groups.setdefault(key, []).append(i)
+    out = []
+    single = len(groups) == 1
+    for (kind, D, P, N, _), idx in groups.items():
+        es = [elems[i] for i in idx]
+        out.append(ElemBatch(kind, D, np.stack([e.nodes for e in es]), np.stack([e.gradN for e in es]),
+                             np.stack([e.wgt for e in es]), es[0].mat,
+                             np.stack([e.N for e in es]) if kind == "CP" else None,
+                             V=np.array([e.V for e in es]),
+                             orig_index=None if single else np.asarray(idx, dtype=np.int64)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# plan = device-resident copy of `elems` + pattern + scatter maps
+# ------------------------------------------------------------------------------------------------
+class Plan:
+    """Built once per (`elems`, size(u)); evaluates makeϕrKt / makeϕrKt_d many times (Newton loop)."""
+
+    def __init__(self, elems, n_nodes, dofs_per_node, device=-1, pf_grad_term="reference", nh2d_extension=False):
+        self.batches = as_batches(elems)
+        self.n_nodes = int(n_nodes)
+        self.dpn = int(dofs_per_node)
+        L = capi.lib()
+        arr = (capi.Batch * len(self.batches))()
+        self._keep = []
+        for i, b in enumerate(self.batches):
+            kind, base, flags, params = material_descriptor(b.mat, pf_grad_term, nh2d_extension)
+            s = arr[i]
+            s.elem_kind = capi.ELEM_CE if b.kind == "CE" else capi.ELEM_CP
+            s.dim, s.n_gauss, s.n_elem_nodes = b.D, b.P, b.N
+            s.mat_kind, s.mat_base, s.mat_flags = kind, base, flags
+            for k in range(8):
+                s.mat_params[k] = params[k]
+            s.n_elems = b.ne
+            s.nodes = b.nodes.ctypes.data
+            s.gradN = b.gradN.ctypes.data
+            s.wgt = b.wgt.ctypes.data
+            s.Nval = b.Nval.ctypes.data if b.Nval is not None else None
+            if b.orig_index is not None:
+                oi = np.ascontiguousarray(b.orig_index, dtype=np.int64)
+                self._keep.append(oi)
+                s.orig_index = oi.ctypes.data
+            else:
+                s.orig_index = None
+        h = C.c_void_p()
+        capi.check(L.ad4sm_plan_create(arr, len(self.batches), self.n_nodes, self.dpn, device, C.byref(h)))
+        self._h = h
+        self._L = L
+        self._fin = weakref.finalize(self, L.ad4sm_plan_destroy, h)
+        self.has_cp = any(b.kind == "CP" for b in self.batches)
+        self.ne = sum(b.ne for b in self.batches)
+
+    def close(self):
+        self._fin()
+
+    # -- pattern ---------------------------------------------------------------------------------
+    def pattern_size(self, field=capi.FIELD_U):
+        n, z = C.c_int64(), C.c_int64()
+        capi.check(self._L.ad4sm_plan_pattern_size(self._h, field, C.byref(n), C.byref(z)))
+        return n.value, z.value
+
+    def pattern(self, field=capi.FIELD_U):
+        n, z = self.pattern_size(field)
+        colptr = np.empty(n + 1, dtype=np.int64)
+        rowval = np.empty(z, dtype=np.int64)
+        capi.check(self._L.ad4sm_plan_pattern(self._h, field, colptr.ctypes.data, rowval.ctypes.data))
+        return colptr, rowval
+
+    # -- host API (reference-facing) --------------------------------------------------------------
+    def _u(self, u):
+        u = np.asarray(u, dtype=np.float64)
+        if u.ndim != 2 or u.shape != (self.dpn, self.n_nodes):
+            raise ValueError(f"DimensionMismatch: u must be {self.dpn}x{self.n_nodes}, got {u.shape}")
+        return np.asfortranarray(u)
+
+    def _d(self, d):
+        d = np.ascontiguousarray(np.asarray(d, dtype=np.float64).reshape(-1))
+        if d.size != self.n_nodes:
+            raise ValueError(f"DimensionMismatch: d must have {self.n_nodes} entries")
+        return d
+
+    def _fetch(self, n_dof, nnz):
+        colptr = np.empty(n_dof + 1, dtype=np.int64)
+        rowval = np.empty(nnz, dtype=np.int64)
+        nzval = np.empty(nnz, dtype=np.float64)
+        capi.check(self._L.ad4sm_fetch_csc(self._h, colptr.ctypes.data, rowval.ctypes.data, nzval.ctypes.data))
+        return SparseMatrixCSC(n_dof, n_dof, colptr, rowval, nzval)
+
+    def makeϕrKt(self, u, d=None, fetch=True):
+        u = self._u(u)
+        phi, nnz = C.c_double(), C.c_int64()
+        r = np.empty(u.size)
+        if d is None:
+            capi.check(self._L.ad4sm_eval(self._h, u.ctypes.data, C.byref(phi), r.ctypes.data, C.byref(nnz)))
+        else:
+            d = self._d(d)
+            capi.check(self._L.ad4sm_eval_pf_u(self._h, u.ctypes.data, d.ctypes.data, C.byref(phi), r.ctypes.data,
+                                               C.byref(nnz)))
+        return phi.value, r, (self._fetch(u.size, nnz.value) if fetch else None)
+
+    def makeϕr(self, u):
+        u = self._u(u)
+        phi = C.c_double()
+        r = np.empty(u.size)
+        capi.check(self._L.ad4sm_eval_phi_r(self._h, u.ctypes.data, C.byref(phi), r.ctypes.data))
+        return phi.value, r
+
+    def makeϕrKt_d(self, u, d, ϕmax=None, fetch=True):
+        u = self._u(u)
+        d = self._d(d)
+        phi, nnz = C.c_double(), C.c_int64()
+        r = np.empty(self.n_nodes)
+        hp = None
+        hist = None
+        if ϕmax is not None:
+            hist = self._split_hist(ϕmax)
+            hp = (C.c_void_p * len(hist))(*[h.ctypes.data for h in hist])
+        capi.check(self._L.ad4sm_eval_pf_d(self._h, u.ctypes.data, d.ctypes.data, hp, C.byref(phi), r.ctypes.data,
+                                           C.byref(nnz)))
+        if ϕmax is not None:
+            self._merge_hist(ϕmax, hist)
+        return phi.value, r, (self._fetch(self.n_nodes, nnz.value) if fetch else None)
+
+    def _split_hist(self, hmax):
+        """ϕmax[e][gp] = (ϕmax⁺, ϕmax⁻): one contiguous [ne_b][P][2] array per batch (views when possible)."""
+        if len(self.batches) == 1 and self.batches[0].orig_index is None:
+            b = self.batches[0]
+            if not (isinstance(hmax, np.ndarray) and hmax.dtype == np.float64 and hmax.flags.c_contiguous
+                    and hmax.shape == (b.ne, b.P, 2)):
+                raise ValueError(f"ϕmax must be a C-contiguous float64 array of shape ({b.ne}, {b.P}, 2)")
+            return [hmax]
+        out = []
+        off = 0
+        for b in self.batches:
+            idx = b.orig_index if b.orig_index is not None else np.arange(off, off + b.ne)
+            out.append(np.ascontiguousarray(np.stack([np.asarray(hmax[i], dtype=np.float64).reshape(b.P, 2) for i in idx])))
+            off += b.ne
+        return out
+
+    def _merge_hist(self, hmax, hist):
+        if len(hist) == 1 and hist[0] is hmax:
+            return
+        off = 0
+        for b, h in zip(self.batches, hist):
+            idx = b.orig_index if b.orig_index is not None else np.arange(off, off + b.ne)
+            for k, i in enumerate(idx):
+                hmax[i][...] = h[k]
+            off += b.ne
+
+    # -- device-resident API (bench / GPU-side callers) ------------------------------------------
+    def set_stream(self, cuda_stream):
+        capi.check(self._L.ad4sm_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def eval_device(self, mode, u_ptr, d_ptr=None, hist_ptr=None):
+        capi.check(self._L.ad4sm_eval_device(self._h, mode, C.c_void_p(u_ptr), C.c_void_p(d_ptr) if d_ptr else None,
+                                             C.c_void_p(hist_ptr) if hist_ptr else None))
+
+    def sync(self):
+        capi.check(self._L.ad4sm_sync(self._h))
+
+    def device_view(self, field=capi.FIELD_U):
+        v = capi.DeviceView()
+        capi.check(self._L.ad4sm_device_view_get(self._h, field, C.byref(v)))
+        return v
+
+    def fetch_csc(self, field=capi.FIELD_U):
+        n, z = self.pattern_size(field)
+        # nnz after dropzeros is only known to the library: over-allocate to the structural size
+        colptr = np.empty(n + 1, dtype=np.int64)
+        rowval = np.empty(z, dtype=np.int64)
+        nzval = np.empty(z, dtype=np.float64)
+        capi.check(self._L.ad4sm_fetch_csc(self._h, colptr.ctypes.data, rowval.ctypes.data, nzval.ctypes.data))
+        k = int(colptr[-1] - 1)
+        return SparseMatrixCSC(n, n, colptr, rowval[:k], nzval[:k])
+
+    def profile_enable(self, on=True):
+        capi.check(self._L.ad4sm_profile_enable(self._h, int(on)))
+
+    def profile_read(self, reset=True):
+        ms = (C.c_double * capi.PROF_NCLASS)()
+        n = (C.c_int64 * capi.PROF_NCLASS)()
+        capi.check(self._L.ad4sm_profile_read(self._h, ms, n, int(reset)))
+        return list(ms), list(n)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-named entry points
+# ------------------------------------------------------------------------------------------------
+_plans: dict = {}
+
+
+def _plan_for(elems, u, **opts):
+    """Plan cache keyed on the identity of `elems` (like the Julia wrapper's `objectid(elems)`)."""
+    u = np.asarray(u)
+    if u.ndim != 2:
+        raise ValueError("u must be a D x nNodes matrix")
+    key = (id(elems), u.shape, tuple(sorted(opts.items())))
+    hit = _plans.get(key)
+    if hit is not None and hit[0]() is elems:
+        return hit[1]
+    plan = Plan(elems, u.shape[1], u.shape[0], **opts)
+    try:
+        ref = weakref.ref(elems, lambda _r, k=key: _plans.pop(k, None))
+    except TypeError:  # plain lists cannot be weakly referenced: keep at most a few plans alive
+        holder = elems
+        ref = lambda h=holder: h  # noqa: E731
+        while len(_plans) >= 4:
+            _plans.pop(next(iter(_plans)))
+    _plans[key] = (ref, plan)
+    return plan
+
+
+def makeϕrKt(elems, u, d=None, **opts):
+    """`makeϕrKt(elems, u)` -> (ϕ, r, Kt)  and  `makeϕrKt(elems, u, d)` (phase-field u-phase)."""
+    return _plan_for(elems, u, **opts).makeϕrKt(u, d)
+
+
+def makeϕrKt_d(elems, u, d, ϕmax=None, **opts):
+    """`makeϕrKt_d(elems, u, d)` / `makeϕrKt_d(elems, u, d, ϕmax)`: ϕmax is updated in place."""
+    return _plan_for(elems, u, **opts).makeϕrKt_d(u, d, ϕmax)
+
+
+def makeϕr(elems, u, **opts):
+    return _plan_for(elems, u, **opts).makeϕr(u)
+
+
+make_phi_r_Kt = makeϕrKt
+make_phi_r_Kt_d = makeϕrKt_d
+make_phi_r = makeϕr

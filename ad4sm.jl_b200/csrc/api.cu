@@ -1,0 +1,744 @@
+// api.cu -- C ABI of libad4sm_b200.so (include/ad4sm_b200.h): plan construction (SoA upload, structural
+// pattern, element -> block source maps) and the evaluation entry points that replace the reference's
+//   makeϕrKt(elems, u)            /root/reference/src/elasticelements.jl:356-358  (-> _assemble_ϕrKt :208-221)
+//   makeϕrKt(Φ, elems, u)         /root/reference/src/elements.toolkit.jl:169-203
+//   makeϕr                        /root/reference/src/elements.toolkit.jl:204-215
+//   makeϕrKt(elems, u, d)         /root/reference/src/phasefieldelements.jl:228-238
+//   makeϕrKt_d(elems, u, d[,ϕmax])/root/reference/src/phasefieldelements.jl:239-262
+// There is no CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ad4sm_b200.h"
+#include "element.cuh"
+#include "internal.h"
+
+using namespace ad4sm;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(e_ == cudaErrorMemoryAllocation ? AD4SM_ENOMEM : AD4SM_ENODEV,                     \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                               \
+  } while (0)
+
+namespace {
+
+struct BatchPlan {
+  K1Args k;            // device pointers + shape (u/dfield/hist/want_K are filled per evaluation)
+  long long hist_off;  // offset (in Gauss points) of the batch in the concatenated history array
+};
+
+struct FieldOut {
+  int dpn = 0;
+  long long n_dof = 0, nnz = 0;
+  double* nzval = nullptr;
+  double* r = nullptr;
+  long long* colptr = nullptr;  // structural pattern, built on first use
+  long long* rowval = nullptr;
+  bool evaluated = false, have_K = false;
+  long long n_zero = 0;  // host copy (valid after a host-API evaluation / fetch)
+  // dropzeros result of the last evaluation (built on demand)
+  long long *dz_colptr = nullptr, *dz_rowval = nullptr;
+  double* dz_nzval = nullptr;
+  long long dz_cap = 0;
+  bool dz_valid = false;
+};
+
+struct EvSet {
+  cudaEvent_t e[4];
+};
+
+}  // namespace
+
+struct ad4sm_plan {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int N = 0, D = 0, dpn = 0;
+  long long n_nodes = 0, ne = 0, n_blocks = 0, n_gp = 0;
+  bool has_cp = false;
+  std::vector<BatchPlan> batches;
+  std::vector<void*> allocs;  // every device allocation, for destroy
+  unsigned *blk_row = nullptr, *nbr_ptr = nullptr, *nbr = nullptr, *blk_ptr = nullptr, *src = nullptr, *adj_ptr = nullptr,
+           *adj = nullptr;
+  double *Ke = nullptr, *re = nullptr, *phie = nullptr, *partials = nullptr, *phi_dev = nullptr;
+  unsigned long long* n_zero_dev = nullptr;
+  double *u_dev = nullptr, *d_dev = nullptr, *hist_dev = nullptr;
+  FieldOut field[2];
+  int last_field = -1;
+  // profiling
+  bool prof = false;
+  std::vector<EvSet> ev_pool;
+  size_t ev_used = 0;
+  double prof_ms[AD4SM_PROF_NCLASS] = {0, 0, 0, 0};
+  long long prof_launches[AD4SM_PROF_NCLASS] = {0, 0, 0, 0};
+  long long pending_k1 = 0;
+};
+
+template <class T> static int dev_alloc(ad4sm_plan* p, T** ptr, size_t count) {
+  *ptr = nullptr;
+  if (count == 0) count = 1;
+  CK(cudaMalloc((void**)ptr, count * sizeof(T)));
+  p->allocs.push_back((void*)*ptr);
+  return 0;
+}
+template <class T> static int dev_upload(ad4sm_plan* p, T** ptr, const T* host, size_t count) {
+  int rc = dev_alloc(p, ptr, count);
+  if (rc) return rc;
+  if (count) CK(cudaMemcpy(*ptr, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int mat_family(const ad4sm_batch& b, int* mf, std::string* why) {
+  const int kind = b.mat_kind;
+  if (kind == AD4SM_MAT_PHASEFIELD) {
+    const int base = b.mat_base;
+    const bool dhn = b.mat_flags & AD4SM_F_DHN;
+    if (base == AD4SM_MAT_HOOKE || base == AD4SM_MAT_HOOKE2D) {
+      *mf = MF_HOOKE;
+      return 0;
+    }
+    if (base == AD4SM_MAT_NEOHOOKE && !dhn) {
+      if (b.dim == 2 && !(b.mat_flags & AD4SM_F_NH2D_EXT)) {
+        *why = "PhaseField{NeoHooke} indexes F[5..9]: BoundsError for 2x2 F in the reference "
+               "(phasefieldmaterials.jl:42-47); set AD4SM_F_NH2D_EXT for the plane-strain embedding";
+        return -1;
+      }
+      *mf = MF_PFNEO;
+      return 0;
+    }
+    *why = "PhaseField base material must be Hooke/Hooke2D (ATn, DHn) or NeoHooke (ATn): the reference's generic "
+           "methods read mat.mat.E/ν (phasefieldmaterials.jl:20-36,56-72)";
+    return -1;
+  }
+  switch (kind) {
+    case AD4SM_MAT_HOOKE:
+      if (b.dim != 3) {
+        *why = "Hooke is 3-D only (indexes E[5], E[9], elasticmaterials.jl:214-216); use Hooke2D";
+        return -1;
+      }
+      *mf = MF_HOOKE;
+      return 0;
+    case AD4SM_MAT_HOOKE2D:
+      if (b.dim != 2) {
+        *why = "Hooke2D needs a 2-D element";
+        return -1;
+      }
+      *mf = MF_HOOKE;
+      return 0;
+    case AD4SM_MAT_NEOHOOKE: *mf = MF_NEO; return 0;
+    case AD4SM_MAT_MOONEYRIVLIN: *mf = MF_MOONEY; return 0;
+    case AD4SM_MAT_OGDEN: *mf = MF_OGDEN; return 0;
+  }
+  *why = "unknown material kind";
+  return -1;
+}
+
+extern "C" {
+
+int ad4sm_abi_version(void) { return AD4SM_ABI_VERSION; }
+const char* ad4sm_last_error(void) { return g_err.c_str(); }
+
+int ad4sm_device_count(int* count) {
+  if (!count) return fail(AD4SM_EINVAL, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(AD4SM_ENODEV, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *count = n;
+  return AD4SM_OK;
+}
+
+void ad4sm_plan_destroy(ad4sm_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  for (void* a : p->allocs) cudaFree(a);
+  for (int f = 0; f < 2; f++) {
+    cudaFree(p->field[f].dz_colptr);
+    cudaFree(p->field[f].dz_rowval);
+    cudaFree(p->field[f].dz_nzval);
+  }
+  for (auto& s : p->ev_pool)
+    for (int i = 0; i < 4; i++) cudaEventDestroy(s.e[i]);
+  if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  delete p;
+}
+
+int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_nodes, int32_t dofs_per_node,
+                      int32_t device, ad4sm_plan** plan_out) {
+  if (!plan_out) return fail(AD4SM_EINVAL, "plan_out is NULL");
+  *plan_out = nullptr;
+  if (!batches || n_batches <= 0) return fail(AD4SM_EINVAL, "makeϕrKt: `elems` is empty (elasticelements.jl:210)");
+  if (n_nodes <= 0 || n_nodes >= (1ll << 31)) return fail(AD4SM_EINVAL, "n_nodes out of range");
+  const int N = batches[0].n_elem_nodes, D = batches[0].dim;
+  long long ne = 0, n_gp = 0;
+  bool has_cp = false;
+  std::vector<int> mfs(n_batches);
+  for (int b = 0; b < n_batches; b++) {
+    const ad4sm_batch& B = batches[b];
+    if (B.n_elem_nodes != N)
+      return fail(AD4SM_EINVAL, "all elements must have the same number of dofs (elasticelements.jl:212-214)");
+    if (B.dim != D) return fail(AD4SM_EINVAL, "all batches must have the same dimension D");
+    if (B.n_elems < 0 || (B.n_elems > 0 && (!B.nodes || !B.gradN || !B.wgt)))
+      return fail(AD4SM_EINVAL, "batch arrays missing");
+    if (B.elem_kind == AD4SM_ELEM_CP && B.n_elems > 0 && !B.Nval) return fail(AD4SM_EINVAL, "CPElem batch needs Nval");
+    if (B.elem_kind != AD4SM_ELEM_CE && B.elem_kind != AD4SM_ELEM_CP) return fail(AD4SM_EINVAL, "unknown elem_kind");
+    std::string why;
+    if (mat_family(B, &mfs[b], &why)) return fail(AD4SM_EINVAL, why);
+    const char* r = k1_unsupported_reason(B.dim, B.n_elem_nodes, B.n_gauss, mfs[b], 0);
+    if (r) return fail(AD4SM_EINVAL, r);
+    has_cp |= (B.elem_kind == AD4SM_ELEM_CP);
+    ne += B.n_elems;
+    n_gp += B.n_elems * B.n_gauss;
+  }
+  if (ne == 0) return fail(AD4SM_EINVAL, "makeϕrKt: `elems` is empty (elasticelements.jl:210)");
+  if (dofs_per_node < D) return fail(AD4SM_EINVAL, "size(u,1) must be >= element dimension (getF reads rows 1:D, toolkit:13)");
+  const int NPB = n_pair_blocks(N);
+  if ((double)ne * N * N >= 4.0e9 || (double)ne * NPB * 2 >= 4.0e9)
+    return fail(AD4SM_EINVAL, "too many elements for 32-bit source maps on one device; partition the mesh");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(AD4SM_ENODEV, "no CUDA device: libad4sm_b200 has no CPU fallback");
+  int dev = device;
+  if (dev < 0) CK(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(AD4SM_EINVAL, "device ordinal out of range");
+  CK(cudaSetDevice(dev));
+
+  // ---- host-side maps ---------------------------------------------------------------------------
+  // slots: position in the concatenation of the batches; `key`: position in `elems` (summation order)
+  std::vector<int> nodes0((size_t)ne * N);
+  std::vector<long long> key(ne);
+  bool keyed = false;
+  {
+    long long s = 0;
+    for (int b = 0; b < n_batches; b++) {
+      const ad4sm_batch& B = batches[b];
+      for (long long e = 0; e < B.n_elems; e++, s++) {
+        for (int a = 0; a < N; a++) {
+          const long long nd = B.nodes[e * N + a];
+          if (nd < 1 || nd > n_nodes) return fail(AD4SM_EINVAL, "node id out of range 1..n_nodes");
+          nodes0[s * N + a] = (int)(nd - 1);
+        }
+        key[s] = B.orig_index ? B.orig_index[e] : s;
+        keyed |= (B.orig_index != nullptr);
+      }
+    }
+  }
+  std::vector<unsigned> order(ne);  // slots in summation order
+  for (long long s = 0; s < ne; s++) order[s] = (unsigned)s;
+  if (keyed) std::stable_sort(order.begin(), order.end(), [&](unsigned x, unsigned y) { return key[x] < key[y]; });
+
+  // node -> (slot, local node) adjacency, lists in summation order
+  std::vector<unsigned> adj_ptr(n_nodes + 1, 0), adj((size_t)ne * N);
+  for (size_t i = 0; i < nodes0.size(); i++) adj_ptr[nodes0[i] + 1]++;
+  for (long long i = 0; i < n_nodes; i++) adj_ptr[i + 1] += adj_ptr[i];
+  {
+    std::vector<unsigned> cur(adj_ptr.begin(), adj_ptr.end() - 1);
+    for (long long o = 0; o < ne; o++) {
+      const unsigned s = order[o];
+      for (int a = 0; a < N; a++) adj[cur[nodes0[(size_t)s * N + a]]++] = s * (unsigned)N + a;
+    }
+  }
+  // neighbour lists (sorted, unique) = block columns of each row node
+  std::vector<unsigned> nbr_ptr(n_nodes + 1, 0);
+#pragma omp parallel
+  {
+    std::vector<int> tmp;
+#pragma omp for schedule(static)
+    for (long long i = 0; i < n_nodes; i++) {
+      tmp.clear();
+      for (unsigned s = adj_ptr[i]; s < adj_ptr[i + 1]; s++) {
+        const unsigned slot = adj[s] / N;
+        for (int b = 0; b < N; b++) tmp.push_back(nodes0[(size_t)slot * N + b]);
+      }
+      std::sort(tmp.begin(), tmp.end());
+      nbr_ptr[i + 1] = (unsigned)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+    }
+  }
+  {
+    unsigned long long tot = 0;
+    for (long long i = 0; i < n_nodes; i++) {
+      tot += nbr_ptr[i + 1];
+      if (tot >= 0xffffffffull) return fail(AD4SM_EINVAL, "too many node-pair blocks for one device; partition the mesh");
+      nbr_ptr[i + 1] = (unsigned)tot;
+    }
+  }
+  const long long n_blocks = nbr_ptr[n_nodes];
+  std::vector<unsigned> nbr(n_blocks), blk_row(n_blocks), blk_ptr(n_blocks + 1, 0);
+#pragma omp parallel
+  {
+    std::vector<int> tmp;
+#pragma omp for schedule(static)
+    for (long long i = 0; i < n_nodes; i++) {
+      tmp.clear();
+      for (unsigned s = adj_ptr[i]; s < adj_ptr[i + 1]; s++) {
+        const unsigned slot = adj[s] / N;
+        for (int b = 0; b < N; b++) tmp.push_back(nodes0[(size_t)slot * N + b]);
+      }
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      const unsigned b0 = nbr_ptr[i];
+      for (size_t p = 0; p < tmp.size(); p++) {
+        nbr[b0 + p] = (unsigned)tmp[p];
+        blk_row[b0 + p] = (unsigned)i;
+      }
+      // source counts per block
+      for (unsigned s = adj_ptr[i]; s < adj_ptr[i + 1]; s++) {
+        const unsigned slot = adj[s] / N;
+        for (int b = 0; b < N; b++) {
+          const int nb = nodes0[(size_t)slot * N + b];
+          const size_t p = std::lower_bound(tmp.begin(), tmp.end(), nb) - tmp.begin();
+          blk_ptr[b0 + p + 1]++;
+        }
+      }
+    }
+  }
+  for (long long k = 0; k < n_blocks; k++) blk_ptr[k + 1] += blk_ptr[k];
+  std::vector<unsigned> src((size_t)ne * N * N);
+#pragma omp parallel
+  {
+    std::vector<unsigned> cur;
+#pragma omp for schedule(static)
+    for (long long i = 0; i < n_nodes; i++) {
+      const unsigned b0 = nbr_ptr[i], nn = nbr_ptr[i + 1] - b0;
+      cur.assign(nn, 0);
+      const unsigned* nb_i = nbr.data() + b0;
+      for (unsigned s = adj_ptr[i]; s < adj_ptr[i + 1]; s++) {
+        const unsigned slot = adj[s] / N, a = adj[s] % N;
+        for (int b = 0; b < N; b++) {
+          const unsigned nb = (unsigned)nodes0[(size_t)slot * N + b];
+          const size_t p = std::lower_bound(nb_i, nb_i + nn, nb) - nb_i;
+          int idx, tr;
+          pair_slot(N, (int)a, b, idx, tr);
+          src[blk_ptr[b0 + p] + cur[p]++] = ((slot * (unsigned)NPB + (unsigned)idx) << 1) | (unsigned)tr;
+        }
+      }
+    }
+  }
+
+  // ---- device side ------------------------------------------------------------------------------
+  ad4sm_plan* p = new ad4sm_plan;
+  p->device = dev;
+  p->N = N;
+  p->D = D;
+  p->dpn = dofs_per_node;
+  p->n_nodes = n_nodes;
+  p->ne = ne;
+  p->n_blocks = n_blocks;
+  p->n_gp = n_gp;
+  p->has_cp = has_cp;
+  int rc = 0;
+#define TRY(x)                   \
+  do {                           \
+    rc = (x);                    \
+    if (rc) {                    \
+      ad4sm_plan_destroy(p);     \
+      return rc;                 \
+    }                            \
+  } while (0)
+  {
+    cudaError_t e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete p;
+      return fail(AD4SM_ENODEV, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    p->stream = p->own_stream;
+  }
+  TRY(dev_upload(p, &p->blk_row, blk_row.data(), blk_row.size()));
+  TRY(dev_upload(p, &p->nbr_ptr, nbr_ptr.data(), nbr_ptr.size()));
+  TRY(dev_upload(p, &p->nbr, nbr.data(), nbr.size()));
+  TRY(dev_upload(p, &p->blk_ptr, blk_ptr.data(), blk_ptr.size()));
+  TRY(dev_upload(p, &p->src, src.data(), src.size()));
+  TRY(dev_upload(p, &p->adj_ptr, adj_ptr.data(), adj_ptr.size()));
+  TRY(dev_upload(p, &p->adj, adj.data(), adj.size()));
+  {
+    long long s0 = 0, h0 = 0;
+    for (int b = 0; b < n_batches; b++) {
+      const ad4sm_batch& B = batches[b];
+      BatchPlan bp;
+      memset(&bp, 0, sizeof(bp));
+      bp.k.mat.kind = B.mat_kind;
+      bp.k.mat.base = B.mat_base;
+      bp.k.mat.flags = B.mat_flags;
+      for (int i = 0; i < 8; i++) bp.k.mat.p[i] = B.mat_params[i];
+      bp.k.ne = B.n_elems;
+      bp.k.slot0 = s0;
+      bp.k.D = D;
+      bp.k.N = N;
+      bp.k.P = B.n_gauss;
+      bp.k.mf = mfs[b];
+      bp.k.dpn = dofs_per_node;
+      bp.hist_off = h0;
+      int* nd = nullptr;
+      TRY(dev_upload(p, &nd, nodes0.data() + (size_t)s0 * N, (size_t)B.n_elems * N));
+      bp.k.nodes = nd;
+      double* x = nullptr;
+      TRY(dev_upload(p, &x, B.gradN, (size_t)B.n_elems * D * B.n_gauss * N));
+      bp.k.gradN = x;
+      TRY(dev_upload(p, &x, B.wgt, (size_t)B.n_elems * B.n_gauss));
+      bp.k.wgt = x;
+      if (B.elem_kind == AD4SM_ELEM_CP) {
+        TRY(dev_upload(p, &x, B.Nval, (size_t)B.n_elems * B.n_gauss * N));
+        bp.k.Nval = x;
+      }
+      p->batches.push_back(bp);
+      s0 += B.n_elems;
+      h0 += B.n_elems * B.n_gauss;
+    }
+  }
+  TRY(dev_alloc(p, &p->Ke, (size_t)ne * NPB * D * D));
+  TRY(dev_alloc(p, &p->re, (size_t)ne * N * D));
+  TRY(dev_alloc(p, &p->phie, (size_t)ne));
+  TRY(dev_alloc(p, &p->partials, (size_t)phi_reduce_partials()));
+  TRY(dev_alloc(p, &p->phi_dev, 1));
+  TRY(dev_alloc(p, &p->n_zero_dev, 1));
+  TRY(dev_alloc(p, &p->u_dev, (size_t)n_nodes * dofs_per_node));
+  FieldOut& fu = p->field[AD4SM_FIELD_U];
+  fu.dpn = dofs_per_node;
+  fu.n_dof = n_nodes * dofs_per_node;
+  fu.nnz = n_blocks * dofs_per_node * dofs_per_node;
+  TRY(dev_alloc(p, &fu.nzval, (size_t)fu.nnz));
+  TRY(dev_alloc(p, &fu.r, (size_t)fu.n_dof));
+  if (has_cp) {
+    FieldOut& fd = p->field[AD4SM_FIELD_D];
+    fd.dpn = 1;
+    fd.n_dof = n_nodes;
+    fd.nnz = n_blocks;
+    TRY(dev_alloc(p, &fd.nzval, (size_t)fd.nnz));
+    TRY(dev_alloc(p, &fd.r, (size_t)fd.n_dof));
+    TRY(dev_alloc(p, &p->d_dev, (size_t)n_nodes));
+    TRY(dev_alloc(p, &p->hist_dev, (size_t)n_gp * 2));
+  }
+#undef TRY
+  *plan_out = p;
+  return AD4SM_OK;
+}
+
+static int check_field(ad4sm_plan* p, int32_t field) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (field != AD4SM_FIELD_U && field != AD4SM_FIELD_D) return fail(AD4SM_EINVAL, "unknown field");
+  if (field == AD4SM_FIELD_D && !p->has_cp) return fail(AD4SM_EINVAL, "plan has no CPElem batch: no phase-field dofs");
+  return 0;
+}
+
+static AsmArgs asm_args(ad4sm_plan* p, int field) {
+  AsmArgs a;
+  a.n_nodes = p->n_nodes;
+  a.n_blocks = p->n_blocks;
+  a.N = p->N;
+  a.DB = field == AD4SM_FIELD_D ? 1 : p->D;
+  a.dpn = p->field[field].dpn;
+  a.blk_row = p->blk_row;
+  a.nbr_ptr = p->nbr_ptr;
+  a.nbr = p->nbr;
+  a.blk_ptr = p->blk_ptr;
+  a.src = p->src;
+  a.adj_ptr = p->adj_ptr;
+  a.adj = p->adj;
+  a.Ke = p->Ke;
+  a.re = p->re;
+  a.nzval = p->field[field].nzval;
+  a.r = p->field[field].r;
+  a.n_zero = p->n_zero_dev;
+  return a;
+}
+
+static int ensure_pattern(ad4sm_plan* p, int field) {
+  FieldOut& f = p->field[field];
+  if (f.colptr) return 0;
+  CK(cudaSetDevice(p->device));
+  int rc = dev_alloc(p, &f.colptr, (size_t)f.n_dof + 1);
+  if (rc) return rc;
+  rc = dev_alloc(p, &f.rowval, (size_t)f.nnz);
+  if (rc) return rc;
+  CK(launch_pattern(asm_args(p, field), f.colptr, f.rowval, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+
+int ad4sm_plan_pattern_size(ad4sm_plan* p, int32_t field, int64_t* n_dof, int64_t* nnz) {
+  int rc = check_field(p, field);
+  if (rc) return rc;
+  if (n_dof) *n_dof = p->field[field].n_dof;
+  if (nnz) *nnz = p->field[field].nnz;
+  return AD4SM_OK;
+}
+
+int ad4sm_plan_pattern(ad4sm_plan* p, int32_t field, int64_t* colptr, int64_t* rowval) {
+  int rc = check_field(p, field);
+  if (rc) return rc;
+  rc = ensure_pattern(p, field);
+  if (rc) return rc;
+  FieldOut& f = p->field[field];
+  if (colptr) CK(cudaMemcpy(colptr, f.colptr, sizeof(long long) * (f.n_dof + 1), cudaMemcpyDeviceToHost));
+  if (rowval) CK(cudaMemcpy(rowval, f.rowval, sizeof(long long) * f.nnz, cudaMemcpyDeviceToHost));
+  return AD4SM_OK;
+}
+
+int ad4sm_set_stream(ad4sm_plan* p, void* cuda_stream) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  CK(cudaSetDevice(p->device));
+  CK(cudaStreamSynchronize(p->stream));
+  p->stream = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
+  return AD4SM_OK;
+}
+
+static EvSet* next_events(ad4sm_plan* p) {
+  if (p->ev_used == p->ev_pool.size()) {
+    EvSet s;
+    for (int i = 0; i < 4; i++)
+      if (cudaEventCreate(&s.e[i]) != cudaSuccess) return nullptr;
+    p->ev_pool.push_back(s);
+  }
+  return &p->ev_pool[p->ev_used++];
+}
+
+static int drain_events(ad4sm_plan* p) {
+  if (p->ev_used == 0) return 0;
+  CK(cudaStreamSynchronize(p->stream));
+  for (size_t i = 0; i < p->ev_used; i++) {
+    EvSet& s = p->ev_pool[i];
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, s.e[0], s.e[1]));
+    p->prof_ms[AD4SM_PROF_ELEMENT] += ms;
+    CK(cudaEventElapsedTime(&ms, s.e[1], s.e[2]));
+    p->prof_ms[AD4SM_PROF_ASSEMBLE] += ms;
+    CK(cudaEventElapsedTime(&ms, s.e[2], s.e[3]));
+    p->prof_ms[AD4SM_PROF_REDUCE] += ms;
+  }
+  p->ev_used = 0;
+  return 0;
+}
+
+int ad4sm_eval_device(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (mode < 0 || mode > 3) return fail(AD4SM_EINVAL, "mode must be 0..3");
+  if (!u_dev) return fail(AD4SM_EINVAL, "u is NULL");
+  const bool needs_d = (mode == MODE_PF_U || mode == MODE_PF_D);
+  if (needs_d && !d_dev) return fail(AD4SM_EINVAL, "d is NULL");
+  if (needs_d && !p->has_cp) return fail(AD4SM_EINVAL, "phase-field evaluation needs CPElem batches");
+  const int field = mode == MODE_PF_D ? AD4SM_FIELD_D : AD4SM_FIELD_U;
+  const bool want_K = mode != MODE_PHI_R;
+  const int kmode = mode == MODE_PHI_R ? MODE_ELASTIC : mode;
+  for (const BatchPlan& b : p->batches) {
+    const bool is_pf = b.k.mat.kind == MAT_PHASEFIELD;
+    if (needs_d && (!is_pf || !b.k.Nval))
+      return fail(AD4SM_EINVAL, "makeϕrKt(elems,u,d) / makeϕrKt_d need CPElem with a PhaseField material");
+    if (!needs_d && is_pf)
+      return fail(AD4SM_EINVAL, "PhaseField material evaluated without d: the reference has no getϕ(F, ::PhaseField)");
+  }
+  CK(cudaSetDevice(p->device));
+  EvSet* ev = p->prof ? next_events(p) : nullptr;
+  if (ev) CK(cudaEventRecord(ev->e[0], p->stream));
+  for (const BatchPlan& b : p->batches) {
+    K1Args a = b.k;
+    a.u = u_dev;
+    a.dfield = d_dev;
+    a.hist = (mode == MODE_PF_D && hist_dev) ? hist_dev + b.hist_off * 2 : nullptr;
+    a.want_K = want_K;
+    a.Ke = p->Ke;
+    a.re = p->re;
+    a.phie = p->phie;
+    cudaError_t e = launch_k1(a, kmode, p->stream);
+    if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("K1 launch: ") + cudaGetErrorString(e));
+  }
+  if (ev) CK(cudaEventRecord(ev->e[1], p->stream));
+  CK(launch_k2(asm_args(p, field), want_K, p->stream));
+  if (ev) CK(cudaEventRecord(ev->e[2], p->stream));
+  CK(launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, p->stream));
+  if (ev) CK(cudaEventRecord(ev->e[3], p->stream));
+  if (p->prof) {
+    p->prof_launches[AD4SM_PROF_ELEMENT] += (long long)p->batches.size();
+    p->prof_launches[AD4SM_PROF_ASSEMBLE] += want_K ? 2 : 1;
+    p->prof_launches[AD4SM_PROF_REDUCE] += 2;
+  }
+  FieldOut& f = p->field[field];
+  f.evaluated = true;
+  f.have_K = want_K;
+  f.dz_valid = false;
+  f.n_zero = -1;
+  p->last_field = field;
+  return AD4SM_OK;
+}
+
+int ad4sm_sync(ad4sm_plan* p) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  CK(cudaSetDevice(p->device));
+  CK(cudaStreamSynchronize(p->stream));
+  return AD4SM_OK;
+}
+
+int ad4sm_device_view_get(ad4sm_plan* p, int32_t field, ad4sm_device_view* v) {
+  int rc = check_field(p, field);
+  if (rc) return rc;
+  if (!v) return fail(AD4SM_EINVAL, "view is NULL");
+  rc = ensure_pattern(p, field);
+  if (rc) return rc;
+  FieldOut& f = p->field[field];
+  v->n_dof = f.n_dof;
+  v->nnz = f.nnz;
+  v->phi_dev = p->phi_dev;
+  v->r_dev = f.r;
+  v->nzval_dev = f.nzval;
+  v->colptr_dev = (const int64_t*)f.colptr;
+  v->rowval_dev = (const int64_t*)f.rowval;
+  v->n_zero_dev = (const int64_t*)p->n_zero_dev;
+  return AD4SM_OK;
+}
+
+// host-pointer evaluation shared by the four reference-facing entry points
+static int eval_host(ad4sm_plan* p, int mode, const double* u, const double* d, double* const* hist, double* phi,
+                     double* r, int64_t* nnz_out) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (!u) return fail(AD4SM_EINVAL, "u is NULL");
+  CK(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  CK(cudaMemcpyAsync(p->u_dev, u, sizeof(double) * p->n_nodes * p->dpn, cudaMemcpyHostToDevice, s));
+  const bool needs_d = (mode == MODE_PF_U || mode == MODE_PF_D);
+  if (needs_d) {
+    if (!d) return fail(AD4SM_EINVAL, "d is NULL");
+    if (!p->has_cp) return fail(AD4SM_EINVAL, "phase-field evaluation needs CPElem batches");
+    CK(cudaMemcpyAsync(p->d_dev, d, sizeof(double) * p->n_nodes, cudaMemcpyHostToDevice, s));
+  }
+  if (hist)
+    for (const BatchPlan& b : p->batches) {
+      const double* h = hist[&b - p->batches.data()];
+      if (!h) return fail(AD4SM_EINVAL, "hist pointer of a batch is NULL");
+      CK(cudaMemcpyAsync(p->hist_dev + b.hist_off * 2, h, sizeof(double) * 2 * b.k.ne * b.k.P, cudaMemcpyHostToDevice, s));
+    }
+  int rc = ad4sm_eval_device(p, mode, p->u_dev, needs_d ? p->d_dev : nullptr, hist ? p->hist_dev : nullptr);
+  if (rc) return rc;
+  const int field = mode == MODE_PF_D ? AD4SM_FIELD_D : AD4SM_FIELD_U;
+  FieldOut& f = p->field[field];
+  unsigned long long nz = 0;
+  if (phi) CK(cudaMemcpyAsync(phi, p->phi_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (r) CK(cudaMemcpyAsync(r, f.r, sizeof(double) * f.n_dof, cudaMemcpyDeviceToHost, s));
+  if (mode != MODE_PHI_R) CK(cudaMemcpyAsync(&nz, p->n_zero_dev, sizeof(nz), cudaMemcpyDeviceToHost, s));
+  if (hist)
+    for (const BatchPlan& b : p->batches) {
+      double* h = hist[&b - p->batches.data()];
+      CK(cudaMemcpyAsync(h, p->hist_dev + b.hist_off * 2, sizeof(double) * 2 * b.k.ne * b.k.P, cudaMemcpyDeviceToHost, s));
+    }
+  CK(cudaStreamSynchronize(s));
+  if (mode != MODE_PHI_R) {
+    f.n_zero = (long long)nz;
+    if (nnz_out) *nnz_out = f.nnz - f.n_zero;
+  }
+  return AD4SM_OK;
+}
+
+int ad4sm_eval(ad4sm_plan* p, const double* u, double* phi, double* r, int64_t* nnz_out) {
+  return eval_host(p, MODE_ELASTIC, u, nullptr, nullptr, phi, r, nnz_out);
+}
+int ad4sm_eval_phi_r(ad4sm_plan* p, const double* u, double* phi, double* r) {
+  return eval_host(p, MODE_PHI_R, u, nullptr, nullptr, phi, r, nullptr);
+}
+int ad4sm_eval_pf_u(ad4sm_plan* p, const double* u, const double* d, double* phi, double* r, int64_t* nnz_out) {
+  return eval_host(p, MODE_PF_U, u, d, nullptr, phi, r, nnz_out);
+}
+int ad4sm_eval_pf_d(ad4sm_plan* p, const double* u, const double* d, double* const* hist, double* phi, double* r,
+                    int64_t* nnz_out) {
+  return eval_host(p, MODE_PF_D, u, d, hist, phi, r, nnz_out);
+}
+
+int ad4sm_fetch_csc(ad4sm_plan* p, int64_t* colptr, int64_t* rowval, double* nzval) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (p->last_field < 0) return fail(AD4SM_ESTATE, "fetch before any evaluation");
+  const int field = p->last_field;
+  FieldOut& f = p->field[field];
+  if (!f.have_K) return fail(AD4SM_ESTATE, "the last evaluation computed ϕ and r only");
+  int rc = ensure_pattern(p, field);
+  if (rc) return rc;
+  CK(cudaSetDevice(p->device));
+  if (f.n_zero < 0) {  // device-path evaluation: read the zero count now
+    unsigned long long nz = 0;
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaMemcpy(&nz, p->n_zero_dev, sizeof(nz), cudaMemcpyDeviceToHost));
+    f.n_zero = (long long)nz;
+  }
+  if (f.n_zero == 0) {  // nothing to drop: the structural pattern is the result
+    if (colptr) CK(cudaMemcpy(colptr, f.colptr, sizeof(long long) * (f.n_dof + 1), cudaMemcpyDeviceToHost));
+    if (rowval) CK(cudaMemcpy(rowval, f.rowval, sizeof(long long) * f.nnz, cudaMemcpyDeviceToHost));
+    if (nzval) CK(cudaMemcpy(nzval, f.nzval, sizeof(double) * f.nnz, cudaMemcpyDeviceToHost));
+    return AD4SM_OK;
+  }
+  const long long nnz_out = f.nnz - f.n_zero;
+  if (!f.dz_valid) {
+    if (!f.dz_colptr) CK(cudaMalloc((void**)&f.dz_colptr, sizeof(long long) * (f.n_dof + 1)));
+    if (f.dz_cap < nnz_out || !f.dz_rowval) {
+      cudaFree(f.dz_rowval);
+      cudaFree(f.dz_nzval);
+      f.dz_rowval = nullptr;
+      f.dz_nzval = nullptr;
+      const long long cap = std::max<long long>(nnz_out, 1);
+      CK(cudaMalloc((void**)&f.dz_rowval, sizeof(long long) * cap));
+      CK(cudaMalloc((void**)&f.dz_nzval, sizeof(double) * cap));
+      f.dz_cap = cap;
+    }
+    void* tmp = nullptr;
+    const size_t tb = dropzeros_tmp_bytes(f.n_dof);
+    CK(cudaMalloc(&tmp, tb ? tb : 1));
+    cudaError_t e = launch_dropzeros(f.n_dof, f.colptr, f.rowval, f.nzval, f.dz_colptr, f.dz_rowval, f.dz_nzval, tmp, tb,
+                                     p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(tmp);
+    CK(e);
+    f.dz_valid = true;
+  }
+  if (colptr) CK(cudaMemcpy(colptr, f.dz_colptr, sizeof(long long) * (f.n_dof + 1), cudaMemcpyDeviceToHost));
+  if (rowval) CK(cudaMemcpy(rowval, f.dz_rowval, sizeof(long long) * nnz_out, cudaMemcpyDeviceToHost));
+  if (nzval) CK(cudaMemcpy(nzval, f.dz_nzval, sizeof(double) * nnz_out, cudaMemcpyDeviceToHost));
+  return AD4SM_OK;
+}
+
+int ad4sm_profile_enable(ad4sm_plan* p, int32_t on) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  CK(cudaSetDevice(p->device));
+  int rc = drain_events(p);
+  if (rc) return rc;
+  p->prof = on != 0;
+  return AD4SM_OK;
+}
+
+int ad4sm_profile_read(ad4sm_plan* p, double ms[AD4SM_PROF_NCLASS], int64_t launches[AD4SM_PROF_NCLASS], int32_t reset) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  CK(cudaSetDevice(p->device));
+  int rc = drain_events(p);
+  if (rc) return rc;
+  for (int i = 0; i < AD4SM_PROF_NCLASS; i++) {
+    if (ms) ms[i] = p->prof_ms[i];
+    if (launches) launches[i] = p->prof_launches[i];
+    if (reset) {
+      p->prof_ms[i] = 0.0;
+      p->prof_launches[i] = 0;
+    }
+  }
+  return AD4SM_OK;
+}
+
+int ad4sm_measure_fp64_peak(int32_t device, double* tflops, double* sm_mhz_est) {
+  if (!tflops) return fail(AD4SM_EINVAL, "tflops is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(AD4SM_ENODEV, "no CUDA device");
+  if (device >= 0) CK(cudaSetDevice(device));
+  double tf = 0.0, mhz = 0.0;
+  CK(launch_fp64_peak(&tf, &mhz));
+  *tflops = tf;
+  if (sm_mhz_est) *sm_mhz_est = mhz;
+  return AD4SM_OK;
+}
+
+}  // extern "C"

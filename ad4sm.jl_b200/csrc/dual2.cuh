@@ -7,7 +7,16 @@
 // (materials.cuh, element kernels), which is the "AD over F followed by the B^T.A.B contraction"
 // form north_star allows, at a fraction of the flops of D2{9,45}.
 #pragma once
+#include <cmath>
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#define AD4SM_DI __host__ __device__ __forceinline__
+#define AD4SM_HD __host__ __device__
+#else
+// host-only compilation (tests/cxx builds these headers with g++ to check the math without a GPU)
+#define AD4SM_DI inline
+#define AD4SM_HD
+#endif
 
 namespace ad4sm {
 
@@ -18,7 +27,6 @@ template <int N> struct Dual2 {
   double h[M];
 };
 
-#define AD4SM_DI __device__ __forceinline__
 
 template <int N> AD4SM_DI Dual2<N> d2_const(double x) {
   Dual2<N> r;

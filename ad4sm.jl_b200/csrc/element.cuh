@@ -1,0 +1,300 @@
+// element.cuh -- per-element building blocks of K1 (element energy / gradient / Hessian).
+//
+// Replaces, for one element, the reference's Gauss loops
+//   getϕ(elem::C3DE, u::Array{<:D2})      /root/reference/src/elasticelements.jl:339-350
+//   _integrate_ϕ                           /root/reference/src/elasticelements.jl:199-206
+//   getϕ(elem::CPElem, u, d[, ϕmax])       /root/reference/src/phasefieldelements.jl:159-223
+//   getF / get_d_and_∇d / chain operator × /root/reference/src/elements.toolkit.jl:8-20,159-167,231-245
+// The reference differentiates with D2{3N,·} duals; here each Gauss point yields the material
+// tangent (ψ, P = ∂ψ/∂F, A = ∂²ψ/∂F∂F, materials.cuh) and the chain to the element dofs is the
+// exact two-stage contraction  K_(a,j),(b,l) = Σ_gp w Σ_k,m ∇N_a,k A_(kj)(ml) ∇N_b,m  (F is linear
+// in u, so this is what `×` computes, toolkit:231-245).
+//
+// Work split (kernels.cu): a Gauss point is evaluated by one thread ("phase 1", gauss_point*),
+// which leaves w·A, w·P, w·ψ in a GP record; then thread q of the element owns column node b = q
+// and accumulates over the Gauss points the blocks K(a,b), a = (q+o) mod N, o = 0..N/2
+// ("phase 2", column_*).  No cross-thread floating-point reduction is needed.
+//
+// Everything here is __host__ __device__ so tests/cxx can run the same code on the CPU.
+#pragma once
+#include "materials.cuh"
+
+namespace ad4sm {
+
+// ---- element block storage ("cyclic" symmetric layout) ------------------------------------------
+// An element tangent has N x N node blocks of DB x DB; only NPB = N(N+1)/2 are stored.  Block
+// (q, o) holds  M[j][l] = K_((q+o)%N, j),(q, l)  at index o*N + q;  o <= N/2, and for even N the
+// o = N/2 blocks only for q < N/2.
+AD4SM_HD constexpr int n_pair_blocks(int N) { return N * (N + 1) / 2; }
+AD4SM_HD constexpr int n_offsets(int N, int q) {  // number of o's owned by column q
+  return (N % 2) ? (N + 1) / 2 : (q < N / 2 ? N / 2 + 1 : N / 2);
+}
+// where K(a,b) (row node a, col node b) lives: index and whether to read it transposed
+AD4SM_HD inline void pair_slot(int N, int a, int b, int& idx, int& tr) {
+  const int o1 = ((a - b) % N + N) % N;
+  if (2 * o1 < N || (2 * o1 == N && b < N / 2)) {
+    idx = o1 * N + b;
+    tr = 0;
+  } else {
+    idx = (((b - a) % N + N) % N) * N + a;
+    tr = 1;
+  }
+}
+
+// ---- GP record -------------------------------------------------------------------------------------
+template <int D> struct GpRec {
+  static constexpr int DD = D * D;
+  static constexpr int NA = DD * (DD + 1) / 2;
+  static constexpr int OFF_A = 0, OFF_P = NA, OFF_PSI = NA + DD;
+  static constexpr int SIZE = NA + DD + 1;
+};
+// d-phase record: [0] w ψ'', [1] w ψ', [2] w ψ, [3] w c (c = Gc l0, "intended" gradient term, else 0), [4..4+D) ∇d
+template <int D> struct GpRecD {
+  static constexpr int SIZE = 4 + D;
+};
+
+// F[k*D+j] = δ_jk + Σ_a ∇N_a,k u_a,j   (toolkit:8-20); G[k*N+a], ue[a*D+j]
+template <int D, int N> AD4SM_DI void deformation_gradient(const double* G, const double* ue, double* F) {
+#pragma unroll
+  for (int k = 0; k < D; k++)
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < N; a++) s += G[k * N + a] * ue[a * D + j];
+      F[k * D + j] = (j == k) ? s + 1.0 : s;
+    }
+}
+
+// phase 1, u-dual paths (elastic and phase-field u-phase): writes the GP record.
+//   G [D][N] physical shape-function gradients at this Gauss point, ue [N][D] nodal displacements,
+//   de [N] nodal phase field and Nv [N] shape-function values (PF only), w = elem.wgt[gp].
+template <int D, int N, int MF, bool PF>
+AD4SM_DI void gauss_point_u(const MatDev& m, const double* G, const double* ue, const double* de, const double* Nv,
+                            double w, double* rec) {
+  using R = GpRec<D>;
+  double F[D * D];
+  deformation_gradient<D, N>(G, ue, F);
+  PfPoint pf;
+  if (PF) {  // get_d_and_∇d, toolkit:159-167
+    double dv = 0.0;
+#pragma unroll
+    for (int a = 0; a < N; a++) dv += Nv[a] * de[a];
+    double g2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < N; a++) s += G[k * N + a] * de[a];
+      g2 += s * s;
+    }
+    pf.d = dv;
+    pf.gd2 = g2;
+  }
+  Tangent<D> t;
+  material_tangent<D, MF>(m, F, PF ? &pf : nullptr, t);
+#pragma unroll
+  for (int i = 0; i < R::NA; i++) rec[R::OFF_A + i] = w * t.A[i];
+#pragma unroll
+  for (int i = 0; i < R::DD; i++) rec[R::OFF_P + i] = w * t.P[i];
+  rec[R::OFF_PSI] = w * t.psi;
+}
+
+// phase 1, d-dual path (makeϕrKt_d, phasefieldelements.jl:239-262; energies phasefieldmaterials.jl:20-135).
+// hist: nullptr or this Gauss point's (ϕmax⁺, ϕmax⁻) pair, updated in place (phasefieldelements.jl:180).
+template <int D, int N>
+AD4SM_DI void gauss_point_d(const MatDev& m, const double* G, const double* Nv, const double* ue, const double* de,
+                            double w, double* hist, double* rec) {
+  double F[D * D];
+  deformation_gradient<D, N>(G, ue, F);
+  double plus, minus;
+  bool tensile;
+  pf_energy_split<D>(m, F, hist != nullptr, plus, minus, tensile);
+  if (hist) {
+    const bool neo = (m.base == MAT_NEOHOOKE) && !(m.flags & F_DHN);
+    if (tensile) {
+      const double h = plus > hist[0] ? plus : hist[0];
+      hist[0] = h;
+      plus = h;
+    } else if (!neo) {
+      const double h = plus > hist[1] ? plus : hist[1];
+      hist[1] = h;
+      plus = h;
+    }
+  }
+  double dv = 0.0;
+#pragma unroll
+  for (int a = 0; a < N; a++) dv += Nv[a] * de[a];
+  double gd[D], g2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < N; a++) s += G[k * N + a] * de[a];
+    gd[k] = s;
+    g2 += s * s;
+  }
+  const double l0 = m.p[4], Gc = m.p[5], n = m.p[6];
+  const double c0 = Gc / (2 * l0);
+  // dⁿ and its derivatives with the reference's `^` rule (adiff.jl:138-139)
+  double pn, pn1, pn2;
+  if (n == 0.0) {
+    pn = 1.0, pn1 = 0.0, pn2 = 0.0;
+  } else if (n == 1.0) {
+    pn = dv, pn1 = 1.0, pn2 = 0.0;
+  } else if (n == 2.0) {
+    pn = dv * dv, pn1 = 2.0 * dv, pn2 = 2.0;
+  } else {
+    pn = pow(dv, n), pn1 = n * pow(dv, n - 1.0), pn2 = n * (n - 1.0) * pow(dv, n - 2.0);
+  }
+  const double omd = 1.0 - dv;
+  const double psi = omd * omd * plus + minus + c0 * (pn + l0 * l0 * g2);
+  const double s1 = -2.0 * omd * plus + c0 * pn1;
+  const double s2 = 2.0 * plus + c0 * pn2;
+  rec[0] = w * s2;
+  rec[1] = w * s1;
+  rec[2] = w * psi;
+  rec[3] = (m.flags & F_PF_GRAD_INTENDED) ? w * (2.0 * c0 * l0 * l0) : 0.0;
+#pragma unroll
+  for (int k = 0; k < D; k++) rec[4 + k] = gd[k];
+}
+
+// T[(k,j)][l] = Σ_m A_(kj)(ml) ∇N_b,m  from the packed symmetric A (81 FMAs for D = 3)
+template <int D> AD4SM_DI void tangent_times_gradient(const double* A, const double* gb, double (*T)[D]) {
+  constexpr int DD = D * D;
+#pragma unroll
+  for (int I = 0; I < DD; I++)
+#pragma unroll
+    for (int l = 0; l < D; l++) T[I][l] = 0.0;
+#pragma unroll
+  for (int J = 0; J < DD; J++)
+#pragma unroll
+    for (int I = 0; I <= J; I++) {
+      const double a = A[J * (J + 1) / 2 + I];
+      T[I][J % D] += a * gb[J / D];
+      if (I != J) T[J][I % D] += a * gb[I / D];
+    }
+}
+
+// blk[j][l] += Σ_k ∇N_a,k T[(k,j)][l]
+template <int D> AD4SM_DI void add_block(const double* ga, const double (*T)[D], double* blk) {
+#pragma unroll
+  for (int j = 0; j < D; j++)
+#pragma unroll
+    for (int l = 0; l < D; l++) {
+      double s = blk[j * D + l];
+#pragma unroll
+      for (int k = 0; k < D; k++) s += ga[k] * T[k * D + j][l];
+      blk[j * D + l] = s;
+    }
+}
+
+// phase 2 (u-dual): column node q of one element.
+//   recs: P GP records, `rstride` doubles apart;  gN: the element's ∇N, [D][P][N] (elem.∇N[k][gp][a]).
+//   Ke:   the element's block storage [NPB][D*D] (may be nullptr when only ϕ, r are wanted)
+//   re:   the element's residual [N][D].
+// PT: compile-time number of Gauss points (0 = use the run-time P), so that a register-resident
+// record (P = 1, thread-per-element path) is indexed statically.
+template <int D, int N, int PT = 0>
+AD4SM_DI void column_u(int q, int Prt, const double* recs, int rstride, const double* gN, double* Ke, double* re) {
+  using R = GpRec<D>;
+  const int P = PT ? PT : Prt;
+  constexpr int DD = D * D;
+  constexpr int NO = N / 2 + 1;  // max offsets per column
+  const int no = n_offsets(N, q);
+  double acc[NO][DD];
+  double rq[D];
+#pragma unroll
+  for (int o = 0; o < NO; o++)
+#pragma unroll
+    for (int i = 0; i < DD; i++) acc[o][i] = 0.0;
+#pragma unroll
+  for (int j = 0; j < D; j++) rq[j] = 0.0;
+  for (int gp = 0; gp < P; gp++) {
+    const double* rec = recs + (long long)gp * rstride;
+    double gb[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) gb[k] = gN[(k * P + gp) * N + q];
+    // r_(q,j) += Σ_k wP_(kj) ∇N_q,k
+#pragma unroll
+    for (int j = 0; j < D; j++)
+#pragma unroll
+      for (int k = 0; k < D; k++) rq[j] += rec[R::OFF_P + k * D + j] * gb[k];
+    if (Ke) {
+      double T[DD][D];
+      tangent_times_gradient<D>(rec + R::OFF_A, gb, T);
+#pragma unroll
+      for (int o = 0; o < NO; o++) {
+        if (o < no) {
+          int a = q + o;
+          if (a >= N) a -= N;
+          double ga[D];
+#pragma unroll
+          for (int k = 0; k < D; k++) ga[k] = gN[(k * P + gp) * N + a];
+          add_block<D>(ga, T, acc[o]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < D; j++) re[q * D + j] = rq[j];
+  if (Ke) {
+    // the diagonal node block is symmetric in exact arithmetic; mirror its upper triangle so that Kt is
+    // bitwise symmetric like the reference's (both triangles read one packed slot, adiff.jl:160)
+#pragma unroll
+    for (int j = 0; j < D; j++)
+#pragma unroll
+      for (int l = j + 1; l < D; l++) acc[0][l * D + j] = acc[0][j * D + l];
+#pragma unroll
+    for (int o = 0; o < NO; o++)
+      if (o < no) {
+#pragma unroll
+        for (int i = 0; i < DD; i++) Ke[(o * N + q) * DD + i] = acc[o][i];
+      }
+  }
+}
+
+// phase 2 (d-dual): column node q; blocks are scalars.  Nv: [P][N] shape-function values.
+template <int D, int N, int PT = 0>
+AD4SM_DI void column_d(int q, int Prt, const double* recs, int rstride, const double* gN, const double* Nv, double* Ke,
+                       double* re) {
+  constexpr int NO = N / 2 + 1;
+  const int P = PT ? PT : Prt;
+  const int no = n_offsets(N, q);
+  double acc[NO];
+#pragma unroll
+  for (int o = 0; o < NO; o++) acc[o] = 0.0;
+  double rq = 0.0;
+  for (int gp = 0; gp < P; gp++) {
+    const double* rec = recs + (long long)gp * rstride;
+    const double ws2 = rec[0], ws1 = rec[1], wc = rec[3];
+    const double nb = Nv[gp * N + q];
+    double gb[D], gdgb = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      gb[k] = gN[(k * P + gp) * N + q];
+      gdgb += rec[4 + k] * gb[k];
+    }
+    rq += ws1 * nb + wc * gdgb;
+    if (Ke) {
+#pragma unroll
+      for (int o = 0; o < NO; o++)
+        if (o < no) {
+          int a = q + o;
+          if (a >= N) a -= N;
+          double gg = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; k++) gg += gN[(k * P + gp) * N + a] * gb[k];
+          acc[o] += ws2 * (Nv[gp * N + a] * nb) + wc * gg;
+        }
+    }
+  }
+  re[q] = rq;
+  if (Ke) {
+#pragma unroll
+    for (int o = 0; o < NO; o++)
+      if (o < no) Ke[o * N + q] = acc[o];
+  }
+}
+
+}  // namespace ad4sm

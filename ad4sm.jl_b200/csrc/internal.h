@@ -1,4 +1,4 @@
-// internal.h -- shared declarations between the kernel translation units and the C-ABI layer.
+// internal.h -- shared declarations between the kernel translation unit (kernels.cu) and the C-ABI layer (api.cu).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -7,53 +7,59 @@
 
 namespace ad4sm {
 
-// device view of one batch (SoA copy of a Vector{CEElem}/Vector{CPElem}, elements.jl:71-111)
-struct BatchDev {
-  int kind, D, P, N;
-  int mf;  // MatFamily
-  int pad;
-  MatDev mat;
-  long long ne;
-  long long s0;          // first staging slot of this batch
-  const int* nodes;      // [ne][N] 0-based
-  const double* gradN;   // [ne][D][P][N]
-  const double* wgt;     // [ne][P]
-  const double* Nval;    // [ne][P][N] or nullptr
-};
-
 enum EvalMode { MODE_ELASTIC = 0, MODE_PF_U = 1, MODE_PF_D = 2, MODE_PHI_R = 3 };
 
-// staging written by K1, consumed by K2
-struct Staging {
-  double* Ke;    // [slots][N][N][DB][DB]   full element tangent, block-row major
-  double* re;    // [slots][N][DB]
-  double* phie;  // [slots]
+// One K1 launch = one batch (SoA copy of a Vector{CEElem}/Vector{CPElem}, elements.jl:71-111).
+struct K1Args {
+  MatDev mat;
+  long long ne;         // elements in the batch
+  long long slot0;      // first staging slot of the batch
+  int D, N, P;          // element dimension, nodes, Gauss points
+  int mf;               // MatFamily
+  int dpn;              // rows of u (dofs per node of the displacement field)
+  int want_K;           // 0: ϕ and r only (makeϕr)
+  const int* nodes;     // [ne][N] 0-based
+  const double* gradN;  // [ne][D][P][N]
+  const double* wgt;    // [ne][P]
+  const double* Nval;   // [ne][P][N] or nullptr
+  const double* u;      // [n_nodes][dpn]
+  const double* dfield; // [n_nodes] or nullptr
+  double* hist;         // [ne][P][2] (this batch) or nullptr
+  // staging written by K1, consumed by K2/K3
+  double* Ke;           // [slots][NPB][DB*DB]  cyclic symmetric block storage (element.cuh)
+  double* re;           // [slots][N][DB]
+  double* phie;         // [slots]
 };
 
-// assembly maps (built once per plan)
-struct AsmMaps {
-  long long n_nodes;
-  int N;                       // nodes per element
-  int max_nbr;                 // max neighbours of a node (incl. itself)
-  const long long* adj_ptr;    // [n_nodes+1]
-  const unsigned* adj;         // [n_adj]  slot*N + local node, in `elems` order per node
-  const unsigned short* pos;   // [n_adj][N] position of each element node in the row node's neighbour list
-  const long long* nbr_ptr;    // [n_nodes+1]
-  const int* nbr;              // [n_nbr] sorted neighbour node ids (0-based)
+// assembly maps (built once per plan, api.cu) + outputs of one field
+struct AsmArgs {
+  long long n_nodes, n_blocks;  // node rows, node-pair blocks of the pattern
+  int N, DB, dpn;               // nodes/element, block size computed by K1, dofs per node of the assembled field
+  const unsigned* blk_row;      // [n_blocks] row node of each block
+  const unsigned* nbr_ptr;      // [n_nodes+1] first block of each row node (blocks = sorted neighbour nodes)
+  const unsigned* nbr;          // [n_blocks]  neighbour (column) node of each block
+  const unsigned* blk_ptr;      // [n_blocks+1] source list of each block
+  const unsigned* src;          // [ne*N*N] (slot*NPB + pair index)*2 + transposed, in `elems` order per block
+  const unsigned* adj_ptr;      // [n_nodes+1]
+  const unsigned* adj;          // [ne*N] slot*N + local node, in `elems` order per node
+  const double* Ke;
+  const double* re;
+  double* nzval;                // [dpn*dpn*n_blocks]
+  double* r;                    // [dpn*n_nodes]
+  unsigned long long* n_zero;   // [1] stored exact zeros in nzval
 };
 
-// ---- launchers (kernels.cu) ----
-cudaError_t launch_k1(const BatchDev& b, int mode, const double* u, int dpn, const double* dfield, double* hist,
-                      const Staging& st, bool want_K, cudaStream_t s);
-cudaError_t launch_k2(const AsmMaps& m, int DB, int dpn, const Staging& st, bool want_K, double* nzval, double* r,
-                      unsigned long long* n_zero, cudaStream_t s);
-cudaError_t launch_phi_reduce(const double* phie, long long n, double* partials, int n_partials, double* phi,
-                              cudaStream_t s);
-cudaError_t launch_pattern(const AsmMaps& m, int dpn, long long* colptr, long long* rowval, cudaStream_t s);
-cudaError_t launch_dropzeros(long long n_dof, long long nnz, const long long* colptr, const long long* rowval,
-                             const double* nzval, long long* colptr_out, long long* rowval_out, double* nzval_out,
-                             long long* nnz_out_host, cudaStream_t s);
-cudaError_t launch_fp64_peak(double* tflops, double* mhz);
+cudaError_t launch_k1(const K1Args& a, int mode, cudaStream_t s);
+const char* k1_unsupported_reason(int D, int N, int P, int mf, int mode);
+cudaError_t launch_k2(const AsmArgs& a, bool want_K, cudaStream_t s);
 int phi_reduce_partials();
+cudaError_t launch_phi_reduce(const double* phie, long long n, double* partials, double* phi, cudaStream_t s);
+cudaError_t launch_pattern(const AsmArgs& a, long long* colptr, long long* rowval, cudaStream_t s);
+// exact-zero compaction (dropzeros, elements.toolkit.jl:202); tmp must hold n_dof+1 long longs
+cudaError_t launch_dropzeros(long long n_dof, const long long* colptr, const long long* rowval, const double* nzval,
+                             long long* colptr_out, long long* rowval_out, double* nzval_out, void* cub_tmp,
+                             size_t cub_tmp_bytes, cudaStream_t s);
+size_t dropzeros_tmp_bytes(long long n_dof);
+cudaError_t launch_fp64_peak(double* tflops, double* mhz);
 
 }  // namespace ad4sm

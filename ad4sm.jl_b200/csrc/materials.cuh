@@ -51,7 +51,7 @@ template <int D> struct Tangent {
   double A[NA];
 };
 
-__host__ __device__ constexpr int pk(int I, int J) { return I <= J ? J * (J + 1) / 2 + I : I * (I + 1) / 2 + J; }
+AD4SM_HD constexpr int pk(int I, int J) { return I <= J ? J * (J + 1) / 2 + I : I * (I + 1) / 2 + J; }
 
 AD4SM_DI void lame(double Es, double nu, double& lam, double& mu) {  // elasticmaterials.jl:211-212
   lam = Es * nu / (1 + nu) / (1 - 2 * nu);

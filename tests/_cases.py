@@ -1,0 +1,70 @@
+"""Shared builders for the parity tests: seeded jittered meshes through the PRODUCT's constructors, and the
+same SoA arrays evaluated by the oracle (C++ restatement of the reference algorithm)."""
+import numpy as np
+
+from ad4sm_b200 import Elements as El, Materials as Ma, mesh
+from oracle import cxx_binding as X
+
+TOL = 1e-12  # north_star: values to relative 1e-12 in fp64
+
+
+def nh():
+    return Ma.NeoHooke(1000.0, 5000.0)
+
+
+def hex_case(n=(5, 4, 3), mat=None, seed=1, amp=0.02, ctor=None, dpn=3):
+    coords, conn = mesh.hex_block(*n, jitter=0.1, seed=seed)
+    b = (ctor or El.Hex08_batch)(conn, coords, mat or nh())
+    u = mesh.random_u(len(coords), dpn, 1.0 / max(n), a=amp, seed=seed + 100)
+    return b, u
+
+
+def quad_case(n=(9, 7), mat=None, seed=2, amp=0.02, ctor=None, dpn=2):
+    coords, conn = mesh.quad_grid(*n, jitter=0.1, seed=seed)
+    b = (ctor or El.Quad_batch)(conn, coords, mat or Ma.Hooke2D(210000.0, 0.3, plane_stress=False))
+    u = mesh.random_u(len(coords), dpn, 1.0 / max(n), a=amp, seed=seed + 100)
+    return b, u
+
+
+def tet_case(n=(4, 3, 3), mat=None, seed=3, amp=0.02, ctor=None):
+    coords, conn = mesh.tet_kuhn(*n, jitter=0.1, seed=seed)
+    b = (ctor or El.Tet04_batch)(conn, coords, mat or Ma.MooneyRivlin(800.0, 200.0, 5000.0))
+    u = mesh.random_u(len(coords), 3, 1.0 / max(n), a=amp, seed=seed + 100)
+    return b, u
+
+
+def tri_case(n=(6, 5), mat=None, seed=4, amp=0.02, ctor=None):
+    coords, conn = mesh.tri_grid(*n, jitter=0.1, seed=seed)
+    b = (ctor or El.Tria_batch)(conn, coords, mat or Ma.Hooke2D(210000.0, 0.3))
+    u = mesh.random_u(len(coords), 2, 1.0 / max(n), a=amp, seed=seed + 100)
+    return b, u
+
+
+def random_d(n_nodes, seed=7, hi=0.5):
+    return np.random.default_rng(seed).uniform(0.0, hi, n_nodes)
+
+
+def oracle_eval(batches, u, mode=X.M_ELASTIC, d=None, hist=None, **kw):
+    """Reference-algorithm result for the same arrays: ϕ, r, (colptr, rowval, nzval)."""
+    if not isinstance(batches, (list, tuple)):
+        batches = [batches]
+    return X.make_phi_r_Kt(batches, u, mode=mode, d=d, hist=hist, **kw)
+
+
+def assert_parity(got, ref, tol=TOL):
+    """(ϕ, r, Kt) from the product vs the oracle: pattern bit-exact, values to `tol` of the matrix scale
+    and per entry to 100·tol of the entry (cancellation-prone small entries)."""
+    phi, r, Kt = got
+    phi0, r0, (cp0, rv0, nz0) = ref
+    assert abs(phi - phi0) <= tol * max(1.0, abs(phi0)), (phi, phi0)
+    rs = max(np.abs(r0).max(), 1e-300)
+    assert np.abs(r - r0).max() <= tol * rs, np.abs(r - r0).max() / rs
+    assert np.array_equal(Kt.colptr, cp0), "colptr differs"
+    assert np.array_equal(Kt.rowval, rv0), "rowval differs"
+    ks = np.abs(nz0).max()
+    err = np.abs(Kt.nzval - nz0)
+    assert err.max() <= tol * ks, err.max() / ks
+
+
+def csc_dense(Kt):
+    return Kt.to_scipy().toarray()

@@ -1,0 +1,164 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Bar (north_star): CSC pattern bit-exact, ϕ / r / nzval to relative 1e-12."""
+import numpy as np
+import pytest
+
+from ad4sm_b200 import Elements as El, Materials as Ma, _capi as capi
+from oracle import cxx_binding as X
+
+import _cases as K
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(b, u, **opts):
+    plan = El.Plan(b, u.shape[1], u.shape[0], **opts)
+    return plan, plan.makeϕrKt(u)
+
+
+ELASTIC = [
+    ("hex8-neohooke", lambda: K.hex_case()),
+    ("hex8-neohooke-incompressible", lambda: K.hex_case(mat=Ma.NeoHooke(1000.0, -1.0))),
+    ("hex8-mooney", lambda: K.hex_case(mat=Ma.MooneyRivlin(800.0, 200.0, 5000.0))),
+    ("hex8-hooke-gl", lambda: K.hex_case(mat=Ma.Hooke(210000.0, 0.3))),
+    ("hex8-hooke-small", lambda: K.hex_case(mat=Ma.Hooke(210000.0, 0.3, small=True))),
+    ("hex8r-neohooke", lambda: K.hex_case(ctor=lambda c, x, m: El.Hex08_batch(c, x, m, GP=El.GP1))),
+    ("tet4-mooney", lambda: K.tet_case()),
+    ("tet4-neohooke", lambda: K.tet_case(mat=K.nh())),
+    ("tet4-hooke", lambda: K.tet_case(mat=Ma.Hooke(210000.0, 0.3))),
+    ("quad4-hooke2d-pe", lambda: K.quad_case()),
+    ("quad4-hooke2d-ps", lambda: K.quad_case(mat=Ma.Hooke2D(210000.0, 0.3))),
+    ("quad4-hooke2d-gl", lambda: K.quad_case(mat=Ma.Hooke2D(210000.0, 0.3, small=False))),
+    ("quad4-neohooke", lambda: K.quad_case(mat=K.nh())),
+    ("quad4-neohooke-ps", lambda: K.quad_case(mat=Ma.NeoHooke(1000.0, -1.0))),
+    ("quad4-mooney", lambda: K.quad_case(mat=Ma.MooneyRivlin(800.0, 200.0, 5000.0))),
+    ("quadr-hooke2d", lambda: K.quad_case(ctor=lambda c, x, m: El.Quad_batch(c, x, m, GP=El.GP1))),
+    ("tria3-hooke2d", lambda: K.tri_case()),
+    ("tria3-neohooke", lambda: K.tri_case(mat=K.nh())),
+]
+
+
+@pytest.mark.parametrize("name,make", ELASTIC, ids=[c[0] for c in ELASTIC])
+def test_elastic_parity(name, make):
+    b, u = make()
+    plan, got = _run(b, u)
+    K.assert_parity(got, K.oracle_eval(b, u))
+    Kd = K.csc_dense(got[2])
+    assert np.array_equal(Kd, Kd.T), "Kt must be bitwise symmetric"
+    again = plan.makeϕrKt(u)
+    assert again[0] == got[0] and np.array_equal(again[1], got[1]) and np.array_equal(again[2].nzval, got[2].nzval), \
+        "two evaluations must be bitwise identical (deterministic assembly)"
+    phi2, r2 = plan.makeϕr(u)
+    assert phi2 == got[0] and np.array_equal(r2, got[1])
+
+
+def test_structural_pattern_matches_csc():
+    b, u = K.hex_case((3, 3, 2))
+    plan, got = _run(b, u)
+    cp, rv = plan.pattern()
+    assert np.array_equal(cp, got[2].colptr) and np.array_equal(rv, got[2].rowval)
+    n, nnz = plan.pattern_size()
+    assert n == u.size and nnz == len(rv)
+
+
+def test_dropzeros_extra_u_rows():
+    """A 3-row u with 2-D elements: the reference seeds all 3 rows but getF reads rows 1:2 (toolkit:13), so
+    every entry touching component 3 is an exact zero that dropzeros removes (toolkit:202)."""
+    b, u = K.quad_case((5, 4), dpn=3)
+    plan, got = _run(b, u)
+    ref = K.oracle_eval(b, u)
+    K.assert_parity(got, ref)
+    n, nnz_struct = plan.pattern_size()
+    assert got[2].nnz < nnz_struct
+    assert np.all(got[1].reshape(-1, 3)[:, 2] == 0.0)
+
+
+def test_mixed_batches_follow_elems_order():
+    """A Vector of element objects with two materials interleaved: duplicates must be summed in `elems` order."""
+    from ad4sm_b200 import mesh
+    coords, conn = mesh.hex_block(3, 3, 2, jitter=0.1, seed=5)
+    m1, m2 = K.nh(), Ma.MooneyRivlin(800.0, 200.0, 5000.0)
+    elems = [El.Hex08(conn[e], coords[conn[e] - 1], mat=(m1 if e % 3 else m2)) for e in range(len(conn))]
+    u = mesh.random_u(len(coords), 3, 1 / 3, seed=9)
+    got = El.makeϕrKt(elems, u)
+    # oracle: one batch per element keeps the exact `elems` order
+    ob = [El.ElemBatch("CE", 3, e.nodes[None], e.gradN[None], e.wgt[None], e.mat) for e in elems]
+    K.assert_parity(got, K.oracle_eval(ob, u))
+
+
+PF2 = Ma.PhaseField(0.01, 100.0, Ma.Hooke2D(210000.0, 0.3, plane_stress=False), 2)
+PF2S = Ma.PhaseField(0.01, 100.0, Ma.Hooke2D(210000.0, 0.3), 2, AT="DHn")
+PF3 = Ma.PhaseField(0.01, 100.0, Ma.Hooke(210000.0, 0.3, small=True), 2)
+PF3N = Ma.PhaseField(0.01, 100.0, K.nh(), 2)
+PFCASES = [
+    ("quadp-hooke2d-atn", lambda: K.quad_case(mat=PF2, ctor=El.QuadP_batch, amp=0.3), {}),
+    ("quadp-hooke2d-ps-dhn", lambda: K.quad_case(mat=PF2S, ctor=El.QuadP_batch, amp=0.3), {}),
+    ("quadp-neohooke-ext", lambda: K.quad_case(mat=PF3N, ctor=El.QuadP_batch, amp=0.3), {"nh2d_extension": True}),
+    ("triap-hooke2d", lambda: K.tri_case(mat=PF2, ctor=El.TriaP_batch, amp=0.3), {}),
+    ("hex8p-hooke", lambda: K.hex_case((4, 3, 3), mat=PF3, ctor=El.Hex08P_batch, amp=0.3), {}),
+    ("hex8p-neohooke", lambda: K.hex_case((4, 3, 3), mat=PF3N, ctor=El.Hex08P_batch, amp=0.3), {}),
+    ("tet4p-neohooke", lambda: K.tet_case(mat=PF3N, ctor=El.Tet04P_batch, amp=0.3), {}),
+]
+
+
+@pytest.mark.parametrize("name,make,opts", PFCASES, ids=[c[0] for c in PFCASES])
+def test_phasefield_u_phase(name, make, opts):
+    b, u = make()
+    d = K.random_d(u.shape[1])
+    plan = El.Plan(b, u.shape[1], u.shape[0], **opts)
+    got = plan.makeϕrKt(u, d)
+    K.assert_parity(got, K.oracle_eval(b, u, mode=X.M_PF_U, d=d, **opts))
+
+
+@pytest.mark.parametrize("grad_term", ["reference", "intended"])
+@pytest.mark.parametrize("with_hist", [False, True])
+@pytest.mark.parametrize("name,make,opts", PFCASES, ids=[c[0] for c in PFCASES])
+def test_phasefield_d_phase(name, make, opts, with_hist, grad_term):
+    b, u = make()
+    d = K.random_d(u.shape[1])
+    plan = El.Plan(b, u.shape[1], u.shape[0], pf_grad_term=grad_term, **opts)
+    rng = np.random.default_rng(3)
+    h_gpu = h_ref = None
+    if with_hist:
+        h0 = rng.uniform(0.0, 2.0, (b.ne, b.P, 2)) * (rng.uniform(size=(b.ne, 1, 1)) > 0.5)
+        h_gpu, h_ref = h0.copy(), h0.copy()
+    got = plan.makeϕrKt_d(u, d, h_gpu)
+    ref = K.oracle_eval(b, u, mode=X.M_PF_D, d=d, hist=None if h_ref is None else [h_ref], grad_term=grad_term, **opts)
+    K.assert_parity(got, ref)
+    if with_hist:
+        assert np.abs(h_gpu - h_ref).max() <= 1e-12 * max(1.0, np.abs(h_ref).max())
+        assert not np.array_equal(h_gpu, h0), "history must be updated in place"
+
+
+def test_error_behaviour():
+    b, u = K.hex_case((2, 2, 2))
+    with pytest.raises(AssertionError):
+        El.makeϕrKt([], u)  # @assert nElems > 0, elasticelements.jl:210
+    bad = El.ElemBatch("CE", 3, b.nodes + 1000, b.gradN, b.wgt, b.mat)
+    with pytest.raises(capi.AD4SMError):
+        El.Plan(bad, u.shape[1], 3)
+    with pytest.raises(capi.AD4SMError):  # PhaseField material without d
+        p = El.Plan(El.Hex08P_batch(b.nodes, np.zeros((u.shape[1], 3)) + np.random.default_rng(0).uniform(size=(u.shape[1], 3)),
+                                    PF3), u.shape[1], 3)
+        p.makeϕrKt(u)
+    with pytest.raises(capi.AD4SMError):  # 2-D PhaseField{NeoHooke}: BoundsError upstream unless the extension is requested
+        q, uq = K.quad_case(mat=PF3N, ctor=El.QuadP_batch)
+        El.Plan(q, uq.shape[1], 2)
+
+
+def test_device_resident_path_matches_host_path():
+    import torch
+    b, u = K.hex_case()
+    plan, got = _run(b, u)
+    ut = torch.from_numpy(np.ascontiguousarray(u.T)).cuda()  # [node][comp] == column-major (dpn, n_nodes)
+    plan.eval_device(capi.MODE_ELASTIC, ut.data_ptr())
+    plan.sync()
+    Kt = plan.fetch_csc()
+    assert np.array_equal(Kt.nzval, got[2].nzval) and np.array_equal(Kt.rowval, got[2].rowval)
+
+
+def test_fp64_peak_microbenchmark_runs():
+    import ctypes as C
+    tf, mhz = C.c_double(), C.c_double()
+    capi.check(capi.lib().ad4sm_measure_fp64_peak(0, C.byref(tf), C.byref(mhz)))
+    assert 5.0 < tf.value < 80.0, tf.value
