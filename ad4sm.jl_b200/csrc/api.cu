@@ -86,8 +86,8 @@ struct ad4sm_plan {
 
 template <class T> static int dev_alloc(ad4sm_plan* p, T** ptr, size_t count) {
   *ptr = nullptr;
-  if (count == 0) count = 1;
-  CK(cudaMalloc((void**)ptr, count * sizeof(T)));
+  // +64 bytes: the TMA bulk copies of K1 round the tail group's wgt / node-id / N rows up to 16 bytes
+  CK(cudaMalloc((void**)ptr, count * sizeof(T) + 64));
   p->allocs.push_back((void*)*ptr);
   return 0;
 }

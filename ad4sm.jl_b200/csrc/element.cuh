@@ -53,6 +53,29 @@ template <int D> struct GpRecD {
   static constexpr int SIZE = 4 + D;
 };
 
+// 16-byte shared-memory access helpers.  A GP record / gradient tile that lives in shared memory is read
+// with LDS.128 (a quarter-warp = the 8 lanes of one element read the same address: one broadcast
+// wavefront); a record held in registers (thread-per-element path) or on the host is read as scalars.
+#ifdef __CUDACC__
+struct VecMem {
+  const double* p;  // 16-byte aligned
+  AD4SM_DI double operator()(int i) const {
+    const double2 v = reinterpret_cast<const double2*>(p)[i >> 1];
+    return (i & 1) ? v.y : v.x;
+  }
+};
+AD4SM_DI void store2(double* p, int i2, double a, double b) { reinterpret_cast<double2*>(p)[i2] = make_double2(a, b); }
+#else
+AD4SM_DI void store2(double* p, int i2, double a, double b) {
+  p[2 * i2] = a;
+  p[2 * i2 + 1] = b;
+}
+#endif
+struct ScalarMem {
+  const double* p;
+  AD4SM_DI double operator()(int i) const { return p[i]; }
+};
+
 // F[k*D+j] = δ_jk + Σ_a ∇N_a,k u_a,j   (toolkit:8-20); G[k*N+a], ue[a*D+j]
 template <int D, int N> AD4SM_DI void deformation_gradient(const double* G, const double* ue, double* F) {
 #pragma unroll
@@ -93,11 +116,12 @@ AD4SM_DI void gauss_point_u(const MatDev& m, const double* G, const double* ue, 
   }
   Tangent<D> t;
   material_tangent<D, MF>(m, F, PF ? &pf : nullptr, t);
+  // record = [w·A (NA) | w·P (DD) | w·ψ], written in 16-byte pairs (rec is 16-byte aligned, capacity SIZE+1)
+  auto val = [&](int i) -> double {
+    return i < R::NA ? w * t.A[i] : (i < R::NA + R::DD ? w * t.P[i - R::NA] : (i == R::OFF_PSI ? w * t.psi : 0.0));
+  };
 #pragma unroll
-  for (int i = 0; i < R::NA; i++) rec[R::OFF_A + i] = w * t.A[i];
-#pragma unroll
-  for (int i = 0; i < R::DD; i++) rec[R::OFF_P + i] = w * t.P[i];
-  rec[R::OFF_PSI] = w * t.psi;
+  for (int i2 = 0; i2 < (R::SIZE + 1) / 2; i2++) store2(rec, i2, val(2 * i2), val(2 * i2 + 1));
 }
 
 // phase 1, d-dual path (makeϕrKt_d, phasefieldelements.jl:239-262; energies phasefieldmaterials.jl:20-135).
@@ -160,7 +184,7 @@ AD4SM_DI void gauss_point_d(const MatDev& m, const double* G, const double* Nv, 
 }
 
 // T[(k,j)][l] = Σ_m A_(kj)(ml) ∇N_b,m  from the packed symmetric A (81 FMAs for D = 3)
-template <int D> AD4SM_DI void tangent_times_gradient(const double* A, const double* gb, double (*T)[D]) {
+template <int D, class Mem> AD4SM_DI void tangent_times_gradient(const Mem& A, const double* gb, double (*T)[D]) {
   constexpr int DD = D * D;
 #pragma unroll
   for (int I = 0; I < DD; I++)
@@ -170,7 +194,7 @@ template <int D> AD4SM_DI void tangent_times_gradient(const double* A, const dou
   for (int J = 0; J < DD; J++)
 #pragma unroll
     for (int I = 0; I <= J; I++) {
-      const double a = A[J * (J + 1) / 2 + I];
+      const double a = A(J * (J + 1) / 2 + I);
       T[I][J % D] += a * gb[J / D];
       if (I != J) T[J][I % D] += a * gb[I / D];
     }
@@ -190,20 +214,20 @@ template <int D> AD4SM_DI void add_block(const double* ga, const double (*T)[D],
 }
 
 // phase 2 (u-dual): column node q of one element.
-//   recs: P GP records, `rstride` doubles apart;  gN: the element's ∇N, [D][P][N] (elem.∇N[k][gp][a]).
+//   recs: P GP records, `rstride` doubles apart, read through Mem (VecMem: shared memory, ScalarMem: registers/host)
+//   gS:   the element's ∇N: ∇N_a,k at Gauss point gp is gS[gp*gstride + k*kstride + a]
 //   Ke:   the element's block storage [NPB][D*D] (may be nullptr when only ϕ, r are wanted)
 //   re:   the element's residual [N][D].
 // PT: compile-time number of Gauss points (0 = use the run-time P), so that a register-resident
 // record (P = 1, thread-per-element path) is indexed statically.
-template <int D, int N, int PT = 0>
-AD4SM_DI void column_u(int q, int Prt, const double* recs, int rstride, const double* gN, double* Ke, double* re) {
+template <int D, int N, int PT, class Mem>
+AD4SM_DI void column_u_acc(int q, int Prt, const double* recs, int rstride, const double* gS, int gstride, int kstride,
+                           bool want_K, double (*acc)[D * D], double* rq) {
   using R = GpRec<D>;
   const int P = PT ? PT : Prt;
   constexpr int DD = D * D;
   constexpr int NO = N / 2 + 1;  // max offsets per column
   const int no = n_offsets(N, q);
-  double acc[NO][DD];
-  double rq[D];
 #pragma unroll
   for (int o = 0; o < NO; o++)
 #pragma unroll
@@ -211,18 +235,19 @@ AD4SM_DI void column_u(int q, int Prt, const double* recs, int rstride, const do
 #pragma unroll
   for (int j = 0; j < D; j++) rq[j] = 0.0;
   for (int gp = 0; gp < P; gp++) {
-    const double* rec = recs + (long long)gp * rstride;
+    const Mem rec{recs + gp * rstride};
+    const double* g = gS + gp * gstride;
     double gb[D];
 #pragma unroll
-    for (int k = 0; k < D; k++) gb[k] = gN[(k * P + gp) * N + q];
+    for (int k = 0; k < D; k++) gb[k] = g[k * kstride + q];
     // r_(q,j) += Σ_k wP_(kj) ∇N_q,k
 #pragma unroll
     for (int j = 0; j < D; j++)
 #pragma unroll
-      for (int k = 0; k < D; k++) rq[j] += rec[R::OFF_P + k * D + j] * gb[k];
-    if (Ke) {
+      for (int k = 0; k < D; k++) rq[j] += rec(R::OFF_P + k * D + j) * gb[k];
+    if (want_K) {
       double T[DD][D];
-      tangent_times_gradient<D>(rec + R::OFF_A, gb, T);
+      tangent_times_gradient<D>(rec, gb, T);
 #pragma unroll
       for (int o = 0; o < NO; o++) {
         if (o < no) {
@@ -230,34 +255,48 @@ AD4SM_DI void column_u(int q, int Prt, const double* recs, int rstride, const do
           if (a >= N) a -= N;
           double ga[D];
 #pragma unroll
-          for (int k = 0; k < D; k++) ga[k] = gN[(k * P + gp) * N + a];
+          for (int k = 0; k < D; k++) ga[k] = g[k * kstride + a];
           add_block<D>(ga, T, acc[o]);
         }
       }
     }
   }
+  // the diagonal node block is symmetric in exact arithmetic; mirror its upper triangle so that Kt is
+  // bitwise symmetric like the reference's (both triangles read one packed slot, adiff.jl:160)
 #pragma unroll
-  for (int j = 0; j < D; j++) re[q * D + j] = rq[j];
-  if (Ke) {
-    // the diagonal node block is symmetric in exact arithmetic; mirror its upper triangle so that Kt is
-    // bitwise symmetric like the reference's (both triangles read one packed slot, adiff.jl:160)
+  for (int j = 0; j < D; j++)
 #pragma unroll
-    for (int j = 0; j < D; j++)
-#pragma unroll
-      for (int l = j + 1; l < D; l++) acc[0][l * D + j] = acc[0][j * D + l];
-#pragma unroll
-    for (int o = 0; o < NO; o++)
-      if (o < no) {
-#pragma unroll
-        for (int i = 0; i < DD; i++) Ke[(o * N + q) * DD + i] = acc[o][i];
-      }
-  }
+    for (int l = j + 1; l < D; l++) acc[0][l * D + j] = acc[0][j * D + l];
 }
 
-// phase 2 (d-dual): column node q; blocks are scalars.  Nv: [P][N] shape-function values.
+// write column q's blocks into the element's block storage Ke [NPB][D*D] (global or shared memory)
+template <int D, int N> AD4SM_DI void column_u_store(int q, const double (*acc)[D * D], double* Ke) {
+  constexpr int DD = D * D;
+  constexpr int NO = N / 2 + 1;
+  const int no = n_offsets(N, q);
+#pragma unroll
+  for (int o = 0; o < NO; o++)
+    if (o < no) {
+#pragma unroll
+      for (int i = 0; i < DD; i++) Ke[(o * N + q) * DD + i] = acc[o][i];
+    }
+}
+
+template <int D, int N, int PT, class Mem>
+AD4SM_DI void column_u(int q, int Prt, const double* recs, int rstride, const double* gS, int gstride, int kstride,
+                       double* Ke, double* re) {
+  double acc[N / 2 + 1][D * D], rq[D];
+  column_u_acc<D, N, PT, Mem>(q, Prt, recs, rstride, gS, gstride, kstride, Ke != nullptr, acc, rq);
+#pragma unroll
+  for (int j = 0; j < D; j++) re[q * D + j] = rq[j];
+  if (Ke) column_u_store<D, N>(q, acc, Ke);
+}
+
+// phase 2 (d-dual): column node q; blocks are scalars.  gS as in column_u; Nv: [gp][a] shape-function values,
+// `nstride` doubles between Gauss points.
 template <int D, int N, int PT = 0>
-AD4SM_DI void column_d(int q, int Prt, const double* recs, int rstride, const double* gN, const double* Nv, double* Ke,
-                       double* re) {
+AD4SM_DI void column_d(int q, int Prt, const double* recs, int rstride, const double* gS, int gstride, const double* Nv,
+                       int nstride, double* Ke, double* re) {
   constexpr int NO = N / 2 + 1;
   const int P = PT ? PT : Prt;
   const int no = n_offsets(N, q);
@@ -266,13 +305,15 @@ AD4SM_DI void column_d(int q, int Prt, const double* recs, int rstride, const do
   for (int o = 0; o < NO; o++) acc[o] = 0.0;
   double rq = 0.0;
   for (int gp = 0; gp < P; gp++) {
-    const double* rec = recs + (long long)gp * rstride;
+    const double* rec = recs + gp * rstride;
+    const double* g = gS + gp * gstride;
+    const double* nv = Nv + gp * nstride;
     const double ws2 = rec[0], ws1 = rec[1], wc = rec[3];
-    const double nb = Nv[gp * N + q];
+    const double nb = nv[q];
     double gb[D], gdgb = 0.0;
 #pragma unroll
     for (int k = 0; k < D; k++) {
-      gb[k] = gN[(k * P + gp) * N + q];
+      gb[k] = g[k * N + q];
       gdgb += rec[4 + k] * gb[k];
     }
     rq += ws1 * nb + wc * gdgb;
@@ -284,8 +325,8 @@ AD4SM_DI void column_d(int q, int Prt, const double* recs, int rstride, const do
           if (a >= N) a -= N;
           double gg = 0.0;
 #pragma unroll
-          for (int k = 0; k < D; k++) gg += gN[(k * P + gp) * N + a] * gb[k];
-          acc[o] += ws2 * (Nv[gp * N + a] * nb) + wc * gg;
+          for (int k = 0; k < D; k++) gg += g[k * N + a] * gb[k];
+          acc[o] += ws2 * (nv[a] * nb) + wc * gg;
         }
     }
   }

@@ -23,13 +23,28 @@ namespace ad4sm {
 
 constexpr int K1_THREADS = 128;
 
-__host__ __device__ inline int k1_rec_stride(int rec_size) { return (rec_size + 1) & ~1; }
-// shared-memory stride (doubles) between the elements of a CTA: the 32/LP elements of a warp read the
-// same record offset at the same time (broadcast within an element), so successive elements are
-// skewed by 16/(32/LP) doubles to land in different banks.
-__host__ __device__ inline int k1_elem_stride(int P, int rstride, int LP) {
-  const int ew = 32 / LP;
-  return ((P * rstride + 15) & ~15) + 16 / ew;
+// Shared-memory layout of one element (doubles):  [P][rstride] GP records | [P][gstride] ∇N as [k][a] | ([P][nstride] N)
+// Strides are even (16-byte aligned rows) with an odd number of 16-byte units, so the 8 lanes of an
+// element, which write rows `stride` apart with STS.128 in phase 1, hit 8 different bank groups.
+__host__ __device__ inline int odd_units_stride(int n) {
+  int s = (n + 1) & ~1;
+  if (((s >> 1) & 1) == 0) s += 2;
+  return s;
+}
+struct SmemLayout {
+  int rstride, gstride, nstride, goff, noff, estride;
+};
+__host__ __device__ inline SmemLayout k1_layout(int rec_size, int D, int N, int P, bool with_N) {
+  SmemLayout L;
+  L.rstride = odd_units_stride(rec_size);
+  L.gstride = odd_units_stride(D * N);
+  L.nstride = with_N ? odd_units_stride(N) : 0;
+  L.goff = P * L.rstride;
+  L.noff = L.goff + P * L.gstride;
+  const int tot = L.noff + P * L.nstride;
+  // phase 2 reads ∇N with LDS.64 (a half-warp spans two elements): skew successive elements by 8 doubles
+  L.estride = ((tot + 15) & ~15) + 8;
+  return L;
 }
 
 template <int D, int N> __device__ __forceinline__ void load_gp_inputs(const K1Args& a, long long e, int gp, double* G,
@@ -45,47 +60,213 @@ template <int D, int N> __device__ __forceinline__ void load_gp_inputs(const K1A
 #pragma unroll
     for (int j = 0; j < D; j++) ue[n * D + j] = __ldg(a.u + (long long)nd[n] * a.dpn + j);
 }
-
-// ---- K1, u-dual, LP lanes per element -----------------------------------------------------------
-template <int D, int N, int LP, int MF, bool PF>
-__global__ void __launch_bounds__(K1_THREADS, 2) k1_u_kernel(const K1Args a, const int rstride, const int estride) {
-  using R = GpRec<D>;
-  constexpr int EPC = K1_THREADS / LP;
-  constexpr int DD = D * D;
-  extern __shared__ double sm[];
-  const int el = threadIdx.x / LP, q = threadIdx.x % LP;
-  const long long e = (long long)blockIdx.x * EPC + el;
-  const int P = a.P;
-  double* recs = sm + el * estride;
-  const bool valid = e < a.ne;
-  if (valid) {
-    int nd[N];
+template <int CNT> __device__ __forceinline__ void store_row(double* dst, const double* src) {
 #pragma unroll
-    for (int n = 0; n < N; n++) nd[n] = __ldg(a.nodes + e * N + n);
-    for (int gp = q; gp < P; gp += LP) {
-      double G[D * N], ue[N * D], de[N], Nv[N];
-      load_gp_inputs<D, N>(a, e, gp, G, ue, nd);
+  for (int i2 = 0; i2 < (CNT + 1) / 2; i2++) store2(dst, i2, src[2 * i2], (2 * i2 + 1 < CNT) ? src[2 * i2 + 1] : 0.0);
+}
+
+// ---- TMA / mbarrier helpers (sm_90+ PTX; SASS: UBLKCP, SYNCS) ----------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// Per-warp shared-memory slice of the persistent K1 (byte offsets).  Each warp is autonomous: it owns
+// 32/LP elements per iteration, a double-buffered input stage filled by TMA bulk copies (∇N, wgt, nodes, N),
+// the GP records, and two mbarriers; no CTA-wide barrier is ever needed.
+struct WarpLayout {
+  int rstride;          // doubles between GP records
+  int rec_el;           // bytes of records per element (P * rstride * 8)
+  int g_off[2], g_el;   // ∇N stage, element stride in bytes (raw [k][gp][a] + skew)
+  int w_off[2];         // wgt stage [EW][P] doubles
+  int n_off[2];         // node ids stage [EW][N] int32
+  int v_off[2];         // shape-function values stage [EW][P][N] doubles (phase field)
+  int bar_off;          // 2 x 8-byte mbarriers
+  int kout_el;          // epilogue staging stride per element (bytes); 0 = store blocks directly
+  int bytes;            // slice size, multiple of 128
+};
+static inline int rup(int x, int m) { return (x + m - 1) / m * m; }
+static WarpLayout k1p_layout(int D, int N, int P, int LP, bool pf) {
+  WarpLayout L;
+  const int EW = 32 / LP, DD = D * D, NPB = n_pair_blocks(N);
+  L.rstride = odd_units_stride(DD * (DD + 1) / 2 + DD + 1);  // GpRec<D>::SIZE
+  L.rec_el = P * L.rstride * 8;
+  const int min_scratch = (N * D + N) * 8;  // u / d gather scratch aliases the records
+  if (L.rec_el < min_scratch) L.rec_el = rup(min_scratch, 16);
+  int off = EW * L.rec_el;
+  L.g_el = D * P * N * 8;
+  if (LP == 8 && (L.g_el % 128) == 0) L.g_el += 64;  // half-warp = 2 elements read ∇N with LDS.64: skew by 64 B
+  for (int s = 0; s < 2; s++) {
+    L.g_off[s] = off;
+    off += EW * L.g_el;
+  }
+  for (int s = 0; s < 2; s++) {
+    L.w_off[s] = off;
+    off += rup(EW * P * 8, 16);
+  }
+  for (int s = 0; s < 2; s++) {
+    L.n_off[s] = off;
+    off += rup(EW * N * 4, 16);
+  }
+  for (int s = 0; s < 2; s++) {
+    L.v_off[s] = off;
+    if (pf) off += rup(EW * P * N * 8, 16);
+  }
+  L.bar_off = off;
+  off += 16;
+  L.bytes = rup(off, 128);
+  // coalesced epilogue: stage the element blocks in the (dead) record region when they fit
+  L.kout_el = 0;
+  if ((NPB * DD) % 2 == 0) {
+    int k = NPB * DD * 8;
+    if (LP == 8)
+      while (k % 128 != 64) k += 16;
+    if (k <= L.rec_el) L.kout_el = k;
+  }
+  return L;
+}
+
+// ---- K1, u-dual, persistent, LP lanes per element, TMA-staged inputs ------------------------------
+template <int D, int N, int LP, int MF, bool PF>
+__global__ void __launch_bounds__(256, 1) k1_u_kernel(const K1Args a, const WarpLayout L, const int warps_per_cta) {
+  using R = GpRec<D>;
+  constexpr int EW = 32 / LP;
+  constexpr int DD = D * D;
+  constexpr int NPB = n_pair_blocks(N);
+  constexpr int NO = N / 2 + 1;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* ws = smraw + (size_t)warp * L.bytes;
+  const int el = lane / LP, q = lane % LP;
+  const int P = a.P;
+  const long long n_groups = (a.ne + EW - 1) / EW;
+  const long long gstep = (long long)gridDim.x * warps_per_cta;
+  const unsigned bar0 = smem_u32(ws + L.bar_off);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  auto issue = [&](long long grp, int s) {  // lane 0: TMA bulk copies of one element group into stage s
+    const long long e0 = grp * EW;
+    const int cnt = (int)((a.ne - e0) < EW ? (a.ne - e0) : EW);
+    const unsigned bar = bar0 + 8 * s;
+    const unsigned gbytes = (unsigned)(D * P * N * 8);
+    const unsigned wbytes = (unsigned)((cnt * P * 8 + 15) & ~15), nbytes = (unsigned)((cnt * N * 4 + 15) & ~15);
+    const unsigned vbytes = PF ? (unsigned)((cnt * P * N * 8 + 15) & ~15) : 0u;
+    fence_proxy_async();
+    mbar_expect_tx(bar, cnt * gbytes + wbytes + nbytes + vbytes);
+    for (int i = 0; i < cnt; i++)
+      tma_load_1d(smem_u32(ws + L.g_off[s] + i * L.g_el), a.gradN + (e0 + i) * (long long)(D * P * N), gbytes, bar);
+    tma_load_1d(smem_u32(ws + L.w_off[s]), a.wgt + e0 * P, wbytes, bar);
+    tma_load_1d(smem_u32(ws + L.n_off[s]), a.nodes + e0 * N, nbytes, bar);
+    if (PF) tma_load_1d(smem_u32(ws + L.v_off[s]), a.Nval + e0 * (long long)(P * N), vbytes, bar);
+  };
+
+  long long grp = (long long)blockIdx.x * warps_per_cta + warp;
+  if (lane == 0 && grp < n_groups) issue(grp, 0);
+  for (int it = 0; grp < n_groups; grp += gstep, it++) {
+    const int s = it & 1;
+    if (lane == 0 && grp + gstep < n_groups) issue(grp + gstep, s ^ 1);
+    mbar_wait(bar0 + 8 * s, (unsigned)((it >> 1) & 1));
+
+    const long long e = grp * EW + el;
+    const bool valid = e < a.ne;
+    const bool active = valid && q < N;
+    const long long slot = a.slot0 + e;
+    double* recs = reinterpret_cast<double*>(ws + (size_t)el * L.rec_el);
+    const double* gS = reinterpret_cast<const double*>(ws + L.g_off[s] + (size_t)el * L.g_el);
+    const double* wS = reinterpret_cast<const double*>(ws + L.w_off[s]) + el * P;
+    const int* nS = reinterpret_cast<const int*>(ws + L.n_off[s]) + el * N;
+    const double* vS = reinterpret_cast<const double*>(ws + L.v_off[s]) + el * P * N;
+
+    // gather: lane q fetches node q's displacement (and phase field) into the element scratch
+    if (active) {
+      const long long node = nS[q];
+#pragma unroll
+      for (int j = 0; j < D; j++) recs[q * D + j] = __ldg(a.u + node * a.dpn + j);
+      if (PF) recs[N * D + q] = __ldg(a.dfield + node);
+    }
+    __syncwarp();
+    double ue[N * D], de[N];
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < N * D; i++) ue[i] = recs[i];
       if (PF) {
 #pragma unroll
-        for (int n = 0; n < N; n++) {
-          de[n] = __ldg(a.dfield + nd[n]);
-          Nv[n] = __ldg(a.Nval + (e * P + gp) * N + n);
-        }
+        for (int n = 0; n < N; n++) de[n] = recs[N * D + n];
       }
-      gauss_point_u<D, N, MF, PF>(a.mat, G, ue, de, Nv, __ldg(a.wgt + e * P + gp), recs + gp * rstride);
     }
-  }
-  __syncthreads();
-  if (valid && q < N) {
-    const long long slot = a.slot0 + e;
-    const double* gN = a.gradN + e * (long long)(D * P * N);
-    double* Ke = a.want_K ? a.Ke + slot * (long long)(n_pair_blocks(N) * DD) : nullptr;
-    column_u<D, N>(q, P, recs, rstride, gN, Ke, a.re + slot * (long long)(N * D));
-    if (q == 0) {  // ϕ_e = Σ_gp w ψ, in Gauss-point order (elasticelements.jl:199-206)
-      double s = 0.0;
-      for (int gp = 0; gp < P; gp++) s += recs[gp * rstride + R::OFF_PSI];
-      a.phie[slot] = s;
+    __syncwarp();
+    // phase 1: one Gauss point per lane
+    if (valid) {
+      for (int gp = q; gp < P; gp += LP) {
+        double G[D * N], Nv[N];
+#pragma unroll
+        for (int k = 0; k < D; k++)
+#pragma unroll
+          for (int n = 0; n < N; n++) G[k * N + n] = gS[(k * P + gp) * N + n];
+        if (PF) {
+#pragma unroll
+          for (int n = 0; n < N; n++) Nv[n] = vS[gp * N + n];
+        }
+        gauss_point_u<D, N, MF, PF>(a.mat, G, ue, de, Nv, wS[gp], recs + gp * L.rstride);
+      }
     }
+    __syncwarp();
+    // phase 2: one column node per lane
+    double acc[NO][DD], rq[D];
+    if (active) column_u_acc<D, N, 0, VecMem>(q, P, recs, L.rstride, gS, N, P * N, a.want_K != 0, acc, rq);
+    if (valid && q == 0) {  // ϕ_e = Σ_gp w ψ, in Gauss-point order (elasticelements.jl:199-206)
+      double ssum = 0.0;
+      for (int gp = 0; gp < P; gp++) ssum += recs[gp * L.rstride + R::OFF_PSI];
+      a.phie[slot] = ssum;
+    }
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < D; j++) a.re[slot * (long long)(N * D) + q * D + j] = rq[j];
+    }
+    __syncwarp();
+    // epilogue: element blocks -> staging
+    if (a.want_K) {
+      if (L.kout_el) {  // transpose through shared memory (the records are dead), then 16-byte coalesced stores
+        if (active) column_u_store<D, N>(q, acc, reinterpret_cast<double*>(ws + (size_t)el * L.kout_el));
+        __syncwarp();
+        constexpr int CPE = NPB * DD / 2;  // 16-byte chunks per element
+        const long long e0 = grp * EW;
+        const int cnt = (int)((a.ne - e0) < EW ? (a.ne - e0) : EW);
+        double2* dst = reinterpret_cast<double2*>(a.Ke + (a.slot0 + e0) * (long long)(NPB * DD));
+        for (int c = lane; c < cnt * CPE; c += 32) {
+          const int ee = c / CPE, off = c - ee * CPE;
+          dst[c] = *reinterpret_cast<const double2*>(ws + (size_t)ee * L.kout_el + (size_t)off * 16);
+        }
+      } else if (active) {
+        column_u_store<D, N>(q, acc, a.Ke + slot * (long long)(NPB * DD));
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -107,25 +288,27 @@ template <int D, int N, int MF, bool PF> __global__ void __launch_bounds__(K1_TH
       Nv[n] = __ldg(a.Nval + e * N + n);
     }
   }
-  double rec[R::SIZE];
+  __align__(16) double rec[R::SIZE + 1];
   gauss_point_u<D, N, MF, PF>(a.mat, G, ue, de, Nv, __ldg(a.wgt + e), rec);
   const long long slot = a.slot0 + e;
   double* Ke = a.want_K ? a.Ke + slot * (long long)(n_pair_blocks(N) * DD) : nullptr;
   double* re = a.re + slot * (long long)(N * D);
 #pragma unroll
-  for (int q = 0; q < N; q++) column_u<D, N, 1>(q, 1, rec, 0, G, Ke, re);  // G is [D][1][N]
+  for (int q = 0; q < N; q++) column_u<D, N, 1, ScalarMem>(q, 1, rec, 0, G, 0, N, Ke, re);  // G is [k][a]
   a.phie[slot] = rec[R::OFF_PSI];
 }
 
 // ---- K1, d-dual (makeϕrKt_d) -----------------------------------------------------------------------
 template <int D, int N, int LP>
-__global__ void __launch_bounds__(K1_THREADS, 2) k1_d_kernel(const K1Args a, const int rstride, const int estride) {
+__global__ void __launch_bounds__(K1_THREADS, 2) k1_d_kernel(const K1Args a, const SmemLayout L) {
   constexpr int EPC = K1_THREADS / LP;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int el = threadIdx.x / LP, q = threadIdx.x % LP;
   const long long e = (long long)blockIdx.x * EPC + el;
   const int P = a.P;
-  double* recs = sm + el * estride;
+  double* recs = sm + el * L.estride;
+  double* gS = recs + L.goff;
+  double* nS = recs + L.noff;
   const bool valid = e < a.ne;
   if (valid) {
     int nd[N];
@@ -139,20 +322,20 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_d_kernel(const K1Args a, con
         de[n] = __ldg(a.dfield + nd[n]);
         Nv[n] = __ldg(a.Nval + (e * P + gp) * N + n);
       }
+      store_row<D * N>(gS + gp * L.gstride, G);
+      store_row<N>(nS + gp * L.nstride, Nv);
       double* h = a.hist ? a.hist + (e * P + gp) * 2 : nullptr;
-      gauss_point_d<D, N>(a.mat, G, Nv, ue, de, __ldg(a.wgt + e * P + gp), h, recs + gp * rstride);
+      gauss_point_d<D, N>(a.mat, G, Nv, ue, de, __ldg(a.wgt + e * P + gp), h, recs + gp * L.rstride);
     }
   }
   __syncthreads();
   if (valid && q < N) {
     const long long slot = a.slot0 + e;
-    const double* gN = a.gradN + e * (long long)(D * P * N);
-    const double* Nv = a.Nval + e * (long long)(P * N);
     double* Ke = a.want_K ? a.Ke + slot * (long long)n_pair_blocks(N) : nullptr;
-    column_d<D, N>(q, P, recs, rstride, gN, Nv, Ke, a.re + slot * (long long)N);
+    column_d<D, N>(q, P, recs, L.rstride, gS, L.gstride, nS, L.nstride, Ke, a.re + slot * (long long)N);
     if (q == 0) {
       double s = 0.0;
-      for (int gp = 0; gp < P; gp++) s += recs[gp * rstride + 2];
+      for (int gp = 0; gp < P; gp++) s += recs[gp * L.rstride + 2];
       a.phie[slot] = s;
     }
   }
@@ -177,7 +360,7 @@ template <int D, int N> __global__ void __launch_bounds__(K1_THREADS) k1_d_kerne
   double* Ke = a.want_K ? a.Ke + slot * (long long)n_pair_blocks(N) : nullptr;
   double* re = a.re + slot * (long long)N;
 #pragma unroll
-  for (int q = 0; q < N; q++) column_d<D, N, 1>(q, 1, rec, 0, G, Nv, Ke, re);
+  for (int q = 0; q < N; q++) column_d<D, N, 1>(q, 1, rec, 0, G, 0, Nv, 0, Ke, re);
   a.phie[slot] = rec[2];
 }
 
@@ -201,7 +384,7 @@ static bool lanes_for(int D, int N, int P, int& LP) {
 const char* k1_unsupported_reason(int D, int N, int P, int mf, int mode) {
   int LP;
   if (!lanes_for(D, N, P, LP)) return "unsupported element shape (D, N): supported are (2,3), (2,4), (3,4), (3,6), (3,8)";
-  if (P < 1 || P > 64) return "number of Gauss points must be in 1..64";
+  if (P < 1 || P > 27) return "number of Gauss points must be in 1..27";
   if (mf == MF_OGDEN) return "Ogden: the reference defines only the scalar energy (no derivative); not implemented";
   if (mf < 0 || mf > MF_OGDEN) return "unknown material family";
   (void)mode;
@@ -214,17 +397,28 @@ template <int D, int N, int LP, int MF, bool PF> static cudaError_t launch_u_t(c
     k1_u_kernel_t1<D, N, MF, PF><<<grid, K1_THREADS, 0, s>>>(a);
     return cudaGetLastError();
   } else {
-    constexpr int EPC = K1_THREADS / LP;
-    const int rstride = k1_rec_stride(GpRec<D>::SIZE);
-    const int estride = k1_elem_stride(a.P, rstride, LP);
-    const size_t smem = (size_t)EPC * estride * sizeof(double);
-    auto kern = k1_u_kernel<D, N, LP, MF, PF>;
-    if (smem > 48 * 1024) {
-      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (err != cudaSuccess) return err;
+    constexpr int EW = 32 / LP;
+    const WarpLayout L = k1p_layout(D, N, a.P, LP, PF);
+    const int smem_max = 227 * 1024;
+    int warps = smem_max / L.bytes;
+    if (warps < 1) return cudaErrorInvalidValue;
+    if (warps > 8) warps = 8;
+    const long long n_groups = (a.ne + EW - 1) / EW;
+    if (n_groups < warps) warps = (int)n_groups;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      if (n_sm <= 0) n_sm = 148;
     }
-    const unsigned grid = (unsigned)((a.ne + EPC - 1) / EPC);
-    kern<<<grid, K1_THREADS, smem, s>>>(a, rstride, estride);
+    long long grid = (n_groups + warps - 1) / warps;
+    if (grid > n_sm) grid = n_sm;  // persistent: one CTA per SM, each warp strides over the element groups
+    const size_t smem = (size_t)warps * L.bytes;
+    auto kern = k1_u_kernel<D, N, LP, MF, PF>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err != cudaSuccess) return err;
+    kern<<<(unsigned)grid, warps * 32, smem, s>>>(a, L, warps);
     return cudaGetLastError();
   }
 }
@@ -246,16 +440,16 @@ template <int D, int N, int LP> static cudaError_t launch_d_t(const K1Args& a, c
     return cudaGetLastError();
   } else {
     constexpr int EPC = K1_THREADS / LP;
-    const int rstride = k1_rec_stride(GpRecD<D>::SIZE);
-    const int estride = k1_elem_stride(a.P, rstride, LP);
-    const size_t smem = (size_t)EPC * estride * sizeof(double);
+    const SmemLayout L = k1_layout(GpRecD<D>::SIZE, D, N, a.P, true);
+    const size_t smem = (size_t)EPC * L.estride * sizeof(double);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
     auto kern = k1_d_kernel<D, N, LP>;
     if (smem > 48 * 1024) {
       cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (err != cudaSuccess) return err;
     }
     const unsigned grid = (unsigned)((a.ne + EPC - 1) / EPC);
-    kern<<<grid, K1_THREADS, smem, s>>>(a, rstride, estride);
+    kern<<<grid, K1_THREADS, smem, s>>>(a, L);
     return cudaGetLastError();
   }
 }
@@ -276,46 +470,60 @@ cudaError_t launch_k1(const K1Args& a, int mode, cudaStream_t s) {
   return cudaErrorInvalidValue;
 }
 
-// ---- K2: Kt values.  One thread per (row node i, row component j, neighbour p): sums the DB x DB source
-// blocks of node pair (i, nbr[p]) in `elems` order (left fold, like Julia's sparse(), toolkit:202) and writes
-// the dpn consecutive values of CSC column / CSR row (i, j).  Consecutive threads write consecutive memory.
+// ---- K2: Kt values.  One thread per node-pair block (row node i, neighbour p): sums the DB x DB source blocks
+// in `elems` order (left fold, like Julia's sparse(), toolkit:202) and writes DB rows of dpn consecutive values
+// into CSC columns / CSR rows (i, 0..dpn-1).  Consecutive threads (p) write consecutive memory in each row.
 template <int DB> __global__ void __launch_bounds__(256) k2_kernel(const AsmArgs a) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= a.n_blocks) return;
   const int dpn = a.dpn;
-  if (g >= a.n_blocks * dpn) return;
-  const unsigned i = __ldg(a.blk_row + g / dpn);
-  const long long nb0 = __ldg(a.nbr_ptr + i);
-  const int nn = (int)(__ldg(a.nbr_ptr + i + 1) - nb0);
-  const int gl = (int)(g - nb0 * dpn);
-  const int j = gl / nn, p = gl - j * nn;
-  const long long blk = nb0 + p;
-  double acc[DB];
+  const unsigned s0 = __ldg(a.blk_ptr + blk), s1 = __ldg(a.blk_ptr + blk + 1);
+  const unsigned i = __ldg(a.blk_row + blk);
+  double acc[DB * DB];
 #pragma unroll
-  for (int l = 0; l < DB; l++) acc[l] = 0.0;
-  if (j < DB) {
-    const unsigned s0 = __ldg(a.blk_ptr + blk), s1 = __ldg(a.blk_ptr + blk + 1);
-    for (unsigned s = s0; s < s1; s++) {
-      const unsigned code = __ldg(a.src + s);
-      const double* B = a.Ke + (long long)(code >> 1) * (DB * DB);
-      if (code & 1u) {
+  for (int t = 0; t < DB * DB; t++) acc[t] = 0.0;
+  unsigned code = s0 < s1 ? __ldg(a.src + s0) : 0u;
+  for (unsigned s = s0; s < s1; s++) {
+    const unsigned cur = code;
+    if (s + 1 < s1) code = __ldg(a.src + s + 1);  // prefetch the next source while this one is summed
+    const double* B = a.Ke + (long long)(cur >> 1) * (DB * DB);
+    double v[DB * DB];
 #pragma unroll
-        for (int l = 0; l < DB; l++) acc[l] += B[l * DB + j];
-      } else {
+    for (int t = 0; t < DB * DB; t++) v[t] = B[t];
+    if (cur & 1u) {
 #pragma unroll
-        for (int l = 0; l < DB; l++) acc[l] += B[j * DB + l];
-      }
+      for (int j = 0; j < DB; j++)
+#pragma unroll
+        for (int l = 0; l < DB; l++) acc[j * DB + l] += v[l * DB + j];
+    } else {
+#pragma unroll
+      for (int t = 0; t < DB * DB; t++) acc[t] += v[t];
     }
   }
-  double* out = a.nzval + nb0 * (dpn * dpn) + (long long)j * dpn * nn + (long long)p * dpn;
+  const long long nb0 = __ldg(a.nbr_ptr + i);
+  const int nn = (int)(__ldg(a.nbr_ptr + i + 1) - nb0);
+  const int p = (int)(blk - nb0);
+  double* out = a.nzval + nb0 * (dpn * dpn) + (long long)p * dpn;
   int nz = 0;
 #pragma unroll
-  for (int l = 0; l < DB; l++) {
-    out[l] = acc[l];
-    nz += (acc[l] == 0.0);
+  for (int j = 0; j < DB; j++) {
+    double* row = out + (long long)j * dpn * nn;
+#pragma unroll
+    for (int l = 0; l < DB; l++) {
+      row[l] = acc[j * DB + l];
+      nz += (acc[j * DB + l] == 0.0);
+    }
+    for (int l = DB; l < dpn; l++) {
+      row[l] = 0.0;
+      nz++;
+    }
   }
-  for (int l = DB; l < dpn; l++) {
-    out[l] = 0.0;
-    nz++;
+  for (int j = DB; j < dpn; j++) {
+    double* row = out + (long long)j * dpn * nn;
+    for (int l = 0; l < dpn; l++) {
+      row[l] = 0.0;
+      nz++;
+    }
   }
   if (nz) atomicAdd(a.n_zero, (unsigned long long)nz);  // integer atomic: order-independent
 }
@@ -340,7 +548,7 @@ cudaError_t launch_k2(const AsmArgs& a, bool want_K, cudaStream_t s) {
   if (want_K) {
     cudaError_t err = cudaMemsetAsync(a.n_zero, 0, sizeof(unsigned long long), s);
     if (err != cudaSuccess) return err;
-    const long long nt = a.n_blocks * a.dpn;
+    const long long nt = a.n_blocks;
     if (nt > 0) {
       const unsigned grid = (unsigned)((nt + 255) / 256);
       switch (a.DB) {

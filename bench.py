@@ -170,7 +170,9 @@ def run_ours(args):
     ne_local = batch.ne
     ne_total = ne_local * world
 
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: the plan launches on it, so torch.cuda.Event timing sees the kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     plan.set_stream(stream.cuda_stream)
     u_pin = torch.from_numpy(np.ascontiguousarray(u.T)).pin_memory()      # [node][comp] == column-major 3 x nNodes
     u_dev = u_pin.cuda(non_blocking=True)

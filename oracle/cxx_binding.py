@@ -155,6 +155,16 @@ def make_phi_r_Kt(batches, u, mode=M_ELASTIC, d=None, hist=None, nthreads=0, tim
     for i, b in enumerate(batches):
         h = None if hist is None else hist[i]
         v, g, H = elem_duals(b.kind, b.D, b.P, b.N, b.mat, b.nodes, b.gradN, b.wgt, b.Nval, mode, u, d, h, nthreads, **kw)
+        if mode != M_PF_D and u.shape[0] > b.D:
+            # the reference seeds every row of u[:, nodes] (elasticelements.jl:217) but getF reads rows 1:D only
+            # (toolkit:13): the extra dofs carry exact-zero derivatives.  Expand (D*N) -> (dpn*N).
+            dpn_, D_, N_ = u.shape[0], b.D, b.N
+            keep = (np.arange(N_)[:, None] * dpn_ + np.arange(D_)[None, :]).reshape(-1)
+            g2 = np.zeros((g.shape[0], dpn_ * N_))
+            H2 = np.zeros((H.shape[0], dpn_ * N_, dpn_ * N_))
+            g2[:, keep] = g
+            H2[:, keep[:, None], keep[None, :]] = H
+            g, H = g2, H2
         vals.append(v), gs.append(g), Hs.append(H), nds.append(np.asarray(b.nodes, dtype=np.int64))
     t1 = time.perf_counter()
     if mode == M_PF_D:

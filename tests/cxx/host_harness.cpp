@@ -40,17 +40,18 @@ template <int D, int N, int MF, bool PF>
 static void element_u_t(const MatDev& m, int P, const double* gN, const double* wgt, const double* Nv, const double* ue,
                         const double* de, double* phi, double* re, double* Ke) {
   using R = GpRec<D>;
-  std::vector<double> recs((size_t)P * R::SIZE);
+  constexpr int RS = R::SIZE + 1;  // record capacity (written in pairs)
+  std::vector<double> recs((size_t)P * RS), GS((size_t)P * D * N);
   for (int gp = 0; gp < P; gp++) {
-    double G[D * N];
+    double* G = GS.data() + (size_t)gp * D * N;  // [gp][k][a], the layout the kernels keep in shared memory
     for (int k = 0; k < D; k++)
       for (int a = 0; a < N; a++) G[k * N + a] = gN[(k * P + gp) * N + a];
-    gauss_point_u<D, N, MF, PF>(m, G, ue, de, PF ? Nv + gp * N : nullptr, wgt[gp], recs.data() + (size_t)gp * R::SIZE);
+    gauss_point_u<D, N, MF, PF>(m, G, ue, de, PF ? Nv + gp * N : nullptr, wgt[gp], recs.data() + (size_t)gp * RS);
   }
   double s = 0.0;
-  for (int gp = 0; gp < P; gp++) s += recs[(size_t)gp * R::SIZE + R::OFF_PSI];
+  for (int gp = 0; gp < P; gp++) s += recs[(size_t)gp * RS + R::OFF_PSI];
   *phi = s;
-  for (int q = 0; q < N; q++) column_u<D, N>(q, P, recs.data(), R::SIZE, gN, Ke, re);
+  for (int q = 0; q < N; q++) column_u<D, N, 0, ScalarMem>(q, P, recs.data(), RS, gN, N, P * N, Ke, re);  // raw [k][gp][a] layout
 }
 
 template <int D, int N>
@@ -72,9 +73,9 @@ template <int D, int N>
 static void element_d_t(const MatDev& m, int P, const double* gN, const double* wgt, const double* Nv, const double* ue,
                         const double* de, double* hist, double* phi, double* re, double* Ke) {
   constexpr int RS = GpRecD<D>::SIZE;
-  std::vector<double> recs((size_t)P * RS);
+  std::vector<double> recs((size_t)P * RS), GS((size_t)P * D * N);
   for (int gp = 0; gp < P; gp++) {
-    double G[D * N];
+    double* G = GS.data() + (size_t)gp * D * N;
     for (int k = 0; k < D; k++)
       for (int a = 0; a < N; a++) G[k * N + a] = gN[(k * P + gp) * N + a];
     gauss_point_d<D, N>(m, G, Nv + gp * N, ue, de, wgt[gp], hist ? hist + 2 * gp : nullptr, recs.data() + (size_t)gp * RS);
@@ -82,7 +83,7 @@ static void element_d_t(const MatDev& m, int P, const double* gN, const double* 
   double s = 0.0;
   for (int gp = 0; gp < P; gp++) s += recs[(size_t)gp * RS + 2];
   *phi = s;
-  for (int q = 0; q < N; q++) column_d<D, N>(q, P, recs.data(), RS, gN, Nv, Ke, re);
+  for (int q = 0; q < N; q++) column_d<D, N>(q, P, recs.data(), RS, GS.data(), D * N, Nv, N, Ke, re);
 }
 
 extern "C" {
