@@ -56,6 +56,12 @@ template <int D> struct GpRecD {
 // 16-byte shared-memory access helpers.  A GP record / gradient tile that lives in shared memory is read
 // with LDS.128 (a quarter-warp = the 8 lanes of one element read the same address: one broadcast
 // wavefront); a record held in registers (thread-per-element path) or on the host is read as scalars.
+// compiler-only fence: bounds how far shared-memory loads are hoisted (register pressure of phase 2)
+#ifdef __CUDA_ARCH__
+#define AD4SM_SCHED_FENCE() asm volatile("" ::: "memory")
+#else
+#define AD4SM_SCHED_FENCE() ((void)0)
+#endif
 #ifdef __CUDACC__
 struct VecMem {
   const double* p;  // 16-byte aligned
@@ -92,10 +98,11 @@ template <int D, int N> AD4SM_DI void deformation_gradient(const double* G, cons
 // phase 1, u-dual paths (elastic and phase-field u-phase): writes the GP record.
 //   G [D][N] physical shape-function gradients at this Gauss point, ue [N][D] nodal displacements,
 //   de [N] nodal phase field and Nv [N] shape-function values (PF only), w = elem.wgt[gp].
+//   psi_out: nullptr -> w·ψ is stored in the record (slot OFF_PSI); else it is written there and the record holds
+//            only w·A and w·P (NA + DD doubles, an even count for D = 2, 3).
 template <int D, int N, int MF, bool PF>
-AD4SM_DI void gauss_point_u(const MatDev& m, const double* G, const double* ue, const double* de, const double* Nv,
-                            double w, double* rec) {
-  using R = GpRec<D>;
+AD4SM_DI void gauss_point_u_eval(const MatDev& m, const double* G, const double* ue, const double* de, const double* Nv,
+                                 Tangent<D>& t) {
   double F[D * D];
   deformation_gradient<D, N>(G, ue, F);
   PfPoint pf;
@@ -114,14 +121,32 @@ AD4SM_DI void gauss_point_u(const MatDev& m, const double* G, const double* ue, 
     pf.d = dv;
     pf.gd2 = g2;
   }
-  Tangent<D> t;
   material_tangent<D, MF>(m, F, PF ? &pf : nullptr, t);
-  // record = [w·A (NA) | w·P (DD) | w·ψ], written in 16-byte pairs (rec is 16-byte aligned, capacity SIZE+1)
+}
+
+// record = [w·A (NA) | w·P (DD) | w·ψ], written in 16-byte pairs (rec is 16-byte aligned, capacity SIZE+1)
+template <int D> AD4SM_DI void gp_record_store(const Tangent<D>& t, double w, double* rec, double* psi_out) {
+  using R = GpRec<D>;
   auto val = [&](int i) -> double {
     return i < R::NA ? w * t.A[i] : (i < R::NA + R::DD ? w * t.P[i - R::NA] : (i == R::OFF_PSI ? w * t.psi : 0.0));
   };
+  if (psi_out) {
+    static_assert((R::NA + R::DD) % 2 == 0, "record body must be a whole number of 16-byte pairs");
+    *psi_out = w * t.psi;
 #pragma unroll
-  for (int i2 = 0; i2 < (R::SIZE + 1) / 2; i2++) store2(rec, i2, val(2 * i2), val(2 * i2 + 1));
+    for (int i2 = 0; i2 < (R::NA + R::DD) / 2; i2++) store2(rec, i2, val(2 * i2), val(2 * i2 + 1));
+  } else {
+#pragma unroll
+    for (int i2 = 0; i2 < (R::SIZE + 1) / 2; i2++) store2(rec, i2, val(2 * i2), val(2 * i2 + 1));
+  }
+}
+
+template <int D, int N, int MF, bool PF>
+AD4SM_DI void gauss_point_u(const MatDev& m, const double* G, const double* ue, const double* de, const double* Nv,
+                            double w, double* rec, double* psi_out = nullptr) {
+  Tangent<D> t;
+  gauss_point_u_eval<D, N, MF, PF>(m, G, ue, de, Nv, t);
+  gp_record_store<D>(t, w, rec, psi_out);
 }
 
 // phase 1, d-dual path (makeϕrKt_d, phasefieldelements.jl:239-262; energies phasefieldmaterials.jl:20-135).
@@ -227,7 +252,6 @@ AD4SM_DI void column_u_acc(int q, int Prt, const double* recs, int rstride, cons
   const int P = PT ? PT : Prt;
   constexpr int DD = D * D;
   constexpr int NO = N / 2 + 1;  // max offsets per column
-  const int no = n_offsets(N, q);
 #pragma unroll
   for (int o = 0; o < NO; o++)
 #pragma unroll
@@ -246,17 +270,32 @@ AD4SM_DI void column_u_acc(int q, int Prt, const double* recs, int rstride, cons
 #pragma unroll
       for (int k = 0; k < D; k++) rq[j] += rec(R::OFF_P + k * D + j) * gb[k];
     if (want_K) {
-      double T[DD][D];
-      tangent_times_gradient<D>(rec, gb, T);
+      // one block column l at a time, so that only D*D intermediate values are live next to the accumulators:
+      //   T_l[(k,j)] = Σ_m A_(kj)(ml) ∇N_q,m ;   K(a,q)[j][l] += Σ_k ∇N_a,k T_l[(k,j)]
 #pragma unroll
-      for (int o = 0; o < NO; o++) {
-        if (o < no) {
+      for (int l = 0; l < D; l++) {
+        AD4SM_SCHED_FENCE();  // keep the record loads of one column from being hoisted over the previous one
+        double Tl[DD];
+#pragma unroll
+        for (int I = 0; I < DD; I++) {
+          double t = 0.0;
+#pragma unroll
+          for (int m = 0; m < D; m++) t += rec(pk(I, m * D + l)) * gb[m];
+          Tl[I] = t;
+        }
+        // every lane accumulates all NO offsets: for even N the o = N/2 block of the columns q >= N/2 is a
+        // duplicate that is never stored, but skipping it would only add a divergent branch (the warp issues the
+        // instructions for the other lanes anyway)
+#pragma unroll
+        for (int o = 0; o < NO; o++) {
           int a = q + o;
           if (a >= N) a -= N;
-          double ga[D];
 #pragma unroll
-          for (int k = 0; k < D; k++) ga[k] = g[k * kstride + a];
-          add_block<D>(ga, T, acc[o]);
+          for (int k = 0; k < D; k++) {
+            const double gak = g[k * kstride + a];
+#pragma unroll
+            for (int j = 0; j < D; j++) acc[o][j * D + l] += gak * Tl[k * D + j];
+          }
         }
       }
     }

@@ -88,6 +88,17 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {  // SASS: LDGSTS
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// shared -> global bulk copy (TMA store, SASS: UBLKCP); completion tracked by the issuing thread's bulk groups
+__device__ __forceinline__ void bulk_store(void* dst, unsigned src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -97,48 +108,58 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 struct WarpLayout {
   int rstride;          // doubles between GP records
   int rec_el;           // bytes of records per element (P * rstride * 8)
-  int g_off[2], g_el;   // ∇N stage, element stride in bytes (raw [k][gp][a] + skew)
-  int w_off[2];         // wgt stage [EW][P] doubles
-  int n_off[2];         // node ids stage [EW][N] int32
-  int v_off[2];         // shape-function values stage [EW][P][N] doubles (phase field)
-  int bar_off;          // 2 x 8-byte mbarriers
-  int kout_el;          // epilogue staging stride per element (bytes); 0 = store blocks directly
+  // two stages each; stage s lives at off + s * stg (plain arithmetic: indexing an array member of a kernel
+  // parameter with a run-time index makes the compiler copy the struct to slow local memory)
+  int g_off, g_stg, g_el;  // ∇N stage, element stride in bytes (raw [k][gp][a] + skew)
+  int w_off, w_stg;        // wgt stage [EW][P] doubles
+  int n_off, n_stg;        // node ids stage [EW][N] int32
+  int v_off, v_stg;        // shape-function values stage [EW][P][N] doubles (phase field)
+  int u_off, u_el;      // gathered nodal u (and d) of one element group: [EW][N*D (+N)] doubles, filled by cp.async
+  int psi_off;          // [EW][P] w·ψ of the Gauss points
+  int bar_off;          // 4 x 8-byte mbarriers: [0,1] ∇N/wgt/N stages, [2,3] node-id stages (loaded two groups ahead)
+  int kout_el;          // epilogue staging stride per element (bytes): blocks, then r; 0 = store directly
+  int re_off;           // byte offset of the element residual inside its epilogue staging
   int bytes;            // slice size, multiple of 128
 };
 static inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 static WarpLayout k1p_layout(int D, int N, int P, int LP, bool pf) {
   WarpLayout L;
   const int EW = 32 / LP, DD = D * D, NPB = n_pair_blocks(N);
-  L.rstride = odd_units_stride(DD * (DD + 1) / 2 + DD + 1);  // GpRec<D>::SIZE
+  L.rstride = odd_units_stride(DD * (DD + 1) / 2 + DD);  // w·A and w·P; w·ψ lives in its own small array
   L.rec_el = P * L.rstride * 8;
-  const int min_scratch = (N * D + N) * 8;  // u / d gather scratch aliases the records
-  if (L.rec_el < min_scratch) L.rec_el = rup(min_scratch, 16);
+  // phase 2 broadcasts a record chunk to the lanes of each element with LDS.128: the EW elements of a warp must sit
+  // in different 16-byte bank groups, i.e. the element stride must be an odd number of 16-byte units
+  if (((L.rec_el >> 4) & 1) == 0) L.rec_el += 16;
   int off = EW * L.rec_el;
   L.g_el = D * P * N * 8;
   if (LP == 8 && (L.g_el % 128) == 0) L.g_el += 64;  // half-warp = 2 elements read ∇N with LDS.64: skew by 64 B
-  for (int s = 0; s < 2; s++) {
-    L.g_off[s] = off;
-    off += EW * L.g_el;
-  }
-  for (int s = 0; s < 2; s++) {
-    L.w_off[s] = off;
-    off += rup(EW * P * 8, 16);
-  }
-  for (int s = 0; s < 2; s++) {
-    L.n_off[s] = off;
-    off += rup(EW * N * 4, 16);
-  }
-  for (int s = 0; s < 2; s++) {
-    L.v_off[s] = off;
-    if (pf) off += rup(EW * P * N * 8, 16);
-  }
+  L.g_off = off;
+  L.g_stg = EW * L.g_el;
+  off += 2 * L.g_stg;
+  L.w_off = off;
+  L.w_stg = rup(EW * P * 8, 16);
+  off += 2 * L.w_stg;
+  L.n_off = off;
+  L.n_stg = rup(EW * N * 4, 16);
+  off += 2 * L.n_stg;
+  L.v_off = off;
+  L.v_stg = pf ? rup(EW * P * N * 8, 16) : 0;
+  off += 2 * L.v_stg;
+  L.u_el = rup((N * D + (pf ? N : 0)) * 8, 16);
+  if (((L.u_el >> 4) & 1) == 0) L.u_el += 16;  // odd number of 16-byte units: conflict-free chunk reads
+  L.u_off = off;  // one buffer: it is consumed into registers before the next group's gather is issued
+  off += EW * L.u_el;
+  L.psi_off = off;
+  off += rup(EW * P * 8, 16);
   L.bar_off = off;
-  off += 16;
+  off += 32;
   L.bytes = rup(off, 128);
-  // coalesced epilogue: stage the element blocks in the (dead) record region when they fit
+  // epilogue: the element blocks and residual are staged in the (dead) record region when they fit, and leave
+  // with one bulk copy each (16-byte granularity)
   L.kout_el = 0;
-  if ((NPB * DD) % 2 == 0) {
-    int k = NPB * DD * 8;
+  L.re_off = NPB * DD * 8;
+  if ((NPB * DD) % 2 == 0 && (N * D) % 2 == 0) {
+    int k = L.re_off + N * D * 8;
     if (LP == 8)
       while (k % 128 != 64) k += 16;
     if (k <= L.rec_el) L.kout_el = k;
@@ -146,84 +167,88 @@ static WarpLayout k1p_layout(int D, int N, int P, int LP, bool pf) {
   return L;
 }
 
-// ---- K1, u-dual, persistent, LP lanes per element, TMA-staged inputs ------------------------------
+// ---- phase 1 of the persistent K1: one Gauss point per lane ----------------------------------------------
+// Register-allocation note (ptxas 12.9): both phases are called by ALL lanes of the warp, unconditionally, with the
+// lane predicates passed in.  Wrapping them in `if (valid)` / `if (active)` made the allocator keep 12 phase-2
+// accumulators in local memory inside the FP64-dense loop although ~80 registers were free; written this way the
+// kernel needs 250 registers and no local memory at all.
+// Operands are read in 16-byte chunks (one node pair of a [gp] row).  Lane q starts at chunk rho(q): the 8 lanes
+// of a Hex8 element read rows 64 B apart, and the rotation spreads them over all eight 16-byte bank groups
+// (conflict-free LDS.128).  Sums over nodes are permutation-invariant as long as G, u, d and N use the same node
+// order, so no un-rotation is needed.
+// Called by ALL lanes of the warp (it contains warp syncs).  After the nodal values are in registers it starts the
+// asynchronous gather (cp.async) of the NEXT group's nodal u into the same buffer, so that it flies during the rest
+// of the iteration.
+//   ng_ids: this lane's element row of node ids of the next group (shared memory), nullptr = no next group
+//   ng_dst: shared address of this lane's element row in the u buffer
 template <int D, int N, int LP, int MF, bool PF>
-__global__ void __launch_bounds__(256, 1) k1_u_kernel(const K1Args a, const WarpLayout L, const int warps_per_cta) {
-  using R = GpRec<D>;
-  constexpr int EW = 32 / LP;
-  constexpr int DD = D * D;
-  constexpr int NPB = n_pair_blocks(N);
-  constexpr int NO = N / 2 + 1;
-  extern __shared__ __align__(128) unsigned char smraw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* ws = smraw + (size_t)warp * L.bytes;
-  const int el = lane / LP, q = lane % LP;
-  const int P = a.P;
-  const long long n_groups = (a.ne + EW - 1) / EW;
-  const long long gstep = (long long)gridDim.x * warps_per_cta;
-  const unsigned bar0 = smem_u32(ws + L.bar_off);
-  if (lane == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
-    fence_mbar_init();
-  }
-  __syncwarp();
-
-  auto issue = [&](long long grp, int s) {  // lane 0: TMA bulk copies of one element group into stage s
-    const long long e0 = grp * EW;
-    const int cnt = (int)((a.ne - e0) < EW ? (a.ne - e0) : EW);
-    const unsigned bar = bar0 + 8 * s;
-    const unsigned gbytes = (unsigned)(D * P * N * 8);
-    const unsigned wbytes = (unsigned)((cnt * P * 8 + 15) & ~15), nbytes = (unsigned)((cnt * N * 4 + 15) & ~15);
-    const unsigned vbytes = PF ? (unsigned)((cnt * P * N * 8 + 15) & ~15) : 0u;
-    fence_proxy_async();
-    mbar_expect_tx(bar, cnt * gbytes + wbytes + nbytes + vbytes);
-    for (int i = 0; i < cnt; i++)
-      tma_load_1d(smem_u32(ws + L.g_off[s] + i * L.g_el), a.gradN + (e0 + i) * (long long)(D * P * N), gbytes, bar);
-    tma_load_1d(smem_u32(ws + L.w_off[s]), a.wgt + e0 * P, wbytes, bar);
-    tma_load_1d(smem_u32(ws + L.n_off[s]), a.nodes + e0 * N, nbytes, bar);
-    if (PF) tma_load_1d(smem_u32(ws + L.v_off[s]), a.Nval + e0 * (long long)(P * N), vbytes, bar);
-  };
-
-  long long grp = (long long)blockIdx.x * warps_per_cta + warp;
-  if (lane == 0 && grp < n_groups) issue(grp, 0);
-  for (int it = 0; grp < n_groups; grp += gstep, it++) {
-    const int s = it & 1;
-    if (lane == 0 && grp + gstep < n_groups) issue(grp + gstep, s ^ 1);
-    mbar_wait(bar0 + 8 * s, (unsigned)((it >> 1) & 1));
-
-    const long long e = grp * EW + el;
-    const bool valid = e < a.ne;
-    const bool active = valid && q < N;
-    const long long slot = a.slot0 + e;
-    double* recs = reinterpret_cast<double*>(ws + (size_t)el * L.rec_el);
-    const double* gS = reinterpret_cast<const double*>(ws + L.g_off[s] + (size_t)el * L.g_el);
-    const double* wS = reinterpret_cast<const double*>(ws + L.w_off[s]) + el * P;
-    const int* nS = reinterpret_cast<const int*>(ws + L.n_off[s]) + el * N;
-    const double* vS = reinterpret_cast<const double*>(ws + L.v_off[s]) + el * P * N;
-
-    // gather: lane q fetches node q's displacement (and phase field) into the element scratch
-    if (active) {
-      const long long node = nS[q];
+__device__ __forceinline__ void k1_phase1(const MatDev* mat, int q, bool valid, int P, int rstride, const double* uS,
+                                       const double* gS, const double* vS, const double* wS, double* recs, double* psiS,
+                                       const int* ng_ids, unsigned ng_dst, const double* u, const double* dfield, int dpn) {
+  constexpr bool VEC = (N % 2 == 0);
+  constexpr int CH = N / 2;
+  const int rho = (N == 8) ? ((q >> 1) & 3) : 0;
+  double ue[N * D], de[N];
+  if (valid) {
+    if constexpr (VEC) {
 #pragma unroll
-      for (int j = 0; j < D; j++) recs[q * D + j] = __ldg(a.u + node * a.dpn + j);
-      if (PF) recs[N * D + q] = __ldg(a.dfield + node);
-    }
-    __syncwarp();
-    double ue[N * D], de[N];
-    if (valid) {
+      for (int c = 0; c < CH; c++) {
+        int pc = c + rho;
+        if (pc >= CH) pc -= CH;
+        const double2* src = reinterpret_cast<const double2*>(uS + 2 * pc * D);
 #pragma unroll
-      for (int i = 0; i < N * D; i++) ue[i] = recs[i];
+        for (int t = 0; t < D; t++) {
+          const double2 v = src[t];
+          ue[2 * c * D + 2 * t] = v.x;
+          ue[2 * c * D + 2 * t + 1] = v.y;
+        }
+        if (PF) {
+          const double2 v = *reinterpret_cast<const double2*>(uS + N * D + 2 * pc);
+          de[2 * c] = v.x;
+          de[2 * c + 1] = v.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N * D; i++) ue[i] = uS[i];
       if (PF) {
 #pragma unroll
-        for (int n = 0; n < N; n++) de[n] = recs[N * D + n];
+        for (int n = 0; n < N; n++) de[n] = uS[N * D + n];
       }
     }
-    __syncwarp();
-    // phase 1: one Gauss point per lane
-    if (valid) {
-      for (int gp = q; gp < P; gp += LP) {
-        double G[D * N], Nv[N];
+  }
+  __syncwarp();  // the u buffer has been consumed
+  if (ng_ids && q < N) {
+    const long long node = ng_ids[q];
+#pragma unroll
+    for (int j = 0; j < D; j++) cp_async8(ng_dst + (q * D + j) * 8, u + node * dpn + j);
+    if (PF) cp_async8(ng_dst + (N * D + q) * 8, dfield + node);
+  }
+  cp_async_commit();
+  const MatDev m = *mat;
+  for (int gp0 = 0; gp0 < P; gp0 += LP) {  // warp-uniform trip count
+    const int gp = gp0 + q;
+    const bool on = valid && gp < P;
+    if (on) {
+      double G[D * N], Nv[N];
+      if constexpr (VEC) {
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+          int pc = c + rho;
+          if (pc >= CH) pc -= CH;
+#pragma unroll
+          for (int k = 0; k < D; k++) {
+            const double2 v = *reinterpret_cast<const double2*>(gS + (k * P + gp) * N + 2 * pc);
+            G[k * N + 2 * c] = v.x;
+            G[k * N + 2 * c + 1] = v.y;
+          }
+          if (PF) {
+            const double2 v = *reinterpret_cast<const double2*>(vS + gp * N + 2 * pc);
+            Nv[2 * c] = v.x;
+            Nv[2 * c + 1] = v.y;
+          }
+        }
+      } else {
 #pragma unroll
         for (int k = 0; k < D; k++)
 #pragma unroll
@@ -232,42 +257,156 @@ __global__ void __launch_bounds__(256, 1) k1_u_kernel(const K1Args a, const Warp
 #pragma unroll
           for (int n = 0; n < N; n++) Nv[n] = vS[gp * N + n];
         }
-        gauss_point_u<D, N, MF, PF>(a.mat, G, ue, de, Nv, wS[gp], recs + gp * L.rstride);
       }
+      gauss_point_u<D, N, MF, PF>(m, G, ue, de, Nv, wS[gp], recs + gp * rstride, psiS + gp);
     }
+  }
+}
+
+// ---- phase 2 of the persistent K1: one column node per lane ------------------------------------------------
+// Called by ALL lanes of the warp (inactive lanes compute on valid shared memory and store nothing): see the note
+// at k1_phase1, and the stores may alias the records other lanes are still reading: accumulate, __syncwarp, store.
+template <int D, int N>
+__device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active, bool want_K, const double* recs,
+                                       const double* gS, double* kout, double* rout) {
+  double acc[N / 2 + 1][D * D], rq[D];
+  column_u_acc<D, N, 0, VecMem>(q, P, recs, rstride, gS, N, P * N, want_K, acc, rq);
+  __syncwarp();
+  if (active) {
+    if (want_K) column_u_store<D, N>(q, acc, kout);
+#pragma unroll
+    for (int j = 0; j < D; j++) rout[q * D + j] = rq[j];
+  }
+}
+
+// ---- K1, u-dual, persistent, LP lanes per element, TMA-staged inputs ------------------------------
+template <int D, int N, int LP, int MF, bool PF>
+__global__ void __launch_bounds__(256, 1)
+    k1_u_kernel(const __grid_constant__ K1Args a, const WarpLayout L, const int warps_per_cta) {
+  using R = GpRec<D>;
+  constexpr int EW = 32 / LP;
+  constexpr int DD = D * D;
+  constexpr int NPB = n_pair_blocks(N);
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* const ws0 = smraw + (size_t)warp * L.bytes;
+  const int el = lane / LP, q = lane % LP;
+  const int P = a.P;
+  const long long n_groups = (a.ne + EW - 1) / EW;
+  const long long gstep = (long long)gridDim.x * warps_per_cta;
+  const unsigned bar0 = smem_u32(ws0 + L.bar_off);
+  if (lane == 0) {
+    for (int i = 0; i < 4; i++) mbar_init(bar0 + 8 * i, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  unsigned char* const ws = ws0;
+
+  // lane 0: TMA bulk copies of one element group into stage s (∇N per element, wgt, N)
+  auto issue = [&](long long grp, int s) {
+    const long long e0 = grp * EW;
+    const int cnt = (int)((a.ne - e0) < EW ? (a.ne - e0) : EW);
+    const unsigned bar = bar0 + 8 * s;
+    const unsigned gbytes = (unsigned)(D * P * N * 8);
+    const unsigned wbytes = (unsigned)((cnt * P * 8 + 15) & ~15);
+    const unsigned vbytes = PF ? (unsigned)((cnt * P * N * 8 + 15) & ~15) : 0u;
+    fence_proxy_async();
+    mbar_expect_tx(bar, cnt * gbytes + wbytes + vbytes);
+    for (int i = 0; i < cnt; i++)
+      tma_load_1d(smem_u32(ws + (L.g_off + (s) * L.g_stg) + i * L.g_el), a.gradN + (e0 + i) * (long long)(D * P * N), gbytes, bar);
+    tma_load_1d(smem_u32(ws + (L.w_off + (s) * L.w_stg)), a.wgt + e0 * P, wbytes, bar);
+    if (PF) tma_load_1d(smem_u32(ws + (L.v_off + (s) * L.v_stg)), a.Nval + e0 * (long long)(P * N), vbytes, bar);
+  };
+  // lane 0: node ids of group grp into id stage s.  They run one group further ahead than the rest, so that the
+  // u gather of group i+1 can start at the beginning of iteration i.
+  auto issue_ids = [&](long long grp, int s) {
+    const long long e0 = grp * EW;
+    const int cnt = (int)((a.ne - e0) < EW ? (a.ne - e0) : EW);
+    const unsigned nbytes = (unsigned)((cnt * N * 4 + 15) & ~15);
+    fence_proxy_async();
+    mbar_expect_tx(bar0 + 16 + 8 * s, nbytes);
+    tma_load_1d(smem_u32(ws + (L.n_off + (s) * L.n_stg)), a.nodes + e0 * N, nbytes, bar0 + 16 + 8 * s);
+  };
+
+  long long grp = (long long)blockIdx.x * warps_per_cta + warp;
+  if (grp < n_groups) {
+    if (lane == 0) {
+      issue(grp, 0);
+      issue_ids(grp, 0);
+      if (grp + gstep < n_groups) issue_ids(grp + gstep, 1);
+    }
+    mbar_wait(bar0 + 16, 0u);
+    const long long e = grp * EW + el;  // first group: gather its u synchronously with the pipeline start
+    if (e < a.ne && q < N) {
+      const long long node = (reinterpret_cast<const int*>(ws + (L.n_off + (0) * L.n_stg)) + el * N)[q];
+      const unsigned dst = smem_u32(ws + L.u_off + el * L.u_el);
+#pragma unroll
+      for (int j = 0; j < D; j++) cp_async8(dst + (q * D + j) * 8, a.u + node * a.dpn + j);
+      if (PF) cp_async8(dst + (N * D + q) * 8, a.dfield + node);
+    }
+    cp_async_commit();
+  }
+  for (int it = 0; grp < n_groups; grp += gstep, it++) {
+    const int s = it & 1;
+    const bool has_next = grp + gstep < n_groups;
+    if (lane == 0) {
+      if (has_next) issue(grp + gstep, s ^ 1);
+      if (grp + 2 * gstep < n_groups) issue_ids(grp + 2 * gstep, s);  // id stage s held this group's ids: gather done
+    }
+    mbar_wait(bar0 + 8 * s, (unsigned)((it >> 1) & 1));                        // this group's ∇N, wgt, N
+    if (has_next) mbar_wait(bar0 + 16 + 8 * (s ^ 1), (unsigned)(((it + 1) >> 1) & 1));  // next group's node ids
+    cp_async_wait_all();                                                        // this group's u
+    if (lane == 0) bulk_wait_read_all();  // the previous bulk stores have read the staging area (aliases the records)
     __syncwarp();
-    // phase 2: one column node per lane
-    double acc[NO][DD], rq[D];
-    if (active) column_u_acc<D, N, 0, VecMem>(q, P, recs, L.rstride, gS, N, P * N, a.want_K != 0, acc, rq);
+
+    const long long e = grp * EW + el;
+    const bool valid = e < a.ne;
+    const bool active = valid && q < N;
+    const long long slot = a.slot0 + e;
+    double* recs = reinterpret_cast<double*>(ws + (size_t)el * L.rec_el);
+    const double* uS = reinterpret_cast<const double*>(ws + L.u_off + (size_t)el * L.u_el);
+    double* psiS = reinterpret_cast<double*>(ws + L.psi_off) + el * P;
+    const double* gS = reinterpret_cast<const double*>(ws + (L.g_off + (s) * L.g_stg) + (size_t)el * L.g_el);
+    const double* wS = reinterpret_cast<const double*>(ws + (L.w_off + (s) * L.w_stg)) + el * P;
+    const double* vS = reinterpret_cast<const double*>(ws + (L.v_off + (s) * L.v_stg)) + el * P * N;
+
+    // phase 1: one Gauss point per lane; it also starts the next group's u gather
+    const int* ng_ids =
+        (has_next && (grp + gstep) * EW + el < a.ne) ? reinterpret_cast<const int*>(ws + (L.n_off + (s ^ 1) * L.n_stg)) + el * N : nullptr;
+    k1_phase1<D, N, LP, MF, PF>(&a.mat, q, valid, P, L.rstride, uS, gS, vS, wS, recs, psiS, ng_ids,
+                                smem_u32(ws + L.u_off + el * L.u_el), a.u, a.dfield, a.dpn);
+    __syncwarp();
+
+    // phase 2: one column node per lane; the element blocks and residual go to the
+    // staging area in the (then dead) record region, or straight to global memory when they do not fit
+    const bool staged = a.want_K && L.kout_el;
+    unsigned char* stg = ws + (size_t)el * L.kout_el;
+    double* kout = staged ? reinterpret_cast<double*>(stg) : a.Ke + slot * (long long)(NPB * DD);
+    double* rout = staged ? reinterpret_cast<double*>(stg + L.re_off) : a.re + slot * (long long)(N * D);
+    k1_phase2<D, N>(q, P, L.rstride, active, a.want_K != 0, recs, gS, kout, rout);
     if (valid && q == 0) {  // ϕ_e = Σ_gp w ψ, in Gauss-point order (elasticelements.jl:199-206)
       double ssum = 0.0;
-      for (int gp = 0; gp < P; gp++) ssum += recs[gp * L.rstride + R::OFF_PSI];
+      for (int gp = 0; gp < P; gp++) ssum += psiS[gp];
       a.phie[slot] = ssum;
     }
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < D; j++) a.re[slot * (long long)(N * D) + q * D + j] = rq[j];
-    }
-    __syncwarp();
-    // epilogue: element blocks -> staging
-    if (a.want_K) {
-      if (L.kout_el) {  // transpose through shared memory (the records are dead), then 16-byte coalesced stores
-        if (active) column_u_store<D, N>(q, acc, reinterpret_cast<double*>(ws + (size_t)el * L.kout_el));
-        __syncwarp();
-        constexpr int CPE = NPB * DD / 2;  // 16-byte chunks per element
+    if (staged) {  // one bulk copy (TMA store) per element and array
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
         const long long e0 = grp * EW;
         const int cnt = (int)((a.ne - e0) < EW ? (a.ne - e0) : EW);
-        double2* dst = reinterpret_cast<double2*>(a.Ke + (a.slot0 + e0) * (long long)(NPB * DD));
-        for (int c = lane; c < cnt * CPE; c += 32) {
-          const int ee = c / CPE, off = c - ee * CPE;
-          dst[c] = *reinterpret_cast<const double2*>(ws + (size_t)ee * L.kout_el + (size_t)off * 16);
+        for (int i = 0; i < cnt; i++) {
+          const long long sl = a.slot0 + e0 + i;
+          const unsigned src = smem_u32(ws + (size_t)i * L.kout_el);
+          bulk_store(a.Ke + sl * (long long)(NPB * DD), src, (unsigned)(NPB * DD * 8));
+          bulk_store(a.re + sl * (long long)(N * D), src + L.re_off, (unsigned)(N * D * 8));
         }
-      } else if (active) {
-        column_u_store<D, N>(q, acc, a.Ke + slot * (long long)(NPB * DD));
+        bulk_commit();
       }
     }
     __syncwarp();
   }
+  if (lane == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk stores
 }
 
 // ---- K1, u-dual, one thread per element (P == 1) ------------------------------------------------
