@@ -53,9 +53,13 @@ class ElemBatch:
     Nval: np.ndarray | None = None  # [ne][P][N]  (CP)
     V: np.ndarray | None = None  # [ne]
     orig_index: np.ndarray | None = None  # [ne] position in `elems` (summation order); None = in order
+    halo: bool = False  # mesh-partitioned runs: elements evaluated by another rank (dist.py); gradN/wgt may be None
+    halo_P: int = 0  # number of Gauss points of a halo batch without wgt
 
     def __post_init__(self):
         self.nodes = np.ascontiguousarray(self.nodes, dtype=np.int64)
+        if self.halo and self.gradN is None:
+            return
         self.gradN = np.ascontiguousarray(self.gradN, dtype=np.float64)
         self.wgt = np.ascontiguousarray(self.wgt, dtype=np.float64)
         if self.Nval is not None:
@@ -74,7 +78,7 @@ class ElemBatch:
 
     @property
     def P(self):
-        return self.wgt.shape[1]
+        return self.wgt.shape[1] if self.wgt is not None else self.halo_P
 
     def __len__(self):
         return self.ne
@@ -455,9 +459,10 @@ class Plan:
             for k in range(8):
                 s.mat_params[k] = params[k]
             s.n_elems = b.ne
+            s.batch_flags = capi.BATCH_HALO if b.halo else 0
             s.nodes = b.nodes.ctypes.data
-            s.gradN = b.gradN.ctypes.data
-            s.wgt = b.wgt.ctypes.data
+            s.gradN = b.gradN.ctypes.data if b.gradN is not None else None
+            s.wgt = b.wgt.ctypes.data if b.wgt is not None else None
             s.Nval = b.Nval.ctypes.data if b.Nval is not None else None
             if b.orig_index is not None:
                 oi = np.ascontiguousarray(b.orig_index, dtype=np.int64)
@@ -577,6 +582,20 @@ class Plan:
     def eval_device(self, mode, u_ptr, d_ptr=None, hist_ptr=None):
         capi.check(self._L.ad4sm_eval_device(self._h, mode, C.c_void_p(u_ptr), C.c_void_p(d_ptr) if d_ptr else None,
                                              C.c_void_p(hist_ptr) if hist_ptr else None))
+
+    def eval_elements_device(self, mode, u_ptr, d_ptr=None, hist_ptr=None):
+        """K1 only (non-halo batches): element blocks / residuals / energies -> staging."""
+        capi.check(self._L.ad4sm_eval_elements_device(self._h, mode, C.c_void_p(u_ptr), C.c_void_p(d_ptr) if d_ptr else None,
+                                                      C.c_void_p(hist_ptr) if hist_ptr else None))
+
+    def eval_assemble_device(self, mode):
+        """K2/K3 + ϕ reduction over the staging of all batches (after any interface exchange)."""
+        capi.check(self._L.ad4sm_eval_assemble_device(self._h, mode))
+
+    def staging_view(self, field=capi.FIELD_U):
+        v = capi.StagingView()
+        capi.check(self._L.ad4sm_staging_view_get(self._h, field, C.byref(v)))
+        return v
 
     def sync(self):
         capi.check(self._L.ad4sm_sync(self._h))

@@ -20,12 +20,20 @@ PROF_ELEMENT, PROF_ASSEMBLE, PROF_REDUCE, PROF_GATHER, PROF_NCLASS = 0, 1, 2, 3,
 class Batch(C.Structure):
     _fields_ = [
         ("elem_kind", C.c_int32), ("dim", C.c_int32), ("n_gauss", C.c_int32), ("n_elem_nodes", C.c_int32),
-        ("mat_kind", C.c_int32), ("mat_base", C.c_int32), ("mat_flags", C.c_uint32), ("reserved", C.c_int32),
+        ("mat_kind", C.c_int32), ("mat_base", C.c_int32), ("mat_flags", C.c_uint32), ("batch_flags", C.c_int32),
         ("mat_params", C.c_double * 8),
         ("n_elems", C.c_int64),
         ("nodes", C.c_void_p), ("gradN", C.c_void_p), ("wgt", C.c_void_p), ("Nval", C.c_void_p),
         ("orig_index", C.c_void_p),
     ]
+
+
+BATCH_HALO = 1
+
+
+class StagingView(C.Structure):
+    _fields_ = [("n_slots", C.c_int64), ("ke_width", C.c_int64), ("re_width", C.c_int64),
+                ("Ke_dev", C.c_void_p), ("re_dev", C.c_void_p), ("phie_dev", C.c_void_p)]
 
 
 class DeviceView(C.Structure):
@@ -62,6 +70,9 @@ SIGNATURES = {
     "ad4sm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ad4sm_eval_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ad4sm_device_view_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DeviceView)]),
+    "ad4sm_eval_elements_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ad4sm_eval_assemble_device": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ad4sm_staging_view_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(StagingView)]),
     "ad4sm_sync": (C.c_int, [C.c_void_p]),
     "ad4sm_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "ad4sm_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),

@@ -36,6 +36,7 @@ namespace {
 struct BatchPlan {
   K1Args k;            // device pointers + shape (u/dfield/hist/want_K are filled per evaluation)
   long long hist_off;  // offset (in Gauss points) of the batch in the concatenated history array
+  bool halo;           // AD4SM_BATCH_HALO: staging filled by the exchange step, not by K1
 };
 
 struct FieldOut {
@@ -55,7 +56,7 @@ struct FieldOut {
 };
 
 struct EvSet {
-  cudaEvent_t e[4];
+  cudaEvent_t e[5];  // [0] start, [1] K1 done, [4] assembly start (after any exchange), [2] K2/K3 done, [3] ϕ done
 };
 
 }  // namespace
@@ -81,7 +82,8 @@ struct ad4sm_plan {
   size_t ev_used = 0;
   double prof_ms[AD4SM_PROF_NCLASS] = {0, 0, 0, 0};
   long long prof_launches[AD4SM_PROF_NCLASS] = {0, 0, 0, 0};
-  long long pending_k1 = 0;
+  EvSet* ev_cur = nullptr;  // events of the evaluation in flight between the elements and assemble stages
+  int elements_mode = -1;
 };
 
 template <class T> static int dev_alloc(ad4sm_plan* p, T** ptr, size_t count) {
@@ -171,7 +173,7 @@ void ad4sm_plan_destroy(ad4sm_plan* p) {
     cudaFree(p->field[f].dz_nzval);
   }
   for (auto& s : p->ev_pool)
-    for (int i = 0; i < 4; i++) cudaEventDestroy(s.e[i]);
+    for (int i = 0; i < 5; i++) cudaEventDestroy(s.e[i]);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   delete p;
 }
@@ -191,9 +193,11 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     if (B.n_elem_nodes != N)
       return fail(AD4SM_EINVAL, "all elements must have the same number of dofs (elasticelements.jl:212-214)");
     if (B.dim != D) return fail(AD4SM_EINVAL, "all batches must have the same dimension D");
-    if (B.n_elems < 0 || (B.n_elems > 0 && (!B.nodes || !B.gradN || !B.wgt)))
+    const bool halo = (B.batch_flags & AD4SM_BATCH_HALO) != 0;
+    if (B.n_elems < 0 || (B.n_elems > 0 && (!B.nodes || (!halo && (!B.gradN || !B.wgt)))))
       return fail(AD4SM_EINVAL, "batch arrays missing");
-    if (B.elem_kind == AD4SM_ELEM_CP && B.n_elems > 0 && !B.Nval) return fail(AD4SM_EINVAL, "CPElem batch needs Nval");
+    if (B.elem_kind == AD4SM_ELEM_CP && B.n_elems > 0 && !halo && !B.Nval)
+      return fail(AD4SM_EINVAL, "CPElem batch needs Nval");
     if (B.elem_kind != AD4SM_ELEM_CE && B.elem_kind != AD4SM_ELEM_CP) return fail(AD4SM_EINVAL, "unknown elem_kind");
     std::string why;
     if (mat_family(B, &mfs[b], &why)) return fail(AD4SM_EINVAL, why);
@@ -382,17 +386,20 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       bp.k.mf = mfs[b];
       bp.k.dpn = dofs_per_node;
       bp.hist_off = h0;
-      int* nd = nullptr;
-      TRY(dev_upload(p, &nd, nodes0.data() + (size_t)s0 * N, (size_t)B.n_elems * N));
-      bp.k.nodes = nd;
-      double* x = nullptr;
-      TRY(dev_upload(p, &x, B.gradN, (size_t)B.n_elems * D * B.n_gauss * N));
-      bp.k.gradN = x;
-      TRY(dev_upload(p, &x, B.wgt, (size_t)B.n_elems * B.n_gauss));
-      bp.k.wgt = x;
-      if (B.elem_kind == AD4SM_ELEM_CP) {
-        TRY(dev_upload(p, &x, B.Nval, (size_t)B.n_elems * B.n_gauss * N));
-        bp.k.Nval = x;
+      bp.halo = (B.batch_flags & AD4SM_BATCH_HALO) != 0;
+      if (!bp.halo) {
+        int* nd = nullptr;
+        TRY(dev_upload(p, &nd, nodes0.data() + (size_t)s0 * N, (size_t)B.n_elems * N));
+        bp.k.nodes = nd;
+        double* x = nullptr;
+        TRY(dev_upload(p, &x, B.gradN, (size_t)B.n_elems * D * B.n_gauss * N));
+        bp.k.gradN = x;
+        TRY(dev_upload(p, &x, B.wgt, (size_t)B.n_elems * B.n_gauss));
+        bp.k.wgt = x;
+        if (B.elem_kind == AD4SM_ELEM_CP) {
+          TRY(dev_upload(p, &x, B.Nval, (size_t)B.n_elems * B.n_gauss * N));
+          bp.k.Nval = x;
+        }
       }
       p->batches.push_back(bp);
       s0 += B.n_elems;
@@ -402,6 +409,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
   TRY(dev_alloc(p, &p->Ke, (size_t)ne * NPB * D * D));
   TRY(dev_alloc(p, &p->re, (size_t)ne * N * D));
   TRY(dev_alloc(p, &p->phie, (size_t)ne));
+  CK(cudaMemset(p->phie, 0, sizeof(double) * (size_t)ne));  // HALO slots stay 0: they add nothing to ϕ on this rank
   TRY(dev_alloc(p, &p->partials, (size_t)phi_reduce_partials()));
   TRY(dev_alloc(p, &p->phi_dev, 1));
   TRY(dev_alloc(p, &p->n_zero_dev, 1));
@@ -499,7 +507,7 @@ int ad4sm_set_stream(ad4sm_plan* p, void* cuda_stream) {
 static EvSet* next_events(ad4sm_plan* p) {
   if (p->ev_used == p->ev_pool.size()) {
     EvSet s;
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 5; i++)
       if (cudaEventCreate(&s.e[i]) != cudaSuccess) return nullptr;
     p->ev_pool.push_back(s);
   }
@@ -514,8 +522,10 @@ static int drain_events(ad4sm_plan* p) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, s.e[0], s.e[1]));
     p->prof_ms[AD4SM_PROF_ELEMENT] += ms;
-    CK(cudaEventElapsedTime(&ms, s.e[1], s.e[2]));
+    CK(cudaEventElapsedTime(&ms, s.e[4], s.e[2]));
     p->prof_ms[AD4SM_PROF_ASSEMBLE] += ms;
+    CK(cudaEventElapsedTime(&ms, s.e[1], s.e[4]));
+    p->prof_ms[AD4SM_PROF_GATHER] += ms;  // interface exchange between the element and assembly stages
     CK(cudaEventElapsedTime(&ms, s.e[2], s.e[3]));
     p->prof_ms[AD4SM_PROF_REDUCE] += ms;
   }
@@ -523,27 +533,34 @@ static int drain_events(ad4sm_plan* p) {
   return 0;
 }
 
-int ad4sm_eval_device(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
+static int check_eval_args(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev) {
   if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
   if (mode < 0 || mode > 3) return fail(AD4SM_EINVAL, "mode must be 0..3");
   if (!u_dev) return fail(AD4SM_EINVAL, "u is NULL");
   const bool needs_d = (mode == MODE_PF_U || mode == MODE_PF_D);
   if (needs_d && !d_dev) return fail(AD4SM_EINVAL, "d is NULL");
   if (needs_d && !p->has_cp) return fail(AD4SM_EINVAL, "phase-field evaluation needs CPElem batches");
-  const int field = mode == MODE_PF_D ? AD4SM_FIELD_D : AD4SM_FIELD_U;
-  const bool want_K = mode != MODE_PHI_R;
-  const int kmode = mode == MODE_PHI_R ? MODE_ELASTIC : mode;
   for (const BatchPlan& b : p->batches) {
     const bool is_pf = b.k.mat.kind == MAT_PHASEFIELD;
-    if (needs_d && (!is_pf || !b.k.Nval))
+    if (needs_d && (!is_pf || (!b.k.Nval && !b.halo)))
       return fail(AD4SM_EINVAL, "makeϕrKt(elems,u,d) / makeϕrKt_d need CPElem with a PhaseField material");
     if (!needs_d && is_pf)
       return fail(AD4SM_EINVAL, "PhaseField material evaluated without d: the reference has no getϕ(F, ::PhaseField)");
   }
+  return 0;
+}
+
+int ad4sm_eval_elements_device(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
+  int rc = check_eval_args(p, mode, u_dev, d_dev);
+  if (rc) return rc;
+  const bool want_K = mode != MODE_PHI_R;
+  const int kmode = mode == MODE_PHI_R ? MODE_ELASTIC : mode;
   CK(cudaSetDevice(p->device));
-  EvSet* ev = p->prof ? next_events(p) : nullptr;
-  if (ev) CK(cudaEventRecord(ev->e[0], p->stream));
+  p->ev_cur = p->prof ? next_events(p) : nullptr;
+  if (p->ev_cur) CK(cudaEventRecord(p->ev_cur->e[0], p->stream));
+  long long launches = 0;
   for (const BatchPlan& b : p->batches) {
+    if (b.halo) continue;
     K1Args a = b.k;
     a.u = u_dev;
     a.dfield = d_dev;
@@ -554,23 +571,59 @@ int ad4sm_eval_device(ad4sm_plan* p, int32_t mode, const double* u_dev, const do
     a.phie = p->phie;
     cudaError_t e = launch_k1(a, kmode, p->stream);
     if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("K1 launch: ") + cudaGetErrorString(e));
+    launches++;
   }
-  if (ev) CK(cudaEventRecord(ev->e[1], p->stream));
+  if (p->ev_cur) CK(cudaEventRecord(p->ev_cur->e[1], p->stream));
+  if (p->prof) p->prof_launches[AD4SM_PROF_ELEMENT] += launches;
+  p->elements_mode = mode;
+  return AD4SM_OK;
+}
+
+int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (mode < 0 || mode > 3) return fail(AD4SM_EINVAL, "mode must be 0..3");
+  if (p->elements_mode != mode) return fail(AD4SM_ESTATE, "ad4sm_eval_assemble_device: no element evaluation of this mode pending");
+  const int field = mode == MODE_PF_D ? AD4SM_FIELD_D : AD4SM_FIELD_U;
+  const bool want_K = mode != MODE_PHI_R;
+  CK(cudaSetDevice(p->device));
+  EvSet* ev = p->ev_cur;
+  if (ev) CK(cudaEventRecord(ev->e[4], p->stream));  // exchange time (if any) lies between e[1] and e[4]
   CK(launch_k2(asm_args(p, field), want_K, p->stream));
   if (ev) CK(cudaEventRecord(ev->e[2], p->stream));
   CK(launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, p->stream));
   if (ev) CK(cudaEventRecord(ev->e[3], p->stream));
   if (p->prof) {
-    p->prof_launches[AD4SM_PROF_ELEMENT] += (long long)p->batches.size();
     p->prof_launches[AD4SM_PROF_ASSEMBLE] += want_K ? 2 : 1;
     p->prof_launches[AD4SM_PROF_REDUCE] += 2;
   }
+  p->ev_cur = nullptr;
+  p->elements_mode = -1;
   FieldOut& f = p->field[field];
   f.evaluated = true;
   f.have_K = want_K;
   f.dz_valid = false;
   f.n_zero = -1;
   p->last_field = field;
+  return AD4SM_OK;
+}
+
+int ad4sm_eval_device(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
+  int rc = ad4sm_eval_elements_device(p, mode, u_dev, d_dev, hist_dev);
+  if (rc) return rc;
+  return ad4sm_eval_assemble_device(p, mode);
+}
+
+int ad4sm_staging_view_get(ad4sm_plan* p, int32_t field, ad4sm_staging_view* v) {
+  int rc = check_field(p, field);
+  if (rc) return rc;
+  if (!v) return fail(AD4SM_EINVAL, "view is NULL");
+  const int DB = field == AD4SM_FIELD_D ? 1 : p->D;
+  v->n_slots = p->ne;
+  v->ke_width = (int64_t)n_pair_blocks(p->N) * DB * DB;
+  v->re_width = (int64_t)p->N * DB;
+  v->Ke_dev = p->Ke;
+  v->re_dev = p->re;
+  v->phie_dev = p->phie;
   return AD4SM_OK;
 }
 

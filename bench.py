@@ -164,7 +164,7 @@ def run_ours(args):
         runner = None
     else:
         from ad4sm_b200 import dist as D
-        runner = D.SlabRunner(n, n * world, rank, world, device=local)
+        runner = D.SlabRunner(n, n, rank, world, device=local)
         plan, batch, u = runner.plan, runner.batch, runner.u_local
     t_build = time.perf_counter() - t_build0
     ne_local = batch.ne
@@ -173,7 +173,7 @@ def run_ours(args):
     # a non-default torch stream: the plan launches on it, so torch.cuda.Event timing sees the kernels
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    plan.set_stream(stream.cuda_stream)
+    plan.set_stream(stream.cuda_stream)   # library kernels, torch ops and NCCL all order on this stream
     u_pin = torch.from_numpy(np.ascontiguousarray(u.T)).pin_memory()      # [node][comp] == column-major 3 x nNodes
     u_dev = u_pin.cuda(non_blocking=True)
     torch.cuda.synchronize()
@@ -287,7 +287,8 @@ def run_ours(args):
                         "(the reference's consumer, lu(Kt[ifree,ifree]), is out of scope)"},
         "gpu_launches": int(sum(prof_n)),
         "roofline": dominant, "roofline_kernels": [roof_k1, roof_k2], "roofline_path": path,
-        "kernel_ms": {"k1_element": k1_ms, "k2k3_assembly": k2_ms, "phi_reduce": red_ms},
+        "kernel_ms": {"k1_element": k1_ms, "k2k3_assembly": k2_ms, "phi_reduce": red_ms,
+                      "interface_exchange": prof_ms[capi.PROF_GATHER] / max(1, args.steps)},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line, ensure_ascii=False))

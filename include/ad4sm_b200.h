@@ -53,6 +53,12 @@ extern "C" {
 #define AD4SM_F_PF_GRAD_INTENDED 8u   /* d-phase: keep d/dd of l0^2|∇d|^2 (reference drops it, toolkit:159-166) */
 #define AD4SM_F_NH2D_EXT 16u          /* PhaseField{NeoHooke} on 2x2 F: plane-strain embedding (extension) */
 
+/* batch flags.  HALO: elements owned by another rank of a mesh-partitioned run.  They take part in the pattern and in
+ * the assembly of this rank's rows, but are not evaluated here: their staged element blocks / residuals are written
+ * into the plan's staging arrays by the exchange step (ad4sm_staging_view_get) between ad4sm_eval_elements_device and
+ * ad4sm_eval_assemble_device.  gradN / wgt / Nval may be NULL for a HALO batch. */
+#define AD4SM_BATCH_HALO 1
+
 /* fields a plan can assemble for */
 #define AD4SM_FIELD_U 0 /* displacement dofs: dofs_per_node per node */
 #define AD4SM_FIELD_D 1 /* phase-field dofs: 1 per node (makeϕrKt_d) */
@@ -68,7 +74,7 @@ typedef struct ad4sm_batch {
   int32_t mat_kind;       /* AD4SM_MAT_* */
   int32_t mat_base;       /* base material kind when mat_kind == PHASEFIELD, else 0 */
   uint32_t mat_flags;     /* AD4SM_F_* */
-  int32_t reserved;
+  int32_t batch_flags;    /* AD4SM_BATCH_* (0 for a plain single-GPU plan) */
   double mat_params[8];
   int64_t n_elems;
   const int64_t* nodes;      /* [n_elems][N]        elem.nodes, 1-based */
@@ -137,6 +143,22 @@ int ad4sm_set_stream(ad4sm_plan* plan, void* cuda_stream); /* cudaStream_t; NULL
  * Asynchronous on the plan's stream. */
 int ad4sm_eval_device(ad4sm_plan* plan, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev);
 int ad4sm_device_view_get(ad4sm_plan* plan, int32_t field, ad4sm_device_view* view);
+
+/* ---- mesh-partitioned runs: the two halves of ad4sm_eval_device, and the staging they communicate through ----
+ * The reference has no multi-device path; this is the seam where interface contributions cross ranks (DESIGN.md
+ * "Multi-GPU").  elements: K1 over the non-HALO batches (element energy/gradient/Hessian -> staging).
+ * assemble: K2/K3 over ALL batches' staging + the ϕ reduction (HALO slots contribute 0 to ϕ). */
+int ad4sm_eval_elements_device(ad4sm_plan* plan, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev);
+int ad4sm_eval_assemble_device(ad4sm_plan* plan, int32_t mode);
+typedef struct ad4sm_staging_view {
+  int64_t n_slots;       /* elements of all batches, in batch order (slot = position in that concatenation) */
+  int64_t ke_width;      /* doubles per slot in Ke_dev: N(N+1)/2 node-pair blocks of DB*DB (DB = D for FIELD_U, 1 for FIELD_D) */
+  int64_t re_width;      /* doubles per slot in re_dev: N*DB */
+  double* Ke_dev;        /* [n_slots][ke_width] */
+  double* re_dev;        /* [n_slots][re_width] */
+  double* phie_dev;      /* [n_slots] */
+} ad4sm_staging_view;
+int ad4sm_staging_view_get(ad4sm_plan* plan, int32_t field, ad4sm_staging_view* view);
 int ad4sm_sync(ad4sm_plan* plan);
 
 /* Per-kernel CUDA-event timing (bench.py roofline): enable, run evaluations, then read the
@@ -144,7 +166,7 @@ int ad4sm_sync(ad4sm_plan* plan);
 #define AD4SM_PROF_ELEMENT 0  /* K1 element energy/gradient/Hessian */
 #define AD4SM_PROF_ASSEMBLE 1 /* K2 segmented assembly of Kt and r */
 #define AD4SM_PROF_REDUCE 2   /* ϕ reduction */
-#define AD4SM_PROF_GATHER 3   /* u gather / misc */
+#define AD4SM_PROF_GATHER 3   /* time between the element and assembly stages (interface exchange of a partitioned run) */
 #define AD4SM_PROF_NCLASS 4
 int ad4sm_profile_enable(ad4sm_plan* plan, int32_t on);
 int ad4sm_profile_read(ad4sm_plan* plan, double ms[AD4SM_PROF_NCLASS], int64_t launches[AD4SM_PROF_NCLASS],

@@ -176,3 +176,53 @@ def test_cuda_path_reproduces_golden_vectors(path):
     import _golden
     case = _golden.load(path)
     _golden.compare(_golden.run_product(case), case, tol=K.TOL)
+
+
+def test_two_rank_halo_exchange_single_gpu():
+    """Mesh-partitioned evaluation (dist.py) emulated on ONE GPU: two in-process plans with HALO batches, the
+    interface staging copied between them where NCCL send/recv would carry it.  Owned rows must be BITWISE equal to
+    the single-plan result (same contributions, same `elems` order)."""
+    import torch
+    from ad4sm_b200 import dist as AD, mesh
+    coords, conn = mesh.hex_block(4, 3, 6, jitter=0.1, seed=21)
+    b = El.Hex08_batch(conn, coords, K.nh())
+    u = mesh.random_u(len(coords), 3, 1 / 6, seed=22)
+    phi0, r0, Kt0 = El.Plan(b, u.shape[1], 3).makeϕrKt(u)
+    world = 2
+    er = AD.contiguous_elem_ranks(len(conn), world)
+    parts = [AD.build_partition(conn, er, g, world) for g in range(world)]
+    backs = []
+    for p in parts:
+        own = El.ElemBatch("CE", 3, p.local_conn(conn[p.own_elems]), b.gradN[p.own_elems], b.wgt[p.own_elems], b.mat)
+        backs.append(AD.GpuBackend(own, p.local_conn(conn[p.halo_elems]), p, 3))
+    for p, be in zip(parts, backs):
+        ul = torch.from_numpy(np.ascontiguousarray(u[:, p.local_nodes - 1].T)).cuda()
+        be.eval_elements(ul)
+        be.plan.sync()
+    for g, (p, be) in enumerate(zip(parts, backs)):
+        for peer, idx in p.send.items():
+            s, c = parts[peer].recv[g]
+            n0 = backs[peer].n_own
+            for src, dst in zip(be.staging(), backs[peer].staging()):
+                dst[n0 + s:n0 + s + c] = src[torch.as_tensor(idx, device="cuda")]
+    torch.cuda.synchronize()
+    phis, seen = [], np.zeros(u.shape[1], dtype=int)
+    for p, be in zip(parts, backs):
+        be.assemble()
+        be.plan.sync()
+        phis.append(float(be.phi_tensor().cpu()[0]))
+        Kt = be.plan.fetch_csc()
+        r = be.r_tensor().cpu().numpy()
+        ln = p.local_nodes
+        for loc in np.where(p.owned)[0]:
+            gn = ln[loc]
+            seen[gn - 1] += 1
+            for c in range(3):
+                lc, gc = loc * 3 + c, (gn - 1) * 3 + c
+                assert r[lc] == r0[gc]
+                ls, gs = slice(Kt.colptr[lc] - 1, Kt.colptr[lc + 1] - 1), slice(Kt0.colptr[gc] - 1, Kt0.colptr[gc + 1] - 1)
+                lrows = Kt.rowval[ls] - 1
+                assert np.array_equal((ln[lrows // 3] - 1) * 3 + lrows % 3 + 1, Kt0.rowval[gs])
+                assert np.array_equal(Kt.nzval[ls], Kt0.nzval[gs])
+    assert np.all(seen == 1)
+    assert abs(sum(phis) - phi0) <= 1e-13 * abs(phi0)
