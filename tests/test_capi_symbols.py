@@ -1,0 +1,48 @@
+"""CPU-only checks of the drop-in boundary: libad4sm_b200.so loads, exports every entry point that
+include/ad4sm_b200.h declares (and the ctypes mirror binds exactly those), and -- there being no CPU fallback --
+refuses to compute without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ad4sm_b200 import _capi as capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "ad4sm_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ad4sm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared()
+    assert len(names) >= 20
+    L = C.CDLL(capi.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ad4sm_b200.h but not exported"
+    assert sorted(capi.SIGNATURES) == names, "ctypes mirror and header disagree"
+
+
+def test_header_constants_match_python_mirror():
+    txt = open(os.path.join(ROOT, "include", "ad4sm_b200.h")).read()
+    for name, val in re.findall(r"#define\s+AD4SM_([A-Z0-9_]+)\s+\(?(-?\d+)u?\)?", txt):
+        py = {"ABI_VERSION": None, "OK": "OK"}.get(name, name)
+        if py and hasattr(capi, py):
+            assert getattr(capi, py) == int(val), name
+    assert capi.lib().ad4sm_abi_version() == 1
+    assert C.sizeof(capi.Batch) == 8 * 4 + 8 * 8 + 8 + 5 * 8
+
+
+@pytest.mark.skipif(capi.device_count() > 0, reason="needs a box WITHOUT a GPU")
+def test_no_cpu_fallback():
+    from ad4sm_b200 import Elements as El, Materials as Ma, mesh
+    coords, conn = mesh.hex_block(2, 2, 2)
+    b = El.Hex08_batch(conn, coords, Ma.NeoHooke(1000.0, 5000.0))
+    with pytest.raises(capi.AD4SMError) as ei:
+        El.makeϕrKt(b, np.zeros((3, len(coords))))
+    assert ei.value.code == capi.ENODEV
