@@ -597,6 +597,14 @@ class Plan:
         capi.check(self._L.ad4sm_staging_view_get(self._h, field, C.byref(v)))
         return v
 
+    def set_option(self, option, value):
+        capi.check(self._L.ad4sm_set_option(self._h, option, int(value)))
+
+    def info(self, what):
+        v = C.c_int64()
+        capi.check(self._L.ad4sm_get_info(self._h, what, C.byref(v)))
+        return v.value
+
     def sync(self):
         capi.check(self._L.ad4sm_sync(self._h))
 

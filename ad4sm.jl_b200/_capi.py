@@ -29,6 +29,8 @@ class Batch(C.Structure):
 
 
 BATCH_HALO = 1
+OPT_FUSED, OPT_FUSED_LAG = 1, 2
+INFO_FUSED, INFO_FUSED_STEPS = 1, 2
 
 
 class StagingView(C.Structure):
@@ -74,6 +76,8 @@ SIGNATURES = {
     "ad4sm_eval_assemble_device": (C.c_int, [C.c_void_p, C.c_int32]),
     "ad4sm_staging_view_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(StagingView)]),
     "ad4sm_sync": (C.c_int, [C.c_void_p]),
+    "ad4sm_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
+    "ad4sm_get_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "ad4sm_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "ad4sm_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "ad4sm_measure_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -8,6 +8,7 @@
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -84,6 +85,10 @@ struct ad4sm_plan {
   long long prof_launches[AD4SM_PROF_NCLASS] = {0, 0, 0, 0};
   EvSet* ev_cur = nullptr;  // events of the evaluation in flight between the elements and assemble stages
   int elements_mode = -1;
+  // fused persistent path (single elastic / PF-u batch, no HALO): K1 + K2 + K3 in one cooperative launch
+  FuseArgs fz = {};
+  bool fused_last = false;  // the pending element stage already assembled Kt and r
+  bool fuse_allowed = false;  // ad4sm_set_option(AD4SM_OPT_FUSED); off by default: measured slower in round 1
 };
 
 template <class T> static int dev_alloc(ad4sm_plan* p, T** ptr, size_t count) {
@@ -430,6 +435,65 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     TRY(dev_alloc(p, &p->d_dev, (size_t)n_nodes));
     TRY(dev_alloc(p, &p->hist_dev, (size_t)n_gp * 2));
   }
+  // ---- fused work lists: which step (= iteration of the persistent K1) makes each block / row complete ----------
+  {
+    const char* env = getenv("AD4SM_FUSED");
+    const bool want = !(env && env[0] == '0');
+    p->fuse_allowed = env && env[0] == '1';
+    K1Config c;
+    const ad4sm_batch& B0 = batches[0];
+    if (want && n_batches == 1 && !(B0.batch_flags & AD4SM_BATCH_HALO) &&
+        k1_config(D, N, B0.n_gauss, B0.elem_kind == AD4SM_ELEM_CP && B0.mat_kind == AD4SM_MAT_PHASEFIELD, ne, &c) &&
+        c.persistent && c.staged) {
+      const long long gstep = (long long)c.grid * c.warps;
+      const long long n_groups = (ne + c.EW - 1) / c.EW;
+      const int n_steps = (int)((n_groups + gstep - 1) / gstep);
+      auto step_of = [&](unsigned slot) { return (int)((slot / (unsigned)c.EW) / gstep); };
+      std::vector<unsigned> kb_ptr(n_steps + 1, 0), kr_ptr(n_steps + 1, 0), blk_sorted(n_blocks), row_sorted(n_nodes);
+      std::vector<int> bstep(n_blocks), rstep(n_nodes);
+#pragma omp parallel for schedule(static)
+      for (long long b = 0; b < n_blocks; b++) {
+        int m = 0;
+        for (unsigned q = blk_ptr[b]; q < blk_ptr[b + 1]; q++) m = std::max(m, step_of((src[q] >> 1) / (unsigned)NPB));
+        bstep[b] = m;
+      }
+#pragma omp parallel for schedule(static)
+      for (long long i = 0; i < n_nodes; i++) {
+        int m = 0;
+        for (unsigned q = adj_ptr[i]; q < adj_ptr[i + 1]; q++) m = std::max(m, step_of(adj[q] / (unsigned)N));
+        rstep[i] = m;
+      }
+      for (long long b = 0; b < n_blocks; b++) kb_ptr[bstep[b] + 1]++;
+      for (long long i = 0; i < n_nodes; i++) kr_ptr[rstep[i] + 1]++;
+      for (int t = 0; t < n_steps; t++) kb_ptr[t + 1] += kb_ptr[t], kr_ptr[t + 1] += kr_ptr[t];
+      {
+        std::vector<unsigned> cb(kb_ptr.begin(), kb_ptr.end() - 1), cr(kr_ptr.begin(), kr_ptr.end() - 1);
+        for (long long b = 0; b < n_blocks; b++) blk_sorted[cb[bstep[b]]++] = (unsigned)b;
+        for (long long i = 0; i < n_nodes; i++) row_sorted[cr[rstep[i]]++] = (unsigned)i;
+      }
+      unsigned *d_kb = nullptr, *d_bs = nullptr, *d_kr = nullptr, *d_rs = nullptr, *d_done = nullptr;
+      int rc2 = dev_upload(p, &d_kb, kb_ptr.data(), kb_ptr.size());
+      if (!rc2) rc2 = dev_upload(p, &d_bs, blk_sorted.data(), blk_sorted.size());
+      if (!rc2) rc2 = dev_upload(p, &d_kr, kr_ptr.data(), kr_ptr.size());
+      if (!rc2) rc2 = dev_upload(p, &d_rs, row_sorted.data(), row_sorted.size());
+      if (!rc2) rc2 = dev_alloc(p, &d_done, (size_t)n_steps + 1);
+      if (rc2) {
+        ad4sm_plan_destroy(p);
+        return rc2;
+      }
+      p->fz.enabled = 1;
+      p->fz.lag = 2;
+      if (const char* l = getenv("AD4SM_FUSED_LAG")) p->fz.lag = std::max(1, atoi(l));
+      p->fz.n_steps = n_steps;
+      p->fz.gstep = gstep;
+      p->fz.n_groups = n_groups;
+      p->fz.done = d_done;
+      p->fz.kb_ptr = d_kb;
+      p->fz.blk_sorted = d_bs;
+      p->fz.kr_ptr = d_kr;
+      p->fz.row_sorted = d_rs;
+    }
+  }
 #undef TRY
   *plan_out = p;
   return AD4SM_OK;
@@ -559,6 +623,12 @@ int ad4sm_eval_elements_device(ad4sm_plan* p, int32_t mode, const double* u_dev,
   p->ev_cur = p->prof ? next_events(p) : nullptr;
   if (p->ev_cur) CK(cudaEventRecord(p->ev_cur->e[0], p->stream));
   long long launches = 0;
+  const bool fuse = p->fz.enabled && want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U) && p->fuse_allowed;
+  p->fused_last = fuse;
+  if (fuse) {
+    CK(cudaMemsetAsync(p->fz.done, 0, sizeof(unsigned) * ((size_t)p->fz.n_steps + 1), p->stream));
+    CK(cudaMemsetAsync(p->n_zero_dev, 0, sizeof(unsigned long long), p->stream));
+  }
   for (const BatchPlan& b : p->batches) {
     if (b.halo) continue;
     K1Args a = b.k;
@@ -569,6 +639,10 @@ int ad4sm_eval_elements_device(ad4sm_plan* p, int32_t mode, const double* u_dev,
     a.Ke = p->Ke;
     a.re = p->re;
     a.phie = p->phie;
+    if (fuse) {
+      a.fz = p->fz;
+      a.as = asm_args(p, AD4SM_FIELD_U);
+    }
     cudaError_t e = launch_k1(a, kmode, p->stream);
     if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("K1 launch: ") + cudaGetErrorString(e));
     launches++;
@@ -588,12 +662,12 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   CK(cudaSetDevice(p->device));
   EvSet* ev = p->ev_cur;
   if (ev) CK(cudaEventRecord(ev->e[4], p->stream));  // exchange time (if any) lies between e[1] and e[4]
-  CK(launch_k2(asm_args(p, field), want_K, p->stream));
+  if (!p->fused_last) CK(launch_k2(asm_args(p, field), want_K, p->stream));
   if (ev) CK(cudaEventRecord(ev->e[2], p->stream));
   CK(launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, p->stream));
   if (ev) CK(cudaEventRecord(ev->e[3], p->stream));
   if (p->prof) {
-    p->prof_launches[AD4SM_PROF_ASSEMBLE] += want_K ? 2 : 1;
+    if (!p->fused_last) p->prof_launches[AD4SM_PROF_ASSEMBLE] += want_K ? 2 : 1;
     p->prof_launches[AD4SM_PROF_REDUCE] += 2;
   }
   p->ev_cur = nullptr;
@@ -625,6 +699,26 @@ int ad4sm_staging_view_get(ad4sm_plan* p, int32_t field, ad4sm_staging_view* v) 
   v->re_dev = p->re;
   v->phie_dev = p->phie;
   return AD4SM_OK;
+}
+
+int ad4sm_set_option(ad4sm_plan* p, int32_t option, int64_t value) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  switch (option) {
+    case AD4SM_OPT_FUSED: p->fuse_allowed = value != 0; return AD4SM_OK;
+    case AD4SM_OPT_FUSED_LAG:
+      if (value < 1 || value > 64) return fail(AD4SM_EINVAL, "lag must be in 1..64");
+      p->fz.lag = (int)value;
+      return AD4SM_OK;
+  }
+  return fail(AD4SM_EINVAL, "unknown option");
+}
+int ad4sm_get_info(ad4sm_plan* p, int32_t what, int64_t* value) {
+  if (!p || !value) return fail(AD4SM_EINVAL, "plan or value is NULL");
+  switch (what) {
+    case AD4SM_INFO_FUSED: *value = p->fz.enabled ? (p->fuse_allowed ? 2 : 1) : 0; return AD4SM_OK;  // 0 n/a, 1 available, 2 on
+    case AD4SM_INFO_FUSED_STEPS: *value = p->fz.n_steps; return AD4SM_OK;
+  }
+  return fail(AD4SM_EINVAL, "unknown info id");
 }
 
 int ad4sm_sync(ad4sm_plan* p) {

@@ -9,6 +9,38 @@ namespace ad4sm {
 
 enum EvalMode { MODE_ELASTIC = 0, MODE_PF_U = 1, MODE_PF_D = 2, MODE_PHI_R = 3 };
 
+// assembly maps (built once per plan, api.cu) + outputs of one field
+struct AsmArgs {
+  long long n_nodes, n_blocks;  // node rows, node-pair blocks of the pattern
+  int N, DB, dpn;               // nodes/element, block size computed by K1, dofs per node of the assembled field
+  const unsigned* blk_row;      // [n_blocks] row node of each block
+  const unsigned* nbr_ptr;      // [n_nodes+1] first block of each row node (blocks = sorted neighbour nodes)
+  const unsigned* nbr;          // [n_blocks]  neighbour (column) node of each block
+  const unsigned* blk_ptr;      // [n_blocks+1] source list of each block
+  const unsigned* src;          // [ne*N*N] (slot*NPB + pair index)*2 + transposed, in `elems` order per block
+  const unsigned* adj_ptr;      // [n_nodes+1]
+  const unsigned* adj;          // [ne*N] slot*N + local node, in `elems` order per node
+  const double* Ke;
+  const double* re;
+  double* nzval;                // [dpn*dpn*n_blocks]
+  double* r;                    // [dpn*n_nodes]
+  unsigned long long* n_zero;   // [1] stored exact zeros in nzval
+};
+
+// Work lists of the FUSED persistent kernel (K1 + K2 + K3 in one launch, DESIGN.md "Fused path").  The element groups a
+// warp processes in its iteration `it` form "step" it; a node-pair block / residual row becomes ready when the last
+// step that contributes to it has been published in `done`.  Blocks and rows are listed sorted by that step.
+struct FuseArgs {
+  int enabled, lag, n_steps, pad;
+  long long gstep;             // element groups per step = grid * warps per CTA of the launch the lists were built for
+  long long n_groups;          // element groups of the batch
+  unsigned* done;              // [n_steps] number of groups of each step whose staging is globally visible
+  const unsigned* kb_ptr;      // [n_steps+1] into blk_sorted
+  const unsigned* blk_sorted;  // [n_blocks] block ids by readiness step (stable: ascending block id inside a step)
+  const unsigned* kr_ptr;      // [n_steps+1] into row_sorted
+  const unsigned* row_sorted;  // [n_nodes] node ids by readiness step
+};
+
 // One K1 launch = one batch (SoA copy of a Vector{CEElem}/Vector{CPElem}, elements.jl:71-111).
 struct K1Args {
   MatDev mat;
@@ -29,25 +61,20 @@ struct K1Args {
   double* Ke;           // [slots][NPB][DB*DB]  cyclic symmetric block storage (element.cuh)
   double* re;           // [slots][N][DB]
   double* phie;         // [slots]
+  // fused assembly (fz.enabled): the persistent kernel also runs K2/K3 over `as`
+  FuseArgs fz;
+  AsmArgs as;
 };
 
-// assembly maps (built once per plan, api.cu) + outputs of one field
-struct AsmArgs {
-  long long n_nodes, n_blocks;  // node rows, node-pair blocks of the pattern
-  int N, DB, dpn;               // nodes/element, block size computed by K1, dofs per node of the assembled field
-  const unsigned* blk_row;      // [n_blocks] row node of each block
-  const unsigned* nbr_ptr;      // [n_nodes+1] first block of each row node (blocks = sorted neighbour nodes)
-  const unsigned* nbr;          // [n_blocks]  neighbour (column) node of each block
-  const unsigned* blk_ptr;      // [n_blocks+1] source list of each block
-  const unsigned* src;          // [ne*N*N] (slot*NPB + pair index)*2 + transposed, in `elems` order per block
-  const unsigned* adj_ptr;      // [n_nodes+1]
-  const unsigned* adj;          // [ne*N] slot*N + local node, in `elems` order per node
-  const double* Ke;
-  const double* re;
-  double* nzval;                // [dpn*dpn*n_blocks]
-  double* r;                    // [dpn*n_nodes]
-  unsigned long long* n_zero;   // [1] stored exact zeros in nzval
+// launch shape of the persistent K1 for a batch (shared by the launcher and the fused work-list builder)
+struct K1Config {
+  int persistent;  // 0: thread-per-element kernel (one Gauss point)
+  int EW;          // elements per warp iteration
+  int warps;       // warps per CTA
+  int grid;        // CTAs
+  int staged;      // blocks/residual leave through the shared-memory staging + bulk stores
 };
+bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c);
 
 cudaError_t launch_k1(const K1Args& a, int mode, cudaStream_t s);
 const char* k1_unsupported_reason(int D, int N, int P, int mf, int mode);

@@ -167,6 +167,86 @@ static WarpLayout k1p_layout(int D, int N, int P, int LP, bool pf) {
   return L;
 }
 
+// ---- assembly of one node-pair block / one residual entry (shared by K2/K3 and the fused persistent kernel) ----------
+// Sums the DB x DB source blocks of node-pair block `blk` in `elems` order (left fold, like Julia's sparse(),
+// toolkit:202) and writes DB rows of dpn consecutive values into CSC columns / CSR rows (i, 0..dpn-1).
+// CG: read the staging with ld.global.cg (L2 only) -- required when it was written earlier in the same kernel.
+template <int DB, bool CG> __device__ __forceinline__ int assemble_block(const AsmArgs& a, long long blk) {
+  const int dpn = a.dpn;
+  const unsigned s0 = __ldg(a.blk_ptr + blk), s1 = __ldg(a.blk_ptr + blk + 1);
+  const unsigned i = __ldg(a.blk_row + blk);
+  double acc[DB * DB];
+#pragma unroll
+  for (int t = 0; t < DB * DB; t++) acc[t] = 0.0;
+  unsigned code = s0 < s1 ? __ldg(a.src + s0) : 0u;
+  for (unsigned s = s0; s < s1; s++) {
+    const unsigned cur = code;
+    if (s + 1 < s1) code = __ldg(a.src + s + 1);  // prefetch the next source while this one is summed
+    const double* B = a.Ke + (long long)(cur >> 1) * (DB * DB);
+    double v[DB * DB];
+#pragma unroll
+    for (int t = 0; t < DB * DB; t++) v[t] = CG ? __ldcg(B + t) : B[t];
+    if (cur & 1u) {
+#pragma unroll
+      for (int j = 0; j < DB; j++)
+#pragma unroll
+        for (int l = 0; l < DB; l++) acc[j * DB + l] += v[l * DB + j];
+    } else {
+#pragma unroll
+      for (int t = 0; t < DB * DB; t++) acc[t] += v[t];
+    }
+  }
+  const long long nb0 = __ldg(a.nbr_ptr + i);
+  const int nn = (int)(__ldg(a.nbr_ptr + i + 1) - nb0);
+  const int p = (int)(blk - nb0);
+  double* out = a.nzval + nb0 * (dpn * dpn) + (long long)p * dpn;
+  int nz = 0;
+#pragma unroll
+  for (int j = 0; j < DB; j++) {
+    double* row = out + (long long)j * dpn * nn;
+#pragma unroll
+    for (int l = 0; l < DB; l++) {
+      row[l] = acc[j * DB + l];
+      nz += (acc[j * DB + l] == 0.0);
+    }
+    for (int l = DB; l < dpn; l++) {
+      row[l] = 0.0;
+      nz++;
+    }
+  }
+  for (int j = DB; j < dpn; j++) {
+    double* row = out + (long long)j * dpn * nn;
+    for (int l = 0; l < dpn; l++) {
+      row[l] = 0.0;
+      nz++;
+    }
+  }
+  return nz;
+}
+// r[(node, j)]: left fold over the node's elements in `elems` order (r[idxii] += grad, toolkit:190)
+template <bool CG> __device__ __forceinline__ void assemble_r_entry(const AsmArgs& a, long long i, int j) {
+  double acc = 0.0;
+  if (j < a.DB) {
+    const unsigned s0 = __ldg(a.adj_ptr + i), s1 = __ldg(a.adj_ptr + i + 1);
+    for (unsigned s = s0; s < s1; s++) {
+      const double* p = a.re + (long long)__ldg(a.adj + s) * a.DB + j;
+      acc += CG ? __ldcg(p) : *p;
+    }
+  }
+  a.r[i * a.dpn + j] = acc;
+}
+
+// ---- fused path: inter-warp publication of finished steps ---------------------------------------------------------
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ---- phase 1 of the persistent K1: one Gauss point per lane ----------------------------------------------
 // Register-allocation note (ptxas 12.9): both phases are called by ALL lanes of the warp, unconditionally, with the
 // lane predicates passed in.  Wrapping them in `if (valid)` / `if (active)` made the allocator keep 12 phase-2
@@ -279,6 +359,47 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
   }
 }
 
+// ---- fused path: this warp's share of the K2/K3 work that became ready with step t -------------------------------
+// Waits (lane 0 polls, then the warp syncs) until every step <= t has been published by all warps that own element
+// groups in it; a warp only ever waits for steps that precede, in every warp's program order, the K1 work still
+// ahead of it, so with all CTAs co-resident (one per SM) there is no cycle.
+template <int D>
+__device__ __forceinline__ void fused_assemble_step(const K1Args& a, int t, int gwarp, int n_warps, int lane, int& verified,
+                                                    int& nzero) {
+  if (t >= a.fz.n_steps) return;
+  while (verified <= t) {
+    if (lane == 0) {
+      const long long first = (long long)verified * a.fz.gstep;
+      long long left = a.fz.n_groups - first;
+      const unsigned target = (unsigned)(left < a.fz.gstep ? left : a.fz.gstep);
+      const unsigned* flag = a.fz.done + verified;
+      while (ld_acquire(flag) < target) __nanosleep(64);
+    }
+    __syncwarp();
+    verified++;
+  }
+  // node-pair blocks
+  {
+    const unsigned b0 = __ldg(a.fz.kb_ptr + t), b1 = __ldg(a.fz.kb_ptr + t + 1);
+    const unsigned cnt = b1 - b0, chunk = (cnt + n_warps - 1) / n_warps;
+    unsigned j0 = b0 + (unsigned)gwarp * chunk, j1 = j0 + chunk;
+    if (j1 > b1) j1 = b1;
+    for (unsigned j = j0 + lane; j < j1; j += 32) nzero += assemble_block<D, true>(a.as, (long long)__ldg(a.fz.blk_sorted + j));
+  }
+  // residual rows
+  {
+    const unsigned r0 = __ldg(a.fz.kr_ptr + t), r1 = __ldg(a.fz.kr_ptr + t + 1);
+    const unsigned cnt = r1 - r0, chunk = (cnt + n_warps - 1) / n_warps;
+    unsigned j0 = r0 + (unsigned)gwarp * chunk, j1 = j0 + chunk;
+    if (j1 > r1) j1 = r1;
+    const int dpn = a.as.dpn;
+    for (unsigned j = j0 * dpn + lane; j < j1 * dpn; j += 32) {
+      const unsigned row = j / dpn;
+      assemble_r_entry<true>(a.as, (long long)__ldg(a.fz.row_sorted + row), (int)(j - row * dpn));
+    }
+  }
+}
+
 // ---- K1, u-dual, persistent, LP lanes per element, TMA-staged inputs ------------------------------
 template <int D, int N, int LP, int MF, bool PF>
 __global__ void __launch_bounds__(256, 1)
@@ -328,7 +449,11 @@ __global__ void __launch_bounds__(256, 1)
     tma_load_1d(smem_u32(ws + (L.n_off + (s) * L.n_stg)), a.nodes + e0 * N, nbytes, bar0 + 16 + 8 * s);
   };
 
-  long long grp = (long long)blockIdx.x * warps_per_cta + warp;
+  const bool fused = a.fz.enabled != 0;
+  const int gwarp = blockIdx.x * warps_per_cta + warp;  // global warp id = its first element group
+  int verified = 0;                                      // steps [0, verified) are known to be published (fused path)
+  int nzero = 0, n_it = 0;
+  long long grp = gwarp;
   if (grp < n_groups) {
     if (lane == 0) {
       issue(grp, 0);
@@ -356,7 +481,16 @@ __global__ void __launch_bounds__(256, 1)
     mbar_wait(bar0 + 8 * s, (unsigned)((it >> 1) & 1));                        // this group's ∇N, wgt, N
     if (has_next) mbar_wait(bar0 + 16 + 8 * (s ^ 1), (unsigned)(((it + 1) >> 1) & 1));  // next group's node ids
     cp_async_wait_all();                                                        // this group's u
-    if (lane == 0) bulk_wait_read_all();  // the previous bulk stores have read the staging area (aliases the records)
+    if (lane == 0) {
+      if (fused && it > 0) {
+        // publish step it-1: its bulk stores are complete (they had a whole iteration), make them visible GPU-wide
+        bulk_wait_all();
+        __threadfence();
+        red_release_add(a.fz.done + (it - 1), 1u);
+      } else {
+        bulk_wait_read_all();  // the previous bulk stores have read the staging area (aliases the records)
+      }
+    }
     __syncwarp();
 
     const long long e = grp * EW + el;
@@ -405,8 +539,26 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
     __syncwarp();
+    if (fused && it >= a.fz.lag) fused_assemble_step<D>(a, it - a.fz.lag, gwarp, (int)gstep, lane, verified, nzero);
+    n_it = it + 1;
   }
-  if (lane == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk stores
+  if (lane == 0) {
+    if (fused && n_it > 0) {
+      bulk_wait_all();
+      __threadfence();
+      red_release_add(a.fz.done + (n_it - 1), 1u);
+    } else {
+      bulk_wait_read_all();  // shared memory must outlive the last bulk stores
+    }
+  }
+  if (fused) {  // the steps this warp has not assembled yet (its last `lag` ones, and any it had no elements in)
+    __syncwarp();
+    int t = n_it - a.fz.lag;
+    if (t < 0) t = 0;
+    for (; t < a.fz.n_steps; t++) fused_assemble_step<D>(a, t, gwarp, (int)gstep, lane, verified, nzero);
+    for (int o = 16; o > 0; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
+    if (lane == 0 && nzero) atomicAdd(a.as.n_zero, (unsigned long long)nzero);
+  }
 }
 
 // ---- K1, u-dual, one thread per element (P == 1) ------------------------------------------------
@@ -530,34 +682,61 @@ const char* k1_unsupported_reason(int D, int N, int P, int mf, int mode) {
   return nullptr;
 }
 
+static int sm_count() {
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  return n_sm;
+}
+
+bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c) {
+  int LP;
+  if (!lanes_for(D, N, P, LP)) return false;
+  c->persistent = LP > 1;
+  c->EW = 32 / LP;
+  c->warps = c->grid = c->staged = 0;
+  if (LP == 1) return true;
+  const WarpLayout L = k1p_layout(D, N, P, LP, pf);
+  int warps = (227 * 1024) / L.bytes;
+  if (warps < 1) return false;
+  if (warps > 8) warps = 8;
+  const long long n_groups = (ne + c->EW - 1) / c->EW;
+  if (n_groups < warps) warps = (int)(n_groups > 0 ? n_groups : 1);
+  long long grid = (n_groups + warps - 1) / warps;
+  if (grid > sm_count()) grid = sm_count();  // persistent: one CTA per SM, each warp strides over the element groups
+  if (grid < 1) grid = 1;
+  c->warps = warps;
+  c->grid = (int)grid;
+  c->staged = L.kout_el != 0;
+  return true;
+}
+
 template <int D, int N, int LP, int MF, bool PF> static cudaError_t launch_u_t(const K1Args& a, cudaStream_t s) {
   if constexpr (LP == 1) {
     const unsigned grid = (unsigned)((a.ne + K1_THREADS - 1) / K1_THREADS);
     k1_u_kernel_t1<D, N, MF, PF><<<grid, K1_THREADS, 0, s>>>(a);
     return cudaGetLastError();
   } else {
-    constexpr int EW = 32 / LP;
+    K1Config c;
+    if (!k1_config(D, N, a.P, PF, a.ne, &c)) return cudaErrorInvalidValue;
     const WarpLayout L = k1p_layout(D, N, a.P, LP, PF);
     const int smem_max = 227 * 1024;
-    int warps = smem_max / L.bytes;
-    if (warps < 1) return cudaErrorInvalidValue;
-    if (warps > 8) warps = 8;
-    const long long n_groups = (a.ne + EW - 1) / EW;
-    if (n_groups < warps) warps = (int)n_groups;
-    static int n_sm = 0;
-    if (n_sm == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-      if (n_sm <= 0) n_sm = 148;
-    }
-    long long grid = (n_groups + warps - 1) / warps;
-    if (grid > n_sm) grid = n_sm;  // persistent: one CTA per SM, each warp strides over the element groups
-    const size_t smem = (size_t)warps * L.bytes;
+    const size_t smem = (size_t)c.warps * L.bytes;
     auto kern = k1_u_kernel<D, N, LP, MF, PF>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err != cudaSuccess) return err;
-    kern<<<(unsigned)grid, warps * 32, smem, s>>>(a, L, warps);
+    if (a.fz.enabled) {
+      // the fused kernel's warps wait on one another: all CTAs must be co-resident -> cooperative launch
+      if (a.fz.gstep != (long long)c.grid * c.warps || !c.staged || !a.want_K) return cudaErrorInvalidValue;
+      int warps = c.warps;
+      void* args[] = {(void*)&a, (void*)&L, (void*)&warps};
+      return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)c.grid), dim3((unsigned)(c.warps * 32)), args, smem, s);
+    }
+    kern<<<(unsigned)c.grid, c.warps * 32, smem, s>>>(a, L, c.warps);
     return cudaGetLastError();
   }
 }
@@ -609,78 +788,22 @@ cudaError_t launch_k1(const K1Args& a, int mode, cudaStream_t s) {
   return cudaErrorInvalidValue;
 }
 
-// ---- K2: Kt values.  One thread per node-pair block (row node i, neighbour p): sums the DB x DB source blocks
-// in `elems` order (left fold, like Julia's sparse(), toolkit:202) and writes DB rows of dpn consecutive values
-// into CSC columns / CSR rows (i, 0..dpn-1).  Consecutive threads (p) write consecutive memory in each row.
+// ---- K2: Kt values.  One thread per node-pair block (row node i, neighbour p); consecutive threads (p) write
+// consecutive memory in each row.
 template <int DB> __global__ void __launch_bounds__(256) k2_kernel(const AsmArgs a) {
   const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (blk >= a.n_blocks) return;
-  const int dpn = a.dpn;
-  const unsigned s0 = __ldg(a.blk_ptr + blk), s1 = __ldg(a.blk_ptr + blk + 1);
-  const unsigned i = __ldg(a.blk_row + blk);
-  double acc[DB * DB];
-#pragma unroll
-  for (int t = 0; t < DB * DB; t++) acc[t] = 0.0;
-  unsigned code = s0 < s1 ? __ldg(a.src + s0) : 0u;
-  for (unsigned s = s0; s < s1; s++) {
-    const unsigned cur = code;
-    if (s + 1 < s1) code = __ldg(a.src + s + 1);  // prefetch the next source while this one is summed
-    const double* B = a.Ke + (long long)(cur >> 1) * (DB * DB);
-    double v[DB * DB];
-#pragma unroll
-    for (int t = 0; t < DB * DB; t++) v[t] = B[t];
-    if (cur & 1u) {
-#pragma unroll
-      for (int j = 0; j < DB; j++)
-#pragma unroll
-        for (int l = 0; l < DB; l++) acc[j * DB + l] += v[l * DB + j];
-    } else {
-#pragma unroll
-      for (int t = 0; t < DB * DB; t++) acc[t] += v[t];
-    }
-  }
-  const long long nb0 = __ldg(a.nbr_ptr + i);
-  const int nn = (int)(__ldg(a.nbr_ptr + i + 1) - nb0);
-  const int p = (int)(blk - nb0);
-  double* out = a.nzval + nb0 * (dpn * dpn) + (long long)p * dpn;
-  int nz = 0;
-#pragma unroll
-  for (int j = 0; j < DB; j++) {
-    double* row = out + (long long)j * dpn * nn;
-#pragma unroll
-    for (int l = 0; l < DB; l++) {
-      row[l] = acc[j * DB + l];
-      nz += (acc[j * DB + l] == 0.0);
-    }
-    for (int l = DB; l < dpn; l++) {
-      row[l] = 0.0;
-      nz++;
-    }
-  }
-  for (int j = DB; j < dpn; j++) {
-    double* row = out + (long long)j * dpn * nn;
-    for (int l = 0; l < dpn; l++) {
-      row[l] = 0.0;
-      nz++;
-    }
-  }
+  const int nz = assemble_block<DB, false>(a, blk);
   if (nz) atomicAdd(a.n_zero, (unsigned long long)nz);  // integer atomic: order-independent
 }
 
-// ---- K3: residual.  One thread per (node, component): left fold over the node's elements in `elems` order
-// (r[idxii] += grad, toolkit:190).
+// ---- K3: residual.  One thread per (node, component).
 __global__ void __launch_bounds__(256) k3_kernel(const AsmArgs a) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int dpn = a.dpn;
   if (g >= a.n_nodes * dpn) return;
   const long long i = g / dpn;
-  const int j = (int)(g - i * dpn);
-  double acc = 0.0;
-  if (j < a.DB) {
-    const unsigned s0 = __ldg(a.adj_ptr + i), s1 = __ldg(a.adj_ptr + i + 1);
-    for (unsigned s = s0; s < s1; s++) acc += a.re[(long long)__ldg(a.adj + s) * a.DB + j];
-  }
-  a.r[g] = acc;
+  assemble_r_entry<false>(a, i, (int)(g - i * dpn));
 }
 
 cudaError_t launch_k2(const AsmArgs& a, bool want_K, cudaStream_t s) {

@@ -161,6 +161,18 @@ typedef struct ad4sm_staging_view {
 int ad4sm_staging_view_get(ad4sm_plan* plan, int32_t field, ad4sm_staging_view* view);
 int ad4sm_sync(ad4sm_plan* plan);
 
+/* Plan options / introspection.  FUSED: a plan with a single non-HALO batch of a multi-Gauss-point element runs the
+ * element stage and the assembly as ONE persistent cooperative kernel (the staged blocks are consumed from L2 a few
+ * steps after they are written); 0 (the default in round 1, where the fused kernel is correct but slower)
+ * uses the separate K1 -> K2/K3 launches.  Results are bitwise the same either way.
+ * AD4SM_INFO_FUSED: 0 = not available for this plan, 1 = available, 2 = switched on. */
+#define AD4SM_OPT_FUSED 1
+#define AD4SM_OPT_FUSED_LAG 2     /* steps between staging a group and assembling the rows it completes */
+#define AD4SM_INFO_FUSED 1
+#define AD4SM_INFO_FUSED_STEPS 2
+int ad4sm_set_option(ad4sm_plan* plan, int32_t option, int64_t value);
+int ad4sm_get_info(ad4sm_plan* plan, int32_t what, int64_t* value);
+
 /* Per-kernel CUDA-event timing (bench.py roofline): enable, run evaluations, then read the
  * accumulated milliseconds and launch counts per kernel class. */
 #define AD4SM_PROF_ELEMENT 0  /* K1 element energy/gradient/Hessian */

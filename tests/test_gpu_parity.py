@@ -226,3 +226,28 @@ def test_two_rank_halo_exchange_single_gpu():
                 assert np.array_equal(Kt.nzval[ls], Kt0.nzval[gs])
     assert np.all(seen == 1)
     assert abs(sum(phis) - phi0) <= 1e-13 * abs(phi0)
+
+
+@pytest.mark.parametrize("n", [(6, 5, 4), (30, 30, 30), (40, 37, 29)])
+def test_fused_persistent_kernel_matches_separate_kernels(n):
+    """The fused path (K1+K2+K3 in one cooperative persistent launch, steps published through global counters) must
+    give bitwise the same ϕ, r, Kt as the separate K1 -> K2/K3 launches, and both must match the oracle."""
+    b, u = K.hex_case(n)
+    plan = El.Plan(b, u.shape[1], 3)
+    assert plan.info(capi.INFO_FUSED) >= 1
+    plan.set_option(capi.OPT_FUSED, 1)
+    f = plan.makeϕrKt(u)
+    f2 = plan.makeϕrKt(u)
+    plan.set_option(capi.OPT_FUSED, 0)
+    s = plan.makeϕrKt(u)
+    for x in (f2, s):
+        assert f[0] == x[0] and np.array_equal(f[1], x[1])
+        assert np.array_equal(f[2].colptr, x[2].colptr) and np.array_equal(f[2].rowval, x[2].rowval)
+        assert np.array_equal(f[2].nzval, x[2].nzval)
+    plan.set_option(capi.OPT_FUSED, 1)
+    for lag in (1, 3, 7):
+        plan.set_option(capi.OPT_FUSED_LAG, lag)
+        g = plan.makeϕrKt(u)
+        assert np.array_equal(f[2].nzval, g[2].nzval) and np.array_equal(f[1], g[1])
+    if b.ne <= 30000:
+        K.assert_parity(f, K.oracle_eval(b, u))
