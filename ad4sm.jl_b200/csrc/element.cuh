@@ -258,12 +258,20 @@ AD4SM_DI void column_u_acc(int q, int Prt, const double* recs, int rstride, cons
     for (int i = 0; i < DD; i++) acc[o][i] = 0.0;
 #pragma unroll
   for (int j = 0; j < D; j++) rq[j] = 0.0;
+  // row-node pointers (a = (q + o) mod N), hoisted: inside the loop only gp * gstride + k * kstride is added
+  const double* ga[NO];
+#pragma unroll
+  for (int o = 0; o < NO; o++) {
+    int a = q + o;
+    if (a >= N) a -= N;
+    ga[o] = gS + a;
+  }
   for (int gp = 0; gp < P; gp++) {
     const Mem rec{recs + gp * rstride};
-    const double* g = gS + gp * gstride;
+    const int goff = gp * gstride;
     double gb[D];
 #pragma unroll
-    for (int k = 0; k < D; k++) gb[k] = g[k * kstride + q];
+    for (int k = 0; k < D; k++) gb[k] = ga[0][goff + k * kstride];
     // r_(q,j) += Σ_k wP_(kj) ∇N_q,k
 #pragma unroll
     for (int j = 0; j < D; j++)
@@ -288,11 +296,9 @@ AD4SM_DI void column_u_acc(int q, int Prt, const double* recs, int rstride, cons
         // instructions for the other lanes anyway)
 #pragma unroll
         for (int o = 0; o < NO; o++) {
-          int a = q + o;
-          if (a >= N) a -= N;
 #pragma unroll
           for (int k = 0; k < D; k++) {
-            const double gak = g[k * kstride + a];
+            const double gak = ga[o][goff + k * kstride];
 #pragma unroll
             for (int j = 0; j < D; j++) acc[o][j * D + l] += gak * Tl[k * D + j];
           }

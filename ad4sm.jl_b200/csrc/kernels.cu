@@ -346,16 +346,22 @@ __device__ __forceinline__ void k1_phase1(const MatDev* mat, int q, bool valid, 
 // ---- phase 2 of the persistent K1: one column node per lane ------------------------------------------------
 // Called by ALL lanes of the warp (inactive lanes compute on valid shared memory and store nothing): see the note
 // at k1_phase1, and the stores may alias the records other lanes are still reading: accumulate, __syncwarp, store.
-template <int D, int N>
-__device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active, bool want_K, const double* recs,
-                                       const double* gS, double* kout, double* rout) {
+template <int D, int N, int PT>
+__device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active, bool want_K, bool staged, const double* recs,
+                                          const double* gS, double* kout_s, double* rout_s, double* kout_g, double* rout_g) {
   double acc[N / 2 + 1][D * D], rq[D];
-  column_u_acc<D, N, 0, VecMem>(q, P, recs, rstride, gS, N, P * N, want_K, acc, rq);
+  column_u_acc<D, N, PT, VecMem>(q, P, recs, rstride, gS, N, (PT ? PT : P) * N, want_K, acc, rq);
   __syncwarp();
   if (active) {
-    if (want_K) column_u_store<D, N>(q, acc, kout);
+    if (staged) {  // shared-memory staging (STS), leaves with the bulk stores
+      column_u_store<D, N>(q, acc, kout_s);
 #pragma unroll
-    for (int j = 0; j < D; j++) rout[q * D + j] = rq[j];
+      for (int j = 0; j < D; j++) rout_s[q * D + j] = rq[j];
+    } else {
+      if (want_K) column_u_store<D, N>(q, acc, kout_g);
+#pragma unroll
+      for (int j = 0; j < D; j++) rout_g[q * D + j] = rq[j];
+    }
   }
 }
 
@@ -515,9 +521,15 @@ __global__ void __launch_bounds__(256, 1)
     // staging area in the (then dead) record region, or straight to global memory when they do not fit
     const bool staged = a.want_K && L.kout_el;
     unsigned char* stg = ws + (size_t)el * L.kout_el;
-    double* kout = staged ? reinterpret_cast<double*>(stg) : a.Ke + slot * (long long)(NPB * DD);
-    double* rout = staged ? reinterpret_cast<double*>(stg + L.re_off) : a.re + slot * (long long)(N * D);
-    k1_phase2<D, N>(q, P, L.rstride, active, a.want_K != 0, recs, gS, kout, rout);
+    constexpr int PTC = (N == 8) ? 8 : ((N == 4) ? 4 : 0);  // the usual Gauss count of the shape, compiled in
+    if (PTC && P == PTC)
+      k1_phase2<D, N, PTC>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS, reinterpret_cast<double*>(stg),
+                           reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
+                           a.re + slot * (long long)(N * D));
+    else
+      k1_phase2<D, N, 0>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS, reinterpret_cast<double*>(stg),
+                         reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
+                         a.re + slot * (long long)(N * D));
     if (valid && q == 0) {  // ϕ_e = Σ_gp w ψ, in Gauss-point order (elasticelements.jl:199-206)
       double ssum = 0.0;
       for (int gp = 0; gp < P; gp++) ssum += psiS[gp];
