@@ -14,6 +14,7 @@
 //            accumulates its 4-5 node blocks K(a,q) = Σ_gp ∇N_aᵀ (A ∇N_q) in registers -- FP64-FMA bound,
 //            no cross-lane floating-point reduction.
 // Elements with one Gauss point and N <= 4 (Tet04, Tria) run one thread per element, all in registers.
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "element.cuh"
@@ -688,7 +689,6 @@ const char* k1_unsupported_reason(int D, int N, int P, int mf, int mode) {
   int LP;
   if (!lanes_for(D, N, P, LP)) return "unsupported element shape (D, N): supported are (2,3), (2,4), (3,4), (3,6), (3,8)";
   if (P < 1 || P > 27) return "number of Gauss points must be in 1..27";
-  if (mf == MF_OGDEN) return "Ogden: the reference defines only the scalar energy (no derivative); not implemented";
   if (mf < 0 || mf > MF_OGDEN) return "unknown material family";
   (void)mode;
   return nullptr;
@@ -759,6 +759,7 @@ template <int D, int N, int LP> static cudaError_t launch_u_mf(const K1Args& a, 
     case MF_NEO: return launch_u_t<D, N, LP, MF_NEO, false>(a, s);
     case MF_MOONEY: return launch_u_t<D, N, LP, MF_MOONEY, false>(a, s);
     case MF_PFNEO: return launch_u_t<D, N, LP, MF_PFNEO, true>(a, s);
+    case MF_OGDEN: return launch_u_t<D, N, LP, MF_OGDEN, false>(a, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -808,7 +809,6 @@ template <int DB> __global__ void __launch_bounds__(256) k2_kernel(const AsmArgs
   const int nz = assemble_block<DB, false>(a, blk);
   if (nz) atomicAdd(a.n_zero, (unsigned long long)nz);  // integer atomic: order-independent
 }
-
 // ---- K3: residual.  One thread per (node, component).
 __global__ void __launch_bounds__(256) k3_kernel(const AsmArgs a) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -419,6 +419,164 @@ template <int D> AD4SM_DI void pfneo_tangent(const MatDev& m, const double* F, d
 }
 
 // ---------------------------------------------------------------------------------------------
+// Ogden (principal stretches)   elasticmaterials.jl:148-172
+//   λ_i = sqrt(σ_i(FᵀF));  K < 0: ψ = μ/α (Σ λ_i^α − 3);  else J = Π λ_i, ψ = μ/α (Σ λ_i^α J^(−α/3) − 3) + K (J−1)².
+//   2-D: F is embedded with F33 = 1/det F (K < 0, plane stress) or 1 (:155-160), i.e. λ3 = 1/(λ1 λ2) or 1.
+// The reference defines only this scalar energy: its `Ogden` cannot be constructed (struct/`new` arity mismatch,
+// :114-120) and `svdvals` has no method for duals (:162), so r and Kt have no reference value.  The
+// derivatives here are the exact ones of that energy, from the spectral representation F = Σ λ_i n_i ⊗ N_i:
+//   P = Σ_i f_i n_i⊗N_i
+//   A = Σ_ij f_ij (n_i⊗N_i)⊗(n_j⊗N_j) + Σ_{i≠j} a_ij (n_i⊗N_j)⊗(n_i⊗N_j) + Σ_{i≠j} b_ij (n_i⊗N_j)⊗(n_j⊗N_i)
+//   a_ij = (λ_i f_i − λ_j f_j)/(λ_i² − λ_j²),  b_ij = (λ_j f_i − λ_i f_j)/(λ_i² − λ_j²)        (Ogden 1984, §6.1.4)
+// Because λ_i f_i = μ s λ_i^α + c with s and c common to all i (s = J^(−α/3) or 1), the quotients are divided
+// differences of x^(α/2) and x^((α−2)/2) in x = λ², evaluated without cancellation -- repeated stretches (u = 0:
+// λ = (1,1,1)) are regular points of these formulas, and any orthonormal eigenbasis may be used there.
+// ---------------------------------------------------------------------------------------------
+// (x_i^p − x_j^p)/(x_i − x_j) for x > 0
+AD4SM_DI double divdiff_pow(double xi, double xj, double p) {
+  const double t = (xi - xj) / xj;
+  const double xjp1 = pow(xj, p - 1.0);
+  if (fabs(t) < 2e-3) {  // series of ((1+t)^p − 1)/t, truncation error t^5/720·|p…(p−5)| < 1e-16
+    return xjp1 * p *
+           (1.0 + (p - 1.0) * t / 2.0 *
+                      (1.0 + (p - 2.0) * t / 3.0 * (1.0 + (p - 3.0) * t / 4.0 * (1.0 + (p - 4.0) * t / 5.0))));
+  }
+  return xjp1 * (pow(1.0 + t, p) - 1.0) / t;
+}
+
+// Eigen-decomposition of a symmetric DxD matrix S (full storage, destroyed): cyclic Jacobi with a fixed number of
+// sweeps (deterministic, robust for repeated eigenvalues).  V columns = eigenvectors, S diagonal = eigenvalues.
+template <int D> AD4SM_DI void jacobi_eig(double* S, double* V) {
+#pragma unroll
+  for (int i = 0; i < D; i++)
+#pragma unroll
+    for (int j = 0; j < D; j++) V[i * D + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < (D == 2 ? 1 : 6); sweep++) {
+#pragma unroll
+    for (int p = 0; p < D - 1; p++)
+#pragma unroll
+      for (int q = p + 1; q < D; q++) {
+        const double apq = S[p * D + q];
+        if (apq != 0.0) {
+          const double theta = (S[q * D + q] - S[p * D + p]) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+#pragma unroll
+          for (int k = 0; k < D; k++) {  // S <- S J
+            const double skp = S[k * D + p], skq = S[k * D + q];
+            S[k * D + p] = c * skp - sn * skq;
+            S[k * D + q] = sn * skp + c * skq;
+          }
+#pragma unroll
+          for (int k = 0; k < D; k++) {  // S <- Jᵀ S
+            const double spk = S[p * D + k], sqk = S[q * D + k];
+            S[p * D + k] = c * spk - sn * sqk;
+            S[q * D + k] = sn * spk + c * sqk;
+          }
+#pragma unroll
+          for (int k = 0; k < D; k++) {
+            const double vkp = V[k * D + p], vkq = V[k * D + q];
+            V[k * D + p] = c * vkp - sn * vkq;
+            V[k * D + q] = sn * vkp + c * vkq;
+          }
+        }
+      }
+  }
+}
+
+// energy on duals of the D in-plane stretches (the third stretch of the 2-D embedding is a function of them)
+template <int D> AD4SM_DI Dual2<D> ogden_energy(const MatDev& m, const Dual2<D>* lam, double& s_out) {
+  const double alpha = m.p[0], mu = m.p[1], K = m.p[2];
+  Dual2<D> S = d2_pow(lam[0], alpha);
+#pragma unroll
+  for (int i = 1; i < D; i++) S = S + d2_pow(lam[i], alpha);
+  Dual2<D> J = lam[0];
+#pragma unroll
+  for (int i = 1; i < D; i++) J = J * lam[i];
+  if (D == 2) S = (K < 0) ? S + d2_pow(J, -alpha) : S + 1.0;  // λ3 = 1/(λ1 λ2) or 1
+  if (K < 0) {
+    s_out = 1.0;
+    return (mu / alpha) * (S - 3.0);
+  }
+  const Dual2<D> sc = d2_pow(J, -alpha / 3.0);  // 3-D: J = λ1λ2λ3; 2-D (K >= 0): λ3 = 1, J = λ1λ2
+  s_out = sc.v;
+  return (mu / alpha) * (S * sc - 3.0) + K * d2_sq(J - 1.0);
+}
+
+template <int D> AD4SM_DI void ogden_tangent(const MatDev& m, const double* F, Tangent<D>& t) {
+  constexpr int DD = D * D;
+  const double alpha = m.p[0], mu = m.p[1];
+  // C = FᵀF (F[k*D+j] = F_jk), eigen-decomposition C = V diag(x) Vᵀ
+  double C[DD], V[DD];
+#pragma unroll
+  for (int a = 0; a < D; a++)
+#pragma unroll
+    for (int b = a; b < D; b++) {
+      double c = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; i++) c += F[a * D + i] * F[b * D + i];
+      C[a * D + b] = C[b * D + a] = c;
+    }
+  jacobi_eig<D>(C, V);
+  double lam[D], x[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    x[i] = C[i * D + i];
+    lam[i] = sqrt(x[i]);
+  }
+  // n_i = F N_i / λ_i;  E_ij[(k, j')] = n_i[j'] N_j[k] in the F[k*D+j'] addressing
+  double U[DD];
+#pragma unroll
+  for (int i = 0; i < D; i++)
+#pragma unroll
+    for (int r = 0; r < D; r++) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; k++) a += F[k * D + r] * V[k * D + i];
+      U[r * D + i] = a / lam[i];
+    }
+  Dual2<D> dl[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) dl[i] = d2_var<D>(lam[i], i);
+  double s;
+  const Dual2<D> f = ogden_energy<D>(m, dl, s);
+  t.psi = f.v;
+  const double c0 = lam[0] * f.g[0] - mu * s * pow(lam[0], alpha);  // λ_i f_i = μ s λ_i^α + c0 for every i
+#pragma unroll
+  for (int I = 0; I < DD; I++) t.P[I] = 0.0;
+#pragma unroll
+  for (int I = 0; I < Tangent<D>::NA; I++) t.A[I] = 0.0;
+  auto E = [&](int i, int j, int I) { return U[(I % D) * D + i] * V[(I / D) * D + j]; };  // (n_i ⊗ N_j)[I]
+#pragma unroll
+  for (int i = 0; i < D; i++)
+#pragma unroll
+    for (int I = 0; I < DD; I++) t.P[I] += f.g[i] * E(i, i, I);
+#pragma unroll
+  for (int i = 0; i < D; i++)
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+      if (i == j || true) {
+        const double fij = f.h[pk(i, j)];
+#pragma unroll
+        for (int J = 0; J < DD; J++)
+#pragma unroll
+          for (int I = 0; I <= J; I++) t.A[pk(I, J)] += fij * E(i, i, I) * E(j, j, J);
+      }
+      if (i < j) {
+        const double a = mu * s * divdiff_pow(x[i], x[j], 0.5 * alpha);
+        const double b = mu * s * lam[i] * lam[j] * divdiff_pow(x[i], x[j], 0.5 * alpha - 1.0) - c0 / (lam[i] * lam[j]);
+#pragma unroll
+        for (int J = 0; J < DD; J++)
+#pragma unroll
+          for (int I = 0; I <= J; I++) {
+            const double eijI = E(i, j, I), eijJ = E(i, j, J), ejiI = E(j, i, I), ejiJ = E(j, i, J);
+            t.A[pk(I, J)] += a * (eijI * eijJ + ejiI * ejiJ) + b * (eijI * ejiJ + ejiI * eijJ);
+          }
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dispatcher: ψ, P, A for one Gauss point.  pf = nullptr for plain elastic materials.
 // For PhaseField the d-dependent but F-independent term Gc/(2 l0) (dⁿ + l0²|∇d|²) is added to ψ.
 // ---------------------------------------------------------------------------------------------
@@ -439,6 +597,8 @@ template <int D, int MF> AD4SM_DI void material_tangent(const MatDev& m, const d
     else hyper_tangent2<true>(m, F, t);
   } else if (MF == MF_PFNEO) {
     pfneo_tangent<D>(m, F, g, t);
+  } else if (MF == MF_OGDEN) {
+    ogden_tangent<D>(m, F, t);
   }
   if (m.kind == MAT_PHASEFIELD && pf) {
     const double l0 = m.p[4], Gc = m.p[5], n = m.p[6];

@@ -251,3 +251,56 @@ def test_fused_persistent_kernel_matches_separate_kernels(n):
         assert np.array_equal(f[2].nzval, g[2].nzval) and np.array_equal(f[1], g[1])
     if b.ne <= 30000:
         K.assert_parity(f, K.oracle_eval(b, u))
+
+
+# ---- Ogden: no reference derivative exists (tests/test_ogden.py pins the tangent against mpmath) ----
+def _ogden(alpha=3.0, mu=1000.0, K=5000.0):
+    return Ma.Ogden(alpha, mu, K)
+
+
+@pytest.mark.parametrize("case", ["hex8", "tet4", "quad4", "quad4-K<0"])
+def test_ogden_alpha2_equals_neohooke_on_gpu(case):
+    """Ogden(α = 2, μ, K) is NeoHooke(μ/2, K) (Σλ² = I1): the spectral-tangent kernels must reproduce the
+    invariant-based ones, and those are pinned by the oracle."""
+    mk = {"hex8": K.hex_case, "tet4": K.tet_case, "quad4": K.quad_case, "quad4-K<0": K.quad_case}[case]
+    Kb = -1.0 if case.endswith("K<0") else 5000.0
+    b1, u = mk(mat=Ma.Ogden(2.0, 1000.0, Kb))
+    b2, _ = mk(mat=Ma.NeoHooke(500.0, Kb))
+    g1 = El.Plan(b1, u.shape[1], u.shape[0]).makeϕrKt(u)
+    g2 = El.Plan(b2, u.shape[1], u.shape[0]).makeϕrKt(u)
+    assert abs(g1[0] - g2[0]) <= 1e-11 * abs(g2[0])
+    assert np.abs(g1[1] - g2[1]).max() <= 1e-10 * np.abs(g2[1]).max()
+    assert np.array_equal(g1[2].rowval, g2[2].rowval)
+    assert np.abs(g1[2].nzval - g2[2].nzval).max() <= 1e-10 * np.abs(g2[2].nzval).max()
+
+
+def test_ogden_hex8_contract_properties():
+    """α = 3 (no closed-form twin): energy against the reference's scalar formula (oracle restatement), and
+    ϕ -> r -> Kt consistency, symmetry, translation null space, determinism."""
+    from oracle import elements as OE, materials as OM
+    b, u = K.hex_case((4, 3, 3), mat=_ogden())
+    plan = El.Plan(b, u.shape[1], 3)
+    phi, r, Kt = plan.makeϕrKt(u)
+    om = OM.Ogden(3.0, 1000.0, 5000.0)
+    phi_ref = sum(float(OE.getphi_elem(OE.Elem("CE", 3, b.nodes[e], b.gradN[e], b.wgt[e], 0.0, om), u[:, b.nodes[e] - 1]))
+                  for e in range(b.ne))
+    assert abs(phi - phi_ref) <= 1e-12 * abs(phi_ref)
+    Kd = K.csc_dense(Kt)
+    assert np.array_equal(Kd, Kd.T)
+    again = plan.makeϕrKt(u)
+    assert again[0] == phi and np.array_equal(again[2].nzval, Kt.nzval)
+    for j in range(3):
+        t = np.zeros_like(u)
+        t[j] = 1.0
+        assert np.abs(Kd @ t.reshape(-1, order="F")).max() <= 1e-10 * np.abs(Kd).max()
+    rng = np.random.default_rng(0)
+    w = rng.uniform(-1, 1, u.shape)
+    h = 1e-6 * np.abs(u).max()
+    pp, rp, _ = plan.makeϕrKt(u + h * w)
+    pm, rm, _ = plan.makeϕrKt(u - h * w)
+    wv = w.reshape(-1, order="F")
+    assert abs((pp - pm) / (2 * h) - r @ wv) <= 1e-6 * np.abs(r).max() * np.abs(wv).sum() / len(wv) * 10
+    assert np.abs((rp - rm) / (2 * h) - Kd @ wv).max() <= 1e-6 * np.abs(Kd @ wv).max()
+    # undeformed state: all stretches equal (the spectral formulas' singular point)
+    p0, r0, K0 = plan.makeϕrKt(np.zeros_like(u))
+    assert abs(p0) <= 1e-12 and np.abs(r0).max() <= 1e-9 * np.abs(K0.nzval).max() and np.all(np.isfinite(K0.nzval))
