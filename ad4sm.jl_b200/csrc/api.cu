@@ -65,6 +65,8 @@ struct EvSet {
 struct ad4sm_plan {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t copy_stream = nullptr;          // host API: ϕ and r travel back while K2 still runs
+  cudaEvent_t ev_r_ready = nullptr, ev_copied = nullptr;
   int N = 0, D = 0, dpn = 0;
   long long n_nodes = 0, ne = 0, n_blocks = 0, n_gp = 0;
   bool has_cp = false;
@@ -179,6 +181,9 @@ void ad4sm_plan_destroy(ad4sm_plan* p) {
   }
   for (auto& s : p->ev_pool)
     for (int i = 0; i < 5; i++) cudaEventDestroy(s.e[i]);
+  if (p->ev_r_ready) cudaEventDestroy(p->ev_r_ready);
+  if (p->ev_copied) cudaEventDestroy(p->ev_copied);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   delete p;
 }
@@ -365,6 +370,12 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       return fail(AD4SM_ENODEV, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     p->stream = p->own_stream;
+    if (cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_r_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_copied, cudaEventDisableTiming) != cudaSuccess) {
+      ad4sm_plan_destroy(p);
+      return fail(AD4SM_ENODEV, "cudaStreamCreate/cudaEventCreate failed");
+    }
   }
   TRY(dev_upload(p, &p->blk_row, blk_row.data(), blk_row.size()));
   TRY(dev_upload(p, &p->nbr_ptr, nbr_ptr.data(), nbr_ptr.size()));
@@ -662,9 +673,12 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   CK(cudaSetDevice(p->device));
   EvSet* ev = p->ev_cur;
   if (ev) CK(cudaEventRecord(ev->e[4], p->stream));  // exchange time (if any) lies between e[1] and e[4]
-  if (!p->fused_last) CK(launch_k2(asm_args(p, field), want_K, p->stream));
-  if (ev) CK(cudaEventRecord(ev->e[2], p->stream));
+  // r and ϕ first: the host API copies them back while the (much longer) Kt assembly is still running
+  if (!p->fused_last) CK(launch_k3(asm_args(p, field), p->stream));
   CK(launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, p->stream));
+  CK(cudaEventRecord(p->ev_r_ready, p->stream));
+  if (!p->fused_last && want_K) CK(launch_k2(asm_args(p, field), p->stream));
+  if (ev) CK(cudaEventRecord(ev->e[2], p->stream));
   if (ev) CK(cudaEventRecord(ev->e[3], p->stream));
   if (p->prof) {
     if (!p->fused_last) p->prof_launches[AD4SM_PROF_ASSEMBLE] += want_K ? 2 : 1;
@@ -771,8 +785,11 @@ static int eval_host(ad4sm_plan* p, int mode, const double* u, const double* d, 
   const int field = mode == MODE_PF_D ? AD4SM_FIELD_D : AD4SM_FIELD_U;
   FieldOut& f = p->field[field];
   unsigned long long nz = 0;
-  if (phi) CK(cudaMemcpyAsync(phi, p->phi_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (r) CK(cudaMemcpyAsync(r, f.r, sizeof(double) * f.n_dof, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamWaitEvent(p->copy_stream, p->ev_r_ready, 0));
+  if (phi) CK(cudaMemcpyAsync(phi, p->phi_dev, sizeof(double), cudaMemcpyDeviceToHost, p->copy_stream));
+  if (r) CK(cudaMemcpyAsync(r, f.r, sizeof(double) * f.n_dof, cudaMemcpyDeviceToHost, p->copy_stream));
+  CK(cudaEventRecord(p->ev_copied, p->copy_stream));
+  CK(cudaStreamWaitEvent(s, p->ev_copied, 0));  // the next evaluation on `s` must not overwrite r before it has left
   if (mode != MODE_PHI_R) CK(cudaMemcpyAsync(&nz, p->n_zero_dev, sizeof(nz), cudaMemcpyDeviceToHost, s));
   if (hist)
     for (const BatchPlan& b : p->batches) {

@@ -78,7 +78,8 @@ bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c);
 
 cudaError_t launch_k1(const K1Args& a, int mode, cudaStream_t s);
 const char* k1_unsupported_reason(int D, int N, int P, int mf, int mode);
-cudaError_t launch_k2(const AsmArgs& a, bool want_K, cudaStream_t s);
+cudaError_t launch_k2(const AsmArgs& a, cudaStream_t s);  // Kt values
+cudaError_t launch_k3(const AsmArgs& a, cudaStream_t s);  // residual
 int phi_reduce_partials();
 cudaError_t launch_phi_reduce(const double* phie, long long n, double* partials, double* phi, cudaStream_t s);
 cudaError_t launch_pattern(const AsmArgs& a, long long* colptr, long long* rowval, cudaStream_t s);

@@ -818,23 +818,22 @@ __global__ void __launch_bounds__(256) k3_kernel(const AsmArgs a) {
   assemble_r_entry<false>(a, i, (int)(g - i * dpn));
 }
 
-cudaError_t launch_k2(const AsmArgs& a, bool want_K, cudaStream_t s) {
-  if (want_K) {
-    cudaError_t err = cudaMemsetAsync(a.n_zero, 0, sizeof(unsigned long long), s);
-    if (err != cudaSuccess) return err;
-    const long long nt = a.n_blocks;
-    if (nt > 0) {
-      const unsigned grid = (unsigned)((nt + 255) / 256);
-      switch (a.DB) {
-        case 1: k2_kernel<1><<<grid, 256, 0, s>>>(a); break;
-        case 2: k2_kernel<2><<<grid, 256, 0, s>>>(a); break;
-        case 3: k2_kernel<3><<<grid, 256, 0, s>>>(a); break;
-        default: return cudaErrorInvalidValue;
-      }
-      err = cudaGetLastError();
-      if (err != cudaSuccess) return err;
+cudaError_t launch_k2(const AsmArgs& a, cudaStream_t s) {
+  cudaError_t err = cudaMemsetAsync(a.n_zero, 0, sizeof(unsigned long long), s);
+  if (err != cudaSuccess) return err;
+  const long long nt = a.n_blocks;
+  if (nt > 0) {
+    const unsigned grid = (unsigned)((nt + 255) / 256);
+    switch (a.DB) {
+      case 1: k2_kernel<1><<<grid, 256, 0, s>>>(a); break;
+      case 2: k2_kernel<2><<<grid, 256, 0, s>>>(a); break;
+      case 3: k2_kernel<3><<<grid, 256, 0, s>>>(a); break;
+      default: return cudaErrorInvalidValue;
     }
   }
+  return cudaGetLastError();
+}
+cudaError_t launch_k3(const AsmArgs& a, cudaStream_t s) {
   const long long nr = a.n_nodes * a.dpn;
   if (nr > 0) k3_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(a);
   return cudaGetLastError();

@@ -230,7 +230,7 @@ def run_ours(args):
     value = ne_total / (ms_step * 1e-3)
 
     # ---- end-to-end through the reference-facing call with host buffers (e2e) -------------------
-    r_host = np.empty(u.size)
+    r_host = torch.empty(u.size, dtype=torch.float64).pin_memory().numpy()  # pinned, like u (bench contract)
     u_np = u_pin.numpy()
     import ctypes as C
     phi, nnz = C.c_double(), C.c_int64()
