@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libad4sm_b200.so")
+LIB_PATH = os.environ.get("AD4SM_B200_LIB") or os.path.join(_HERE, "lib", "libad4sm_b200.so")
 
 OK, EINVAL, ENODEV, ENOMEM, ESTATE, ENCCL = 0, -1, -2, -3, -4, -5
 ELEM_CE, ELEM_CP = 0, 1
@@ -29,8 +29,8 @@ class Batch(C.Structure):
 
 
 BATCH_HALO = 1
-OPT_FUSED, OPT_FUSED_LAG = 1, 2
-INFO_FUSED, INFO_FUSED_STEPS = 1, 2
+OPT_FUSED, OPT_FUSED_LAG, OPT_SORTED = 1, 2, 3
+INFO_FUSED, INFO_FUSED_STEPS, INFO_SORTED = 1, 2, 3
 
 
 class StagingView(C.Structure):

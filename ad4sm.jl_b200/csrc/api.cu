@@ -91,6 +91,11 @@ struct ad4sm_plan {
   FuseArgs fz = {};
   bool fused_last = false;  // the pending element stage already assembled Kt and r
   bool fuse_allowed = false;  // ad4sm_set_option(AD4SM_OPT_FUSED); off by default: measured slower in round 1
+  // destination-sorted staging (single 3-D batch of a persistent-kernel shape, dpn == 3)
+  bool sorted_built = false, sorted_on = true, sorted_last = false;
+  long long n_pairs = 0;
+  unsigned *cpos = nullptr, *cptr = nullptr, *out_up = nullptr, *out_lo = nullptr, *nn_pack = nullptr;
+  double* C = nullptr;
 };
 
 template <class T> static int dev_alloc(ad4sm_plan* p, T** ptr, size_t count) {
@@ -446,6 +451,78 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     TRY(dev_alloc(p, &p->d_dev, (size_t)n_nodes));
     TRY(dev_alloc(p, &p->hist_dev, (size_t)n_gp * 2));
   }
+  // ---- destination-sorted staging: contributions grouped by unordered node pair, in `elems` order inside a pair ----
+  {
+    const char* env = getenv("AD4SM_SORTED");
+    K1Config c;
+    const ad4sm_batch& B0 = batches[0];
+    if (!(env && env[0] == '0') && n_batches == 1 && !(B0.batch_flags & AD4SM_BATCH_HALO) && D == 3 && dofs_per_node == 3 &&
+        k1_config(D, N, B0.n_gauss, B0.elem_kind == AD4SM_ELEM_CP && B0.mat_kind == AD4SM_MAT_PHASEFIELD, ne, &c) &&
+        c.persistent && (double)n_blocks * 9.0 < 4.0e9) {
+      std::vector<unsigned> up_index(n_blocks, 0xffffffffu);
+      long long U = 0;
+      for (long long i = 0; i < n_nodes; i++)
+        for (unsigned b = nbr_ptr[i]; b < nbr_ptr[i + 1]; b++)
+          if (nbr[b] >= (unsigned)i) up_index[b] = (unsigned)U++;
+      auto find_blk = [&](unsigned row, unsigned col) -> unsigned {
+        const unsigned* lo = nbr.data() + nbr_ptr[row];
+        const unsigned* hi = nbr.data() + nbr_ptr[row + 1];
+        return (unsigned)(std::lower_bound(lo, hi, col) - nbr.data());
+      };
+      const size_t n_contrib = (size_t)ne * NPB;
+      std::vector<unsigned> dest(n_contrib), cptr(U + 1, 0), cpos(n_contrib);
+#pragma omp parallel for schedule(static)
+      for (long long sl = 0; sl < ne; sl++)
+        for (int idx = 0; idx < NPB; idx++) {
+          const int o = idx / N, q = idx % N;
+          const unsigned na = (unsigned)nodes0[(size_t)sl * N + (q + o) % N], nb = (unsigned)nodes0[(size_t)sl * N + q];
+          const unsigned row = std::min(na, nb), col = std::max(na, nb);
+          dest[(size_t)sl * NPB + idx] = (up_index[find_blk(row, col)] << 1) | (na > nb ? 1u : 0u);
+        }
+      for (size_t k = 0; k < n_contrib; k++) cptr[(dest[k] >> 1) + 1]++;
+      for (long long u = 0; u < U; u++) cptr[u + 1] += cptr[u];
+      {
+        std::vector<unsigned> cur(cptr.begin(), cptr.end() - 1);
+        for (long long o = 0; o < ne; o++) {  // `elems` order inside every pair
+          const size_t sl = order[o];
+          for (int idx = 0; idx < NPB; idx++) {
+            const unsigned d = dest[sl * NPB + idx];
+            cpos[sl * NPB + idx] = (cur[d >> 1]++ << 1) | (d & 1u);
+          }
+        }
+      }
+      std::vector<unsigned> out_up(U), out_lo(U), nn_pack(U);
+      const unsigned dd = (unsigned)(dofs_per_node * dofs_per_node);
+      bool ok = true;
+#pragma omp parallel for schedule(static)
+      for (long long i = 0; i < n_nodes; i++)
+        for (unsigned b = nbr_ptr[i]; b < nbr_ptr[i + 1]; b++) {
+          const unsigned pn = nbr[b];
+          if (pn < (unsigned)i) continue;
+          const unsigned u = up_index[b];
+          const unsigned nni = nbr_ptr[i + 1] - nbr_ptr[i], nnp = nbr_ptr[pn + 1] - nbr_ptr[pn];
+          if (nni > 0xffffu || nnp > 0xffffu) ok = false;
+          out_up[u] = nbr_ptr[i] * dd + (b - nbr_ptr[i]) * (unsigned)dofs_per_node;
+          const unsigned b2 = find_blk(pn, (unsigned)i);
+          out_lo[u] = nbr_ptr[pn] * dd + (b2 - nbr_ptr[pn]) * (unsigned)dofs_per_node;
+          nn_pack[u] = nni | (nnp << 16);
+        }
+      if (ok) {
+        int rc2 = dev_upload(p, &p->cpos, cpos.data(), cpos.size());
+        if (!rc2) rc2 = dev_upload(p, &p->cptr, cptr.data(), cptr.size());
+        if (!rc2) rc2 = dev_upload(p, &p->out_up, out_up.data(), out_up.size());
+        if (!rc2) rc2 = dev_upload(p, &p->out_lo, out_lo.data(), out_lo.size());
+        if (!rc2) rc2 = dev_upload(p, &p->nn_pack, nn_pack.data(), nn_pack.size());
+        if (!rc2) rc2 = dev_alloc(p, &p->C, n_contrib * (size_t)CBLK3);
+        if (rc2) {
+          ad4sm_plan_destroy(p);
+          return rc2;
+        }
+        p->n_pairs = U;
+        p->sorted_built = true;
+      }
+    }
+  }
   // ---- fused work lists: which step (= iteration of the persistent K1) makes each block / row complete ----------
   {
     const char* env = getenv("AD4SM_FUSED");
@@ -536,6 +613,12 @@ static AsmArgs asm_args(ad4sm_plan* p, int field) {
   a.nzval = p->field[field].nzval;
   a.r = p->field[field].r;
   a.n_zero = p->n_zero_dev;
+  a.n_pairs = (p->sorted_built && field == AD4SM_FIELD_U) ? p->n_pairs : 0;
+  a.cptr = p->cptr;
+  a.out_up = p->out_up;
+  a.out_lo = p->out_lo;
+  a.nn_pack = p->nn_pack;
+  a.C = p->C;
   return a;
 }
 
@@ -625,7 +708,11 @@ static int check_eval_args(ad4sm_plan* p, int32_t mode, const double* u_dev, con
   return 0;
 }
 
-int ad4sm_eval_elements_device(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
+// `internal`: called from ad4sm_eval_device, which also runs the assembly and may therefore pick a staging layout of its
+// own (destination-sorted, or consumed inside the fused kernel).  The public two-stage API promises the element-major
+// staging of ad4sm_staging_view_get between the stages (interface exchange of partitioned runs).
+static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev,
+                              bool internal) {
   int rc = check_eval_args(p, mode, u_dev, d_dev);
   if (rc) return rc;
   const bool want_K = mode != MODE_PHI_R;
@@ -634,8 +721,11 @@ int ad4sm_eval_elements_device(ad4sm_plan* p, int32_t mode, const double* u_dev,
   p->ev_cur = p->prof ? next_events(p) : nullptr;
   if (p->ev_cur) CK(cudaEventRecord(p->ev_cur->e[0], p->stream));
   long long launches = 0;
-  const bool fuse = p->fz.enabled && want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U) && p->fuse_allowed;
+  const bool fuse = internal && p->fz.enabled && want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U) && p->fuse_allowed;
   p->fused_last = fuse;
+  const bool sorted =
+      internal && !fuse && p->sorted_built && p->sorted_on && want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U);
+  p->sorted_last = sorted;
   if (fuse) {
     CK(cudaMemsetAsync(p->fz.done, 0, sizeof(unsigned) * ((size_t)p->fz.n_steps + 1), p->stream));
     CK(cudaMemsetAsync(p->n_zero_dev, 0, sizeof(unsigned long long), p->stream));
@@ -653,6 +743,10 @@ int ad4sm_eval_elements_device(ad4sm_plan* p, int32_t mode, const double* u_dev,
     if (fuse) {
       a.fz = p->fz;
       a.as = asm_args(p, AD4SM_FIELD_U);
+    }
+    if (sorted) {
+      a.cpos = p->cpos;
+      a.C = p->C;
     }
     cudaError_t e = launch_k1(a, kmode, p->stream);
     if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("K1 launch: ") + cudaGetErrorString(e));
@@ -677,7 +771,10 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   if (!p->fused_last) CK(launch_k3(asm_args(p, field), p->stream));
   CK(launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, p->stream));
   CK(cudaEventRecord(p->ev_r_ready, p->stream));
-  if (!p->fused_last && want_K) CK(launch_k2(asm_args(p, field), p->stream));
+  if (!p->fused_last && want_K) {
+    if (p->sorted_last) CK(launch_k2s(asm_args(p, field), p->stream));
+    else CK(launch_k2(asm_args(p, field), p->stream));
+  }
   if (ev) CK(cudaEventRecord(ev->e[2], p->stream));
   if (ev) CK(cudaEventRecord(ev->e[3], p->stream));
   if (p->prof) {
@@ -695,8 +792,12 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   return AD4SM_OK;
 }
 
+int ad4sm_eval_elements_device(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
+  return eval_elements_impl(p, mode, u_dev, d_dev, hist_dev, false);
+}
+
 int ad4sm_eval_device(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
-  int rc = ad4sm_eval_elements_device(p, mode, u_dev, d_dev, hist_dev);
+  int rc = eval_elements_impl(p, mode, u_dev, d_dev, hist_dev, true);
   if (rc) return rc;
   return ad4sm_eval_assemble_device(p, mode);
 }
@@ -719,6 +820,7 @@ int ad4sm_set_option(ad4sm_plan* p, int32_t option, int64_t value) {
   if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
   switch (option) {
     case AD4SM_OPT_FUSED: p->fuse_allowed = value != 0; return AD4SM_OK;
+    case AD4SM_OPT_SORTED: p->sorted_on = value != 0; return AD4SM_OK;
     case AD4SM_OPT_FUSED_LAG:
       if (value < 1 || value > 64) return fail(AD4SM_EINVAL, "lag must be in 1..64");
       p->fz.lag = (int)value;
@@ -731,6 +833,7 @@ int ad4sm_get_info(ad4sm_plan* p, int32_t what, int64_t* value) {
   switch (what) {
     case AD4SM_INFO_FUSED: *value = p->fz.enabled ? (p->fuse_allowed ? 2 : 1) : 0; return AD4SM_OK;  // 0 n/a, 1 available, 2 on
     case AD4SM_INFO_FUSED_STEPS: *value = p->fz.n_steps; return AD4SM_OK;
+    case AD4SM_INFO_SORTED: *value = p->sorted_built ? (p->sorted_on ? 2 : 1) : 0; return AD4SM_OK;
   }
   return fail(AD4SM_EINVAL, "unknown info id");
 }

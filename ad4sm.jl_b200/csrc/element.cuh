@@ -266,6 +266,9 @@ AD4SM_DI void column_u_acc(int q, int Prt, const double* recs, int rstride, cons
     if (a >= N) a -= N;
     ga[o] = gS + a;
   }
+#if defined(AD4SM_VAR_UNROLL2)
+#pragma unroll 2
+#endif
   for (int gp = 0; gp < P; gp++) {
     const Mem rec{recs + gp * rstride};
     const int goff = gp * gstride;
@@ -282,7 +285,9 @@ AD4SM_DI void column_u_acc(int q, int Prt, const double* recs, int rstride, cons
       //   T_l[(k,j)] = Σ_m A_(kj)(ml) ∇N_q,m ;   K(a,q)[j][l] += Σ_k ∇N_a,k T_l[(k,j)]
 #pragma unroll
       for (int l = 0; l < D; l++) {
+#if !defined(AD4SM_VAR_NOFENCE)
         AD4SM_SCHED_FENCE();  // keep the record loads of one column from being hoisted over the previous one
+#endif
         double Tl[DD];
 #pragma unroll
         for (int I = 0; I < DD; I++) {

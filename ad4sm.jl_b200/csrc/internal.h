@@ -25,7 +25,15 @@ struct AsmArgs {
   double* nzval;                // [dpn*dpn*n_blocks]
   double* r;                    // [dpn*n_nodes]
   unsigned long long* n_zero;   // [1] stored exact zeros in nzval
+  // destination-sorted staging (DESIGN.md "K2s"): contributions of one unordered node pair are contiguous
+  long long n_pairs;            // unordered node pairs {i <= p} of the pattern (0: not built)
+  const unsigned* cptr;         // [n_pairs+1] contribution range of each pair (in `elems` order inside a pair)
+  const unsigned* out_up;       // [n_pairs] nzval offset of block (i, p)
+  const unsigned* out_lo;       // [n_pairs] nzval offset of block (p, i)   (== out_up for i == p)
+  const unsigned* nn_pack;      // [n_pairs] row lengths: nn(i) | nn(p) << 16
+  const double* C;              // [ne*NPB][CBLK] contribution blocks, canonical orientation (row node <= col node)
 };
+constexpr int CBLK3 = 10;       // doubles per 3x3 contribution block: 9 + 1 pad = 80 B, 16-byte aligned
 
 // Work lists of the FUSED persistent kernel (K1 + K2 + K3 in one launch, DESIGN.md "Fused path").  The element groups a
 // warp processes in its iteration `it` form "step" it; a node-pair block / residual row becomes ready when the last
@@ -61,6 +69,9 @@ struct K1Args {
   double* Ke;           // [slots][NPB][DB*DB]  cyclic symmetric block storage (element.cuh)
   double* re;           // [slots][N][DB]
   double* phie;         // [slots]
+  // destination-sorted staging: cpos[slot*NPB + block] = position << 1 | transposed; nullptr = element-major staging
+  const unsigned* cpos;
+  double* C;
   // fused assembly (fz.enabled): the persistent kernel also runs K2/K3 over `as`
   FuseArgs fz;
   AsmArgs as;
@@ -80,6 +91,7 @@ cudaError_t launch_k1(const K1Args& a, int mode, cudaStream_t s);
 const char* k1_unsupported_reason(int D, int N, int P, int mf, int mode);
 cudaError_t launch_k2(const AsmArgs& a, cudaStream_t s);  // Kt values
 cudaError_t launch_k3(const AsmArgs& a, cudaStream_t s);  // residual
+cudaError_t launch_k2s(const AsmArgs& a, cudaStream_t s); // Kt values from the destination-sorted staging
 int phi_reduce_partials();
 cudaError_t launch_phi_reduce(const double* phie, long long n, double* partials, double* phi, cudaStream_t s);
 cudaError_t launch_pattern(const AsmArgs& a, long long* colptr, long long* rowval, cudaStream_t s);

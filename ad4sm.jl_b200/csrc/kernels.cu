@@ -349,9 +349,42 @@ __device__ __forceinline__ void k1_phase1(const MatDev* mat, int q, bool valid, 
 // at k1_phase1, and the stores may alias the records other lanes are still reading: accumulate, __syncwarp, store.
 template <int D, int N, int PT>
 __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active, bool want_K, bool staged, const double* recs,
-                                          const double* gS, double* kout_s, double* rout_s, double* kout_g, double* rout_g) {
-  double acc[N / 2 + 1][D * D], rq[D];
+                                          const double* gS, double* kout_s, double* rout_s, double* kout_g, double* rout_g,
+                                          const unsigned* cpos_e, double* C) {
+  constexpr int NO = N / 2 + 1, DD = D * D;
+  // destination-sorted staging: this lane's block positions, fetched now so that the loads fly during the contraction
+  unsigned cp[NO];
+  if (cpos_e) {
+#pragma unroll
+    for (int o = 0; o < NO; o++) cp[o] = (active && o < n_offsets(N, q)) ? __ldg(cpos_e + o * N + q) : 0xffffffffu;
+  }
+  double acc[NO][DD], rq[D];
   column_u_acc<D, N, PT, VecMem>(q, P, recs, rstride, gS, N, (PT ? PT : P) * N, want_K, acc, rq);
+  if (cpos_e) {  // (D == 3 only) blocks go straight from registers to their sorted slots, 16 bytes at a time
+    if constexpr (D == 3) {
+      if (active) {
+#pragma unroll
+        for (int o = 0; o < NO; o++) {
+          if (cp[o] != 0xffffffffu) {
+            const bool tr = cp[o] & 1u;
+            double2* dst = reinterpret_cast<double2*>(C + (long long)(cp[o] >> 1) * CBLK3);
+            double v[10];
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+              for (int l = 0; l < 3; l++) v[j * 3 + l] = tr ? acc[o][l * 3 + j] : acc[o][j * 3 + l];
+            v[9] = 0.0;
+#pragma unroll
+            for (int t = 0; t < 5; t++) dst[t] = make_double2(v[2 * t], v[2 * t + 1]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < D; j++) rout_g[q * D + j] = rq[j];
+      }
+    }
+    __syncwarp();
+    return;
+  }
   __syncwarp();
   if (active) {
     if (staged) {  // shared-memory staging (STS), leaves with the bulk stores
@@ -520,17 +553,19 @@ __global__ void __launch_bounds__(256, 1)
 
     // phase 2: one column node per lane; the element blocks and residual go to the
     // staging area in the (then dead) record region, or straight to global memory when they do not fit
-    const bool staged = a.want_K && L.kout_el;
+    const bool sorted = a.cpos != nullptr && a.want_K;
+    const unsigned* cpos_e = sorted ? a.cpos + slot * (long long)NPB : nullptr;
+    const bool staged = a.want_K && L.kout_el && !sorted;
     unsigned char* stg = ws + (size_t)el * L.kout_el;
     constexpr int PTC = (N == 8) ? 8 : ((N == 4) ? 4 : 0);  // the usual Gauss count of the shape, compiled in
     if (PTC && P == PTC)
       k1_phase2<D, N, PTC>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS, reinterpret_cast<double*>(stg),
                            reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
-                           a.re + slot * (long long)(N * D));
+                           a.re + slot * (long long)(N * D), cpos_e, a.C);
     else
       k1_phase2<D, N, 0>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS, reinterpret_cast<double*>(stg),
                          reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
-                         a.re + slot * (long long)(N * D));
+                         a.re + slot * (long long)(N * D), cpos_e, a.C);
     if (valid && q == 0) {  // ϕ_e = Σ_gp w ψ, in Gauss-point order (elasticelements.jl:199-206)
       double ssum = 0.0;
       for (int gp = 0; gp < P; gp++) ssum += psiS[gp];
@@ -716,6 +751,10 @@ bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c) {
   int warps = (227 * 1024) / L.bytes;
   if (warps < 1) return false;
   if (warps > 8) warps = 8;
+  if (const char* e = getenv("AD4SM_K1_WARPS")) {  // experiment knob (profiles/): warps per CTA of the persistent K1
+    const int w = atoi(e);
+    if (w >= 1 && w < warps) warps = w;
+  }
   const long long n_groups = (ne + c->EW - 1) / c->EW;
   if (n_groups < warps) warps = (int)(n_groups > 0 ? n_groups : 1);
   long long grid = (n_groups + warps - 1) / warps;
@@ -831,6 +870,69 @@ cudaError_t launch_k2(const AsmArgs& a, cudaStream_t s) {
       default: return cudaErrorInvalidValue;
     }
   }
+  return cudaGetLastError();
+}
+// ---- K2s: Kt values from the destination-sorted staging.  One thread per unordered node pair {i <= p}: its
+// contributions are contiguous (streaming 16-byte loads, no source-map indirection, neighbouring threads read
+// neighbouring memory), summed in `elems` order like K2; the sum is written to block (i, p) and, transposed, to
+// block (p, i) -- both triangles carry the same bits.  (A CTA-cooperative variant that streams the range through
+// shared memory was measured slower: 1.58 vs 1.44 ms.)
+#define AD4SM_K2S_MINB 4
+#define AD4SM_K2S_UNROLL2 1  // measured: 1.39 ms vs 1.43 ms rolled; occupancy variants (40 / 32 registers) were no faster
+constexpr int K2S_THREADS = 256;
+__device__ __forceinline__ void k2s_add(double* acc, const double2* B) {
+  const double2 v0 = B[0], v1 = B[1], v2 = B[2], v3 = B[3], v4 = B[4];
+  acc[0] += v0.x, acc[1] += v0.y, acc[2] += v1.x, acc[3] += v1.y, acc[4] += v2.x;
+  acc[5] += v2.y, acc[6] += v3.x, acc[7] += v3.y, acc[8] += v4.x;
+}
+__global__ void __launch_bounds__(K2S_THREADS, AD4SM_K2S_MINB) k2s_kernel3(const AsmArgs a) {
+  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= a.n_pairs) return;
+  const unsigned c0 = __ldg(a.cptr + u), c1 = __ldg(a.cptr + u + 1);
+  const unsigned oup = __ldg(a.out_up + u), olo = __ldg(a.out_lo + u), nn = __ldg(a.nn_pack + u);
+  double acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; t++) acc[t] = 0.0;
+  const double2* C2 = reinterpret_cast<const double2*>(a.C);
+#ifdef AD4SM_K2S_UNROLL2
+  unsigned c = c0;
+  for (; c + 1 < c1; c += 2) {  // two blocks in flight; still folded in ascending (`elems`) order
+    const double2* B = C2 + (long long)c * (CBLK3 / 2);
+    const double2 v0 = B[0], v1 = B[1], v2 = B[2], v3 = B[3], v4 = B[4];
+    const double2 w0 = B[5], w1 = B[6], w2 = B[7], w3 = B[8], w4 = B[9];
+    acc[0] += v0.x, acc[1] += v0.y, acc[2] += v1.x, acc[3] += v1.y, acc[4] += v2.x;
+    acc[5] += v2.y, acc[6] += v3.x, acc[7] += v3.y, acc[8] += v4.x;
+    acc[0] += w0.x, acc[1] += w0.y, acc[2] += w1.x, acc[3] += w1.y, acc[4] += w2.x;
+    acc[5] += w2.y, acc[6] += w3.x, acc[7] += w3.y, acc[8] += w4.x;
+  }
+  if (c < c1) k2s_add(acc, C2 + (long long)c * (CBLK3 / 2));
+#else
+  for (unsigned c = c0; c < c1; c++) k2s_add(acc, C2 + (long long)c * (CBLK3 / 2));
+#endif
+  const int dpn = 3;
+  const long long su = (long long)dpn * (nn & 0xffffu), sl = (long long)dpn * (nn >> 16);
+  int nz = 0;
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+      a.nzval[oup + j * su + l] = acc[j * 3 + l];
+      nz += (acc[j * 3 + l] == 0.0);
+    }
+  if (olo != oup) {
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) a.nzval[olo + l * sl + j] = acc[j * 3 + l];
+    nz *= 2;
+  }
+  if (nz) atomicAdd(a.n_zero, (unsigned long long)nz);
+}
+cudaError_t launch_k2s(const AsmArgs& a, cudaStream_t s) {
+  if (a.DB != 3 || a.dpn != 3 || a.n_pairs <= 0) return cudaErrorInvalidValue;
+  cudaError_t err = cudaMemsetAsync(a.n_zero, 0, sizeof(unsigned long long), s);
+  if (err != cudaSuccess) return err;
+  k2s_kernel3<<<(unsigned)((a.n_pairs + K2S_THREADS - 1) / K2S_THREADS), K2S_THREADS, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_k3(const AsmArgs& a, cudaStream_t s) {

@@ -168,8 +168,10 @@ int ad4sm_sync(ad4sm_plan* plan);
  * AD4SM_INFO_FUSED: 0 = not available for this plan, 1 = available, 2 = switched on. */
 #define AD4SM_OPT_FUSED 1
 #define AD4SM_OPT_FUSED_LAG 2     /* steps between staging a group and assembling the rows it completes */
+#define AD4SM_OPT_SORTED 3        /* destination-sorted staging + streaming assembly (K2s); default on where available */
 #define AD4SM_INFO_FUSED 1
 #define AD4SM_INFO_FUSED_STEPS 2
+#define AD4SM_INFO_SORTED 3       /* 0 = not available for this plan, 1 = available but off, 2 = on */
 int ad4sm_set_option(ad4sm_plan* plan, int32_t option, int64_t value);
 int ad4sm_get_info(ad4sm_plan* plan, int32_t what, int64_t* value);
 

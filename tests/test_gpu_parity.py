@@ -304,3 +304,21 @@ def test_ogden_hex8_contract_properties():
     # undeformed state: all stretches equal (the spectral formulas' singular point)
     p0, r0, K0 = plan.makeϕrKt(np.zeros_like(u))
     assert abs(p0) <= 1e-12 and np.abs(r0).max() <= 1e-9 * np.abs(K0.nzval).max() and np.all(np.isfinite(K0.nzval))
+
+
+@pytest.mark.parametrize("make", [lambda: K.hex_case((7, 6, 5)), lambda: K.hex_case((5, 4, 3), mat=Ma.MooneyRivlin(800.0, 200.0, 5000.0)),
+                                  lambda: K.hex_case((20, 20, 20))], ids=["hex8-nh", "hex8-mr", "hex8-8000"])
+def test_sorted_staging_matches_element_major_staging(make):
+    """Destination-sorted staging + streaming assembly (K2s) vs element-major staging + gather assembly (K2): the same
+    contributions are summed in the same `elems` order, so every bit must agree."""
+    b, u = make()
+    plan = El.Plan(b, u.shape[1], 3)
+    assert plan.info(capi.INFO_SORTED) == 2
+    s = plan.makeϕrKt(u)
+    plan.set_option(capi.OPT_SORTED, 0)
+    e = plan.makeϕrKt(u)
+    assert s[0] == e[0] and np.array_equal(s[1], e[1])
+    assert np.array_equal(s[2].colptr, e[2].colptr) and np.array_equal(s[2].rowval, e[2].rowval)
+    assert np.array_equal(s[2].nzval, e[2].nzval)
+    Kd = s[2].to_scipy()
+    assert abs(Kd - Kd.T).max() == 0.0
