@@ -96,6 +96,12 @@ struct ad4sm_plan {
   long long n_pairs = 0;
   unsigned *cpos = nullptr, *cptr = nullptr, *out_up = nullptr, *out_lo = nullptr, *nn_pack = nullptr;
   double* C = nullptr;
+  // fused + sorted (FuseArgs mode 2): batches of node pairs by readiness step
+  uint4* batch_rec = nullptr;
+  unsigned* sb_ptr = nullptr;
+  unsigned* done2 = nullptr;
+  int n_steps2 = 0, fused_mode_last = 0;
+  long long gstep2 = 0, n_groups2 = 0;
 };
 
 template <class T> static int dev_alloc(ad4sm_plan* p, T** ptr, size_t count) {
@@ -520,6 +526,54 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
         }
         p->n_pairs = U;
         p->sorted_built = true;
+        // ---- batches for the fused K2s: consecutive pairs, contiguous contributions, readiness = prefix max ----
+        const long long gstep = (long long)c.grid * c.warps;
+        const long long n_groups = (ne + c.EW - 1) / c.EW;
+        const int n_steps = (int)((n_groups + gstep - 1) / gstep);
+        const int cap_blocks = std::min<int>(FUSE_BATCH_BLOCKS, c.rec_bytes / (CBLK3 * 8));
+        std::vector<int> pready(U, 0);
+        for (size_t k = 0; k < n_contrib; k++) {
+          const int st = (int)(((long long)(k / NPB) / c.EW) / gstep);
+          int& r = pready[dest[k] >> 1];
+          if (st > r) r = st;
+        }
+        std::vector<uint4> brec;
+        std::vector<int> bready;
+        bool fits = cap_blocks >= 8;
+        for (long long u = 0; u < U && fits;) {
+          long long v = u;
+          int rdy = 0;
+          while (v < U && v - u < FUSE_BATCH_PAIRS && (int)(cptr[v + 1] - cptr[u]) <= cap_blocks) {
+            rdy = std::max(rdy, pready[v]);
+            v++;
+          }
+          if (v == u) {  // a single pair with more contributions than the landing buffer holds (very high valence)
+            fits = false;
+            break;
+          }
+          brec.push_back(make_uint4((unsigned)u, (unsigned)v, cptr[u], cptr[v]));
+          bready.push_back(rdy);
+          u = v;
+        }
+        if (fits) {
+          std::vector<unsigned> sb_ptr(n_steps + 1, 0);
+          int pm = 0;
+          for (size_t k = 0; k < brec.size(); k++) {
+            pm = std::max(pm, bready[k]);
+            sb_ptr[pm + 1]++;
+          }
+          for (int t = 0; t < n_steps; t++) sb_ptr[t + 1] += sb_ptr[t];
+          int rc3 = dev_upload(p, &p->batch_rec, brec.data(), brec.size());
+          if (!rc3) rc3 = dev_upload(p, &p->sb_ptr, sb_ptr.data(), sb_ptr.size());
+          if (!rc3) rc3 = dev_alloc(p, &p->done2, (size_t)n_steps + 1);
+          if (rc3) {
+            ad4sm_plan_destroy(p);
+            return rc3;
+          }
+          p->n_steps2 = n_steps;
+          p->gstep2 = gstep;
+          p->n_groups2 = n_groups;
+        }
       }
     }
   }
@@ -721,15 +775,17 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
   p->ev_cur = p->prof ? next_events(p) : nullptr;
   if (p->ev_cur) CK(cudaEventRecord(p->ev_cur->e[0], p->stream));
   long long launches = 0;
-  const bool fuse = internal && p->fz.enabled && want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U) && p->fuse_allowed;
+  const bool kmode_ok = internal && want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U);
+  const bool sorted_ok = kmode_ok && p->sorted_built && p->sorted_on;
+  const bool fuse2 = sorted_ok && p->fuse_allowed && p->batch_rec != nullptr;      // K1 + K2s in one kernel
+  const bool fuse = !fuse2 && kmode_ok && p->fz.enabled && p->fuse_allowed;       // K1 + K2 + K3 in one kernel
+  const bool sorted = sorted_ok && !fuse;
+  p->fused_mode_last = fuse2 ? 2 : (fuse ? 1 : 0);
   p->fused_last = fuse;
-  const bool sorted =
-      internal && !fuse && p->sorted_built && p->sorted_on && want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U);
   p->sorted_last = sorted;
-  if (fuse) {
-    CK(cudaMemsetAsync(p->fz.done, 0, sizeof(unsigned) * ((size_t)p->fz.n_steps + 1), p->stream));
-    CK(cudaMemsetAsync(p->n_zero_dev, 0, sizeof(unsigned long long), p->stream));
-  }
+  if (fuse) CK(cudaMemsetAsync(p->fz.done, 0, sizeof(unsigned) * ((size_t)p->fz.n_steps + 1), p->stream));
+  if (fuse2) CK(cudaMemsetAsync(p->done2, 0, sizeof(unsigned) * ((size_t)p->n_steps2 + 1), p->stream));
+  if (fuse || fuse2) CK(cudaMemsetAsync(p->n_zero_dev, 0, sizeof(unsigned long long), p->stream));
   for (const BatchPlan& b : p->batches) {
     if (b.halo) continue;
     K1Args a = b.k;
@@ -747,6 +803,24 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
     if (sorted) {
       a.cpos = p->cpos;
       a.C = p->C;
+      static int tma = -1;
+      if (tma < 0) {
+        const char* e = getenv("AD4SM_SORTED_TMA");
+        tma = e ? atoi(e) : 0;  // measured: 36 x 80-byte bulk copies per element make K1 2.74 ms; plain STG.128 1.93 ms
+      }
+      a.sorted_tma = tma;
+    }
+    if (fuse2) {
+      a.fz = FuseArgs{};
+      a.fz.enabled = 2;
+      a.fz.lag = p->fz.lag > 0 ? p->fz.lag : 2;
+      a.fz.n_steps = p->n_steps2;
+      a.fz.gstep = p->gstep2;
+      a.fz.n_groups = p->n_groups2;
+      a.fz.done = p->done2;
+      a.fz.batch_rec = p->batch_rec;
+      a.fz.sb_ptr = p->sb_ptr;
+      a.as = asm_args(p, AD4SM_FIELD_U);
     }
     cudaError_t e = launch_k1(a, kmode, p->stream);
     if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("K1 launch: ") + cudaGetErrorString(e));
@@ -771,7 +845,7 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   if (!p->fused_last) CK(launch_k3(asm_args(p, field), p->stream));
   CK(launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, p->stream));
   CK(cudaEventRecord(p->ev_r_ready, p->stream));
-  if (!p->fused_last && want_K) {
+  if (!p->fused_last && p->fused_mode_last != 2 && want_K) {
     if (p->sorted_last) CK(launch_k2s(asm_args(p, field), p->stream));
     else CK(launch_k2(asm_args(p, field), p->stream));
   }
@@ -831,7 +905,7 @@ int ad4sm_set_option(ad4sm_plan* p, int32_t option, int64_t value) {
 int ad4sm_get_info(ad4sm_plan* p, int32_t what, int64_t* value) {
   if (!p || !value) return fail(AD4SM_EINVAL, "plan or value is NULL");
   switch (what) {
-    case AD4SM_INFO_FUSED: *value = p->fz.enabled ? (p->fuse_allowed ? 2 : 1) : 0; return AD4SM_OK;  // 0 n/a, 1 available, 2 on
+    case AD4SM_INFO_FUSED: *value = (p->fz.enabled || p->batch_rec) ? (p->fuse_allowed ? 2 : 1) : 0; return AD4SM_OK;
     case AD4SM_INFO_FUSED_STEPS: *value = p->fz.n_steps; return AD4SM_OK;
     case AD4SM_INFO_SORTED: *value = p->sorted_built ? (p->sorted_on ? 2 : 1) : 0; return AD4SM_OK;
   }

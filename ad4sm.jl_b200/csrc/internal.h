@@ -47,7 +47,13 @@ struct FuseArgs {
   const unsigned* blk_sorted;  // [n_blocks] block ids by readiness step (stable: ascending block id inside a step)
   const unsigned* kr_ptr;      // [n_steps+1] into row_sorted
   const unsigned* row_sorted;  // [n_nodes] node ids by readiness step
+  // enabled == 2: destination-sorted staging.  Consecutive node pairs are grouped into batches whose contribution
+  // blocks are one contiguous range (<= FUSE_BATCH_BLOCKS); batches are listed in pair order, which is also their
+  // (prefix-max) readiness order.
+  const uint4* batch_rec;      // [n_batches] {first pair, end pair, first contribution, end contribution}
+  const unsigned* sb_ptr;      // [n_steps+1] batches that become ready with each step
 };
+constexpr int FUSE_BATCH_PAIRS = 64, FUSE_BATCH_BLOCKS = 160;
 
 // One K1 launch = one batch (SoA copy of a Vector{CEElem}/Vector{CPElem}, elements.jl:71-111).
 struct K1Args {
@@ -72,6 +78,7 @@ struct K1Args {
   // destination-sorted staging: cpos[slot*NPB + block] = position << 1 | transposed; nullptr = element-major staging
   const unsigned* cpos;
   double* C;
+  int sorted_tma;       // sorted blocks leave through shared memory + one 80-byte bulk copy each (else plain STG.128)
   // fused assembly (fz.enabled): the persistent kernel also runs K2/K3 over `as`
   FuseArgs fz;
   AsmArgs as;
@@ -84,6 +91,7 @@ struct K1Config {
   int warps;       // warps per CTA
   int grid;        // CTAs
   int staged;      // blocks/residual leave through the shared-memory staging + bulk stores
+  int rec_bytes;   // bytes of the per-warp record area (landing buffer of the fused K2s batches)
 };
 bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c);
 

@@ -153,7 +153,7 @@ static WarpLayout k1p_layout(int D, int N, int P, int LP, bool pf) {
   L.psi_off = off;
   off += rup(EW * P * 8, 16);
   L.bar_off = off;
-  off += 32;
+  off += 48;  // 5 mbarriers (the fifth: fused K2s batches), padded to 16 bytes
   L.bytes = rup(off, 128);
   // epilogue: the element blocks and residual are staged in the (dead) record region when they fit, and leave
   // with one bulk copy each (16-byte granularity)
@@ -355,32 +355,53 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
   // destination-sorted staging: this lane's block positions, fetched now so that the loads fly during the contraction
   unsigned cp[NO];
   if (cpos_e) {
+    // volatile asm: the compiler must not sink these loads to their use after the contraction (it did, and the
+    // epilogue then stalled on them)
 #pragma unroll
-    for (int o = 0; o < NO; o++) cp[o] = (active && o < n_offsets(N, q)) ? __ldg(cpos_e + o * N + q) : 0xffffffffu;
+    for (int o = 0; o < NO; o++) {
+      cp[o] = 0xffffffffu;
+      if (active && o < n_offsets(N, q))
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cp[o]) : "l"(cpos_e + o * N + q));
+    }
   }
   double acc[NO][DD], rq[D];
   column_u_acc<D, N, PT, VecMem>(q, P, recs, rstride, gS, N, (PT ? PT : P) * N, want_K, acc, rq);
-  if (cpos_e) {  // (D == 3 only) blocks go straight from registers to their sorted slots, 16 bytes at a time
+  if (cpos_e) {  // (D == 3 only) every block goes to its own sorted slot
     if constexpr (D == 3) {
+      __syncwarp();  // all lanes are done reading the records: their area becomes the staging
       if (active) {
 #pragma unroll
         for (int o = 0; o < NO; o++) {
           if (cp[o] != 0xffffffffu) {
             const bool tr = cp[o] & 1u;
-            double2* dst = reinterpret_cast<double2*>(C + (long long)(cp[o] >> 1) * CBLK3);
             double v[10];
 #pragma unroll
             for (int j = 0; j < 3; j++)
 #pragma unroll
               for (int l = 0; l < 3; l++) v[j * 3 + l] = tr ? acc[o][l * 3 + j] : acc[o][j * 3 + l];
             v[9] = 0.0;
+            if (kout_s) {  // via shared memory + one 80-byte bulk copy (TMA) per block: no store burst through the LSU
+              double2* st = reinterpret_cast<double2*>(kout_s + (o * N + q) * CBLK3);
 #pragma unroll
-            for (int t = 0; t < 5; t++) dst[t] = make_double2(v[2 * t], v[2 * t + 1]);
+              for (int t = 0; t < 5; t++) st[t] = make_double2(v[2 * t], v[2 * t + 1]);
+            } else {
+              double2* dst = reinterpret_cast<double2*>(C + (long long)(cp[o] >> 1) * CBLK3);
+#pragma unroll
+              for (int t = 0; t < 5; t++) dst[t] = make_double2(v[2 * t], v[2 * t + 1]);
+            }
           }
+        }
+        if (kout_s) {
+          fence_proxy_async();  // this lane's own STS -> its own bulk copies: no cross-lane dependency
+#pragma unroll
+          for (int o = 0; o < NO; o++)
+            if (cp[o] != 0xffffffffu)
+              bulk_store(C + (long long)(cp[o] >> 1) * CBLK3, smem_u32(kout_s + (o * N + q) * CBLK3), (unsigned)(CBLK3 * 8));
         }
 #pragma unroll
         for (int j = 0; j < D; j++) rout_g[q * D + j] = rq[j];
       }
+      if (kout_s) bulk_commit();
     }
     __syncwarp();
     return;
@@ -440,6 +461,84 @@ __device__ __forceinline__ void fused_assemble_step(const K1Args& a, int t, int 
   }
 }
 
+__device__ __forceinline__ void k2s_add(double* acc, const double2* B);
+// ---- fused path, destination-sorted staging: this warp's batches of node pairs that became ready with step t -------
+// A batch's contribution blocks are one contiguous range of C: they arrive with ONE bulk copy (TMA) in the warp's
+// record area (dead between phase 2 and the next phase 1) while the lanes fetch their pairs' metadata; then every
+// lane folds its (<= 2) pairs in `elems` order and writes block (i, p) and its mirror -- as K2s does.
+__device__ __forceinline__ void fused_wait_steps(const K1Args& a, int t, int lane, int& verified) {
+  while (verified <= t) {
+    if (lane == 0) {
+      const long long first = (long long)verified * a.fz.gstep;
+      long long left = a.fz.n_groups - first;
+      const unsigned target = (unsigned)(left < a.fz.gstep ? left : a.fz.gstep);
+      const unsigned* flag = a.fz.done + verified;
+      while (ld_acquire(flag) < target) __nanosleep(64);
+    }
+    __syncwarp();
+    verified++;
+  }
+}
+__device__ __forceinline__ void fused_sorted_step(const K1Args& a, int t, int gwarp, int n_warps, int lane, unsigned char* ws,
+                                                  unsigned kbar, unsigned& kphase, int& verified, int& nzero) {
+  if (t >= a.fz.n_steps) return;
+  fused_wait_steps(a, t, lane, verified);
+  const unsigned b0 = __ldg(a.fz.sb_ptr + t), b1 = __ldg(a.fz.sb_ptr + t + 1);
+  const unsigned cnt = b1 - b0, chunk = (cnt + n_warps - 1) / n_warps;
+  unsigned k0 = b0 + (unsigned)gwarp * chunk, k1 = k0 + chunk;
+  if (k1 > b1) k1 = b1;
+  const double2* smc = reinterpret_cast<const double2*>(ws);
+  for (unsigned k = k0; k < k1; k++) {
+    const uint4 rec = __ldg(a.fz.batch_rec + k);  // {p0, p1, c_lo, c_hi}
+    const unsigned bytes = (rec.w - rec.z) * (unsigned)(CBLK3 * 8);
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(kbar, bytes);
+      tma_load_1d(smem_u32(ws), a.as.C + (long long)rec.z * CBLK3, bytes, kbar);
+    }
+    unsigned c0[2], c1[2], oup[2], olo[2], nn[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const unsigned u = rec.x + lane + 32 * h;
+      const bool on = u < rec.y;
+      c0[h] = on ? __ldg(a.as.cptr + u) : 0u;
+      c1[h] = on ? __ldg(a.as.cptr + u + 1) : 0u;
+      oup[h] = on ? __ldg(a.as.out_up + u) : 0u;
+      olo[h] = on ? __ldg(a.as.out_lo + u) : 0u;
+      nn[h] = on ? __ldg(a.as.nn_pack + u) : 0u;
+    }
+    mbar_wait(kbar, kphase);
+    kphase ^= 1u;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      if (rec.x + lane + 32 * h < rec.y) {
+        double acc[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) acc[i] = 0.0;
+        for (unsigned c = c0[h]; c < c1[h]; c++) k2s_add(acc, smc + (c - rec.z) * (CBLK3 / 2));
+        const long long su = 3ll * (nn[h] & 0xffffu), sl = 3ll * (nn[h] >> 16);
+        int nz = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+          for (int l = 0; l < 3; l++) {
+            a.as.nzval[oup[h] + j * su + l] = acc[j * 3 + l];
+            nz += (acc[j * 3 + l] == 0.0);
+          }
+        if (olo[h] != oup[h]) {
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int l = 0; l < 3; l++) a.as.nzval[olo[h] + l * sl + j] = acc[j * 3 + l];
+          nz *= 2;
+        }
+        nzero += nz;
+      }
+    }
+    __syncwarp();  // the record area is reused by the next batch / the next phase 1
+  }
+}
+
 // ---- K1, u-dual, persistent, LP lanes per element, TMA-staged inputs ------------------------------
 template <int D, int N, int LP, int MF, bool PF>
 __global__ void __launch_bounds__(256, 1)
@@ -457,7 +556,7 @@ __global__ void __launch_bounds__(256, 1)
   const long long gstep = (long long)gridDim.x * warps_per_cta;
   const unsigned bar0 = smem_u32(ws0 + L.bar_off);
   if (lane == 0) {
-    for (int i = 0; i < 4; i++) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < 5; i++) mbar_init(bar0 + 8 * i, 1);
     fence_mbar_init();
   }
   __syncwarp();
@@ -489,7 +588,9 @@ __global__ void __launch_bounds__(256, 1)
     tma_load_1d(smem_u32(ws + (L.n_off + (s) * L.n_stg)), a.nodes + e0 * N, nbytes, bar0 + 16 + 8 * s);
   };
 
-  const bool fused = a.fz.enabled != 0;
+  const bool fused = a.fz.enabled == 1;   // element-major staging, K2 + K3 inside the kernel
+  const bool fused2 = a.fz.enabled == 2;  // destination-sorted staging, K2s inside the kernel
+  unsigned kphase = 0;
   const int gwarp = blockIdx.x * warps_per_cta + warp;  // global warp id = its first element group
   int verified = 0;                                      // steps [0, verified) are known to be published (fused path)
   int nzero = 0, n_it = 0;
@@ -521,6 +622,11 @@ __global__ void __launch_bounds__(256, 1)
     mbar_wait(bar0 + 8 * s, (unsigned)((it >> 1) & 1));                        // this group's ∇N, wgt, N
     if (has_next) mbar_wait(bar0 + 16 + 8 * (s ^ 1), (unsigned)(((it + 1) >> 1) & 1));  // next group's node ids
     cp_async_wait_all();                                                        // this group's u
+    if (a.cpos && a.sorted_tma) {  // sorted staging through per-lane bulk copies
+      if (fused2 && it > 0) bulk_wait_all();  // complete (visible) before the step is published
+      else bulk_wait_read_all();              // their shared-memory source may be overwritten
+    }
+    if (fused2 && it > 0) __threadfence();  // this lane's block stores of step it-1 are visible GPU-wide
     if (lane == 0) {
       if (fused && it > 0) {
         // publish step it-1: its bulk stores are complete (they had a whole iteration), make them visible GPU-wide
@@ -532,6 +638,7 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
     __syncwarp();
+    if (fused2 && it > 0 && lane == 0) red_release_add(a.fz.done + (it - 1), 1u);  // after every lane's fence
 
     const long long e = grp * EW + el;
     const bool valid = e < a.ne;
@@ -556,14 +663,17 @@ __global__ void __launch_bounds__(256, 1)
     const bool sorted = a.cpos != nullptr && a.want_K;
     const unsigned* cpos_e = sorted ? a.cpos + slot * (long long)NPB : nullptr;
     const bool staged = a.want_K && L.kout_el && !sorted;
-    unsigned char* stg = ws + (size_t)el * L.kout_el;
+    const bool sorted_tma = sorted && (NPB * CBLK3 * 8 <= L.rec_el) && a.sorted_tma;
+    unsigned char* stg = ws + (size_t)el * (sorted ? L.rec_el : L.kout_el);
     constexpr int PTC = (N == 8) ? 8 : ((N == 4) ? 4 : 0);  // the usual Gauss count of the shape, compiled in
     if (PTC && P == PTC)
-      k1_phase2<D, N, PTC>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS, reinterpret_cast<double*>(stg),
+      k1_phase2<D, N, PTC>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS,
+                           (sorted && !sorted_tma) ? nullptr : reinterpret_cast<double*>(stg),
                            reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
                            a.re + slot * (long long)(N * D), cpos_e, a.C);
     else
-      k1_phase2<D, N, 0>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS, reinterpret_cast<double*>(stg),
+      k1_phase2<D, N, 0>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS,
+                         (sorted && !sorted_tma) ? nullptr : reinterpret_cast<double*>(stg),
                          reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
                          a.re + slot * (long long)(N * D), cpos_e, a.C);
     if (valid && q == 0) {  // ϕ_e = Σ_gp w ψ, in Gauss-point order (elasticelements.jl:199-206)
@@ -588,7 +698,22 @@ __global__ void __launch_bounds__(256, 1)
     }
     __syncwarp();
     if (fused && it >= a.fz.lag) fused_assemble_step<D>(a, it - a.fz.lag, gwarp, (int)gstep, lane, verified, nzero);
+    if (fused2 && a.sorted_tma) {  // the record area is about to receive K2s batches: its bulk stores must have read it
+      bulk_wait_read_all();
+      __syncwarp();
+    }
+    if (fused2 && it >= a.fz.lag)
+      fused_sorted_step(a, it - a.fz.lag, gwarp, (int)gstep, lane, ws, bar0 + 32, kphase, verified, nzero);
     n_it = it + 1;
+  }
+  if (a.cpos && a.sorted_tma) {
+    if (fused2) bulk_wait_all();
+    else bulk_wait_read_all();
+  }
+  if (fused2 && n_it > 0) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) red_release_add(a.fz.done + (n_it - 1), 1u);
   }
   if (lane == 0) {
     if (fused && n_it > 0) {
@@ -604,6 +729,14 @@ __global__ void __launch_bounds__(256, 1)
     int t = n_it - a.fz.lag;
     if (t < 0) t = 0;
     for (; t < a.fz.n_steps; t++) fused_assemble_step<D>(a, t, gwarp, (int)gstep, lane, verified, nzero);
+    for (int o = 16; o > 0; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
+    if (lane == 0 && nzero) atomicAdd(a.as.n_zero, (unsigned long long)nzero);
+  }
+  if (fused2) {
+    __syncwarp();
+    int t = n_it - a.fz.lag;
+    if (t < 0) t = 0;
+    for (; t < a.fz.n_steps; t++) fused_sorted_step(a, t, gwarp, (int)gstep, lane, ws, bar0 + 32, kphase, verified, nzero);
     for (int o = 16; o > 0; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
     if (lane == 0 && nzero) atomicAdd(a.as.n_zero, (unsigned long long)nzero);
   }
@@ -745,7 +878,7 @@ bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c) {
   if (!lanes_for(D, N, P, LP)) return false;
   c->persistent = LP > 1;
   c->EW = 32 / LP;
-  c->warps = c->grid = c->staged = 0;
+  c->warps = c->grid = c->staged = c->rec_bytes = 0;
   if (LP == 1) return true;
   const WarpLayout L = k1p_layout(D, N, P, LP, pf);
   int warps = (227 * 1024) / L.bytes;
@@ -763,6 +896,7 @@ bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c) {
   c->warps = warps;
   c->grid = (int)grid;
   c->staged = L.kout_el != 0;
+  c->rec_bytes = c->EW * L.rec_el;
   return true;
 }
 
@@ -782,7 +916,9 @@ template <int D, int N, int LP, int MF, bool PF> static cudaError_t launch_u_t(c
     if (err != cudaSuccess) return err;
     if (a.fz.enabled) {
       // the fused kernel's warps wait on one another: all CTAs must be co-resident -> cooperative launch
-      if (a.fz.gstep != (long long)c.grid * c.warps || !c.staged || !a.want_K) return cudaErrorInvalidValue;
+      if (a.fz.gstep != (long long)c.grid * c.warps || !a.want_K) return cudaErrorInvalidValue;
+      if (a.fz.enabled == 1 && !c.staged) return cudaErrorInvalidValue;
+      if (a.fz.enabled == 2 && (!a.cpos || D != 3)) return cudaErrorInvalidValue;
       int warps = c.warps;
       void* args[] = {(void*)&a, (void*)&L, (void*)&warps};
       return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)c.grid), dim3((unsigned)(c.warps * 32)), args, smem, s);

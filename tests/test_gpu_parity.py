@@ -230,25 +230,32 @@ def test_two_rank_halo_exchange_single_gpu():
 
 @pytest.mark.parametrize("n", [(6, 5, 4), (30, 30, 30), (40, 37, 29)])
 def test_fused_persistent_kernel_matches_separate_kernels(n):
-    """The fused path (K1+K2+K3 in one cooperative persistent launch, steps published through global counters) must
-    give bitwise the same ϕ, r, Kt as the separate K1 -> K2/K3 launches, and both must match the oracle."""
+    """The four execution modes of a single-batch Hex8 plan -- {element-major, destination-sorted staging} x {separate
+    K1 -> K2 launches, ONE fused cooperative persistent launch with steps published through global counters} -- sum the
+    same contributions in the same `elems` order: ϕ, r and Kt must agree bit for bit, and match the oracle."""
     b, u = K.hex_case(n)
     plan = El.Plan(b, u.shape[1], 3)
-    assert plan.info(capi.INFO_FUSED) >= 1
-    plan.set_option(capi.OPT_FUSED, 1)
-    f = plan.makeϕrKt(u)
-    f2 = plan.makeϕrKt(u)
-    plan.set_option(capi.OPT_FUSED, 0)
-    s = plan.makeϕrKt(u)
-    for x in (f2, s):
-        assert f[0] == x[0] and np.array_equal(f[1], x[1])
-        assert np.array_equal(f[2].colptr, x[2].colptr) and np.array_equal(f[2].rowval, x[2].rowval)
-        assert np.array_equal(f[2].nzval, x[2].nzval)
-    plan.set_option(capi.OPT_FUSED, 1)
-    for lag in (1, 3, 7):
-        plan.set_option(capi.OPT_FUSED_LAG, lag)
-        g = plan.makeϕrKt(u)
-        assert np.array_equal(f[2].nzval, g[2].nzval) and np.array_equal(f[1], g[1])
+    assert plan.info(capi.INFO_FUSED) >= 1 and plan.info(capi.INFO_SORTED) == 2
+    res = {}
+    for sorted_on in (1, 0):
+        for fused_on in (1, 0):
+            plan.set_option(capi.OPT_SORTED, sorted_on)
+            plan.set_option(capi.OPT_FUSED, fused_on)
+            res[(sorted_on, fused_on)] = plan.makeϕrKt(u)
+            again = plan.makeϕrKt(u)
+            assert np.array_equal(again[2].nzval, res[(sorted_on, fused_on)][2].nzval)
+    f = res[(1, 1)]
+    for key, x in res.items():
+        assert f[0] == x[0] and np.array_equal(f[1], x[1]), key
+        assert np.array_equal(f[2].colptr, x[2].colptr) and np.array_equal(f[2].rowval, x[2].rowval), key
+        assert np.array_equal(f[2].nzval, x[2].nzval), key
+    for sorted_on in (1, 0):
+        plan.set_option(capi.OPT_SORTED, sorted_on)
+        plan.set_option(capi.OPT_FUSED, 1)
+        for lag in (1, 3, 7):
+            plan.set_option(capi.OPT_FUSED_LAG, lag)
+            g = plan.makeϕrKt(u)
+            assert np.array_equal(f[2].nzval, g[2].nzval) and np.array_equal(f[1], g[1])
     if b.ne <= 30000:
         K.assert_parity(f, K.oracle_eval(b, u))
 
