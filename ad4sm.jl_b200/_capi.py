@@ -38,6 +38,13 @@ class StagingView(C.Structure):
                 ("Ke_dev", C.c_void_p), ("re_dev", C.c_void_p), ("phie_dev", C.c_void_p)]
 
 
+PEER_HANDLE_BYTES = 128
+
+
+class PeerLink(C.Structure):
+    _fields_ = [("first_slot", C.c_int64), ("count", C.c_int64), ("remote_first_slot", C.c_int64), ("peer_handles", C.c_void_p)]
+
+
 class DeviceView(C.Structure):
     _fields_ = [
         ("n_dof", C.c_int64), ("nnz", C.c_int64),
@@ -75,6 +82,9 @@ SIGNATURES = {
     "ad4sm_eval_elements_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ad4sm_eval_assemble_device": (C.c_int, [C.c_void_p, C.c_int32]),
     "ad4sm_staging_view_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(StagingView)]),
+    "ad4sm_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ad4sm_peer_attach": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(PeerLink)]),
+    "ad4sm_export_ranges": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ad4sm_sync": (C.c_int, [C.c_void_p]),
     "ad4sm_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     "ad4sm_get_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),

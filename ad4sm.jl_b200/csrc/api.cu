@@ -101,6 +101,12 @@ struct ad4sm_plan {
   unsigned* sb_ptr = nullptr;
   unsigned* done2 = nullptr;
   int n_steps2 = 0, fused_mode_last = 0;
+  long long n_own_sorted = 0;  // slots [n_own_sorted, ne) are HALO: scattered into C before K2s
+  bool dist_aware = false;     // the caller declared its export ranges / peer links (ad4sm_peer_attach / ad4sm_export_ranges)
+  // peer staging / export ranges
+  int n_xr = 0, n_xr_local = 0;
+  K1Args::PeerRange xr[AD4SM_MAX_PEER_LINKS] = {};
+  std::vector<void*> ipc_open;
   long long gstep2 = 0, n_groups2 = 0;
 };
 
@@ -184,6 +190,7 @@ void ad4sm_plan_destroy(ad4sm_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
+  for (void* m : p->ipc_open) cudaIpcCloseMemHandle(m);
   for (void* a : p->allocs) cudaFree(a);
   for (int f = 0; f < 2; f++) {
     cudaFree(p->field[f].dz_colptr);
@@ -462,8 +469,10 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     const char* env = getenv("AD4SM_SORTED");
     K1Config c;
     const ad4sm_batch& B0 = batches[0];
-    if (!(env && env[0] == '0') && n_batches == 1 && !(B0.batch_flags & AD4SM_BATCH_HALO) && D == 3 && dofs_per_node == 3 &&
-        k1_config(D, N, B0.n_gauss, B0.elem_kind == AD4SM_ELEM_CP && B0.mat_kind == AD4SM_MAT_PHASEFIELD, ne, &c) &&
+    bool rest_halo = true;
+    for (int b = 1; b < n_batches; b++) rest_halo &= (batches[b].batch_flags & AD4SM_BATCH_HALO) != 0;
+    if (!(env && env[0] == '0') && rest_halo && !(B0.batch_flags & AD4SM_BATCH_HALO) && D == 3 && dofs_per_node == 3 &&
+        k1_config(D, N, B0.n_gauss, B0.elem_kind == AD4SM_ELEM_CP && B0.mat_kind == AD4SM_MAT_PHASEFIELD, B0.n_elems, &c) &&
         c.persistent && (double)n_blocks * 9.0 < 4.0e9) {
       std::vector<unsigned> up_index(n_blocks, 0xffffffffu);
       long long U = 0;
@@ -526,6 +535,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
         }
         p->n_pairs = U;
         p->sorted_built = true;
+        p->n_own_sorted = B0.n_elems;
         // ---- batches for the fused K2s: consecutive pairs, contiguous contributions, readiness = prefix max ----
         const long long gstep = (long long)c.grid * c.warps;
         const long long n_groups = (ne + c.EW - 1) / c.EW;
@@ -539,7 +549,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
         }
         std::vector<uint4> brec;
         std::vector<int> bready;
-        bool fits = cap_blocks >= 8;
+        bool fits = cap_blocks >= 8 && n_batches == 1;
         for (long long u = 0; u < U && fits;) {
           long long v = u;
           int rdy = 0;
@@ -775,10 +785,14 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
   p->ev_cur = p->prof ? next_events(p) : nullptr;
   if (p->ev_cur) CK(cudaEventRecord(p->ev_cur->e[0], p->stream));
   long long launches = 0;
-  const bool kmode_ok = internal && want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U);
-  const bool sorted_ok = kmode_ok && p->sorted_built && p->sorted_on;
-  const bool fuse2 = sorted_ok && p->fuse_allowed && p->batch_rec != nullptr;      // K1 + K2s in one kernel
-  const bool fuse = !fuse2 && kmode_ok && p->fz.enabled && p->fuse_allowed;       // K1 + K2 + K3 in one kernel
+  // the two-stage API promises element-major staging between the stages; a caller that declared which slot ranges
+  // it reads (export ranges / peer links) gets the sorted path, with K1 materialising exactly those ranges
+  const bool kmode_ok = want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U);
+  const bool sorted_ok = kmode_ok && p->sorted_built && p->sorted_on && (internal || p->dist_aware);
+  if (!internal && !sorted_ok && p->dist_aware && p->n_xr_local)
+    return fail(AD4SM_ESTATE, "export ranges are only served by the sorted path");
+  const bool fuse2 = internal && sorted_ok && p->fuse_allowed && p->batch_rec != nullptr;  // K1 + K2s in one kernel
+  const bool fuse = internal && !fuse2 && kmode_ok && p->fz.enabled && p->fuse_allowed;   // K1 + K2 + K3 in one kernel
   const bool sorted = sorted_ok && !fuse;
   p->fused_mode_last = fuse2 ? 2 : (fuse ? 1 : 0);
   p->fused_last = fuse;
@@ -796,6 +810,12 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
     a.Ke = p->Ke;
     a.re = p->re;
     a.phie = p->phie;
+    if (p->n_xr && !internal) {  // two-stage API of a partitioned run: K1 also writes the interface rows for the owners
+      if (b.k.slot0 == 0) {
+        a.n_xr = p->n_xr;
+        for (int x = 0; x < p->n_xr; x++) a.xr[x] = p->xr[x];
+      }
+    }
     if (fuse) {
       a.fz = p->fz;
       a.as = asm_args(p, AD4SM_FIELD_U);
@@ -846,7 +866,11 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   CK(launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, p->stream));
   CK(cudaEventRecord(p->ev_r_ready, p->stream));
   if (!p->fused_last && p->fused_mode_last != 2 && want_K) {
-    if (p->sorted_last) CK(launch_k2s(asm_args(p, field), p->stream));
+    if (p->sorted_last) {
+      if (p->n_own_sorted < p->ne)
+        CK(launch_halo_scatter(p->Ke, p->cpos, p->C, p->n_own_sorted, p->ne - p->n_own_sorted, n_pair_blocks(p->N), p->stream));
+      CK(launch_k2s(asm_args(p, field), p->stream));
+    }
     else CK(launch_k2(asm_args(p, field), p->stream));
   }
   if (ev) CK(cudaEventRecord(ev->e[2], p->stream));
@@ -910,6 +934,63 @@ int ad4sm_get_info(ad4sm_plan* p, int32_t what, int64_t* value) {
     case AD4SM_INFO_SORTED: *value = p->sorted_built ? (p->sorted_on ? 2 : 1) : 0; return AD4SM_OK;
   }
   return fail(AD4SM_EINVAL, "unknown info id");
+}
+
+int ad4sm_peer_export(ad4sm_plan* p, void* handles_out) {
+  if (!p || !handles_out) return fail(AD4SM_EINVAL, "plan or handles_out is NULL");
+  CK(cudaSetDevice(p->device));
+  cudaIpcMemHandle_t h[2];
+  CK(cudaIpcGetMemHandle(&h[0], p->Ke));
+  CK(cudaIpcGetMemHandle(&h[1], p->re));
+  static_assert(sizeof(h) == AD4SM_PEER_HANDLE_BYTES, "handle size");
+  memcpy(handles_out, h, sizeof(h));
+  return AD4SM_OK;
+}
+
+int ad4sm_peer_attach(ad4sm_plan* p, int32_t n_links, const ad4sm_peer_link* links) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (n_links < 0 || n_links > AD4SM_MAX_PEER_LINKS || (n_links && !links)) return fail(AD4SM_EINVAL, "bad peer links");
+  CK(cudaSetDevice(p->device));
+  const long long kw = (long long)n_pair_blocks(p->N) * p->D * p->D, rw = (long long)p->N * p->D;
+  p->n_xr = 0;
+  for (int i = 0; i < n_links; i++) {
+    const ad4sm_peer_link& L = links[i];
+    if (L.first_slot < 0 || L.count <= 0 || L.first_slot + L.count > p->ne || !L.peer_handles)
+      return fail(AD4SM_EINVAL, "peer link range outside the plan");
+    cudaIpcMemHandle_t h[2];
+    memcpy(h, L.peer_handles, sizeof(h));
+    void *ke = nullptr, *re = nullptr;
+    CK(cudaIpcOpenMemHandle(&ke, h[0], cudaIpcMemLazyEnablePeerAccess));
+    p->ipc_open.push_back(ke);
+    CK(cudaIpcOpenMemHandle(&re, h[1], cudaIpcMemLazyEnablePeerAccess));
+    p->ipc_open.push_back(re);
+    p->xr[i].first = L.first_slot;
+    p->xr[i].count = L.count;
+    p->xr[i].ke = (double*)ke + L.remote_first_slot * kw;
+    p->xr[i].re = (double*)re + L.remote_first_slot * rw;
+  }
+  p->n_xr = n_links;
+  p->n_xr_local = 0;
+  p->dist_aware = true;
+  return AD4SM_OK;
+}
+
+int ad4sm_export_ranges(ad4sm_plan* p, int32_t n_ranges, const int64_t* first_slot, const int64_t* count) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (n_ranges < 0 || n_ranges > AD4SM_MAX_PEER_LINKS || (n_ranges && (!first_slot || !count)))
+    return fail(AD4SM_EINVAL, "bad export ranges");
+  const long long kw = (long long)n_pair_blocks(p->N) * p->D * p->D, rw = (long long)p->N * p->D;
+  for (int i = 0; i < n_ranges; i++) {
+    if (first_slot[i] < 0 || count[i] <= 0 || first_slot[i] + count[i] > p->ne) return fail(AD4SM_EINVAL, "export range outside the plan");
+    p->xr[i].first = first_slot[i];
+    p->xr[i].count = count[i];
+    p->xr[i].ke = p->Ke + first_slot[i] * kw;
+    p->xr[i].re = p->re + first_slot[i] * rw;
+  }
+  p->n_xr = n_ranges;
+  p->n_xr_local = n_ranges;
+  p->dist_aware = true;
+  return AD4SM_OK;
 }
 
 int ad4sm_sync(ad4sm_plan* p) {

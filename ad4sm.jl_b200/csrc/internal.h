@@ -79,6 +79,13 @@ struct K1Args {
   const unsigned* cpos;
   double* C;
   int sorted_tma;       // sorted blocks leave through shared memory + one 80-byte bulk copy each (else plain STG.128)
+  // peer staging: slots [first, first+count) are also written to the owner rank's staging over NVLink
+  int n_xr;
+  struct PeerRange {
+    long long first, count;
+    double* ke;  // peer Ke + remote_first_slot * width, i.e. indexed by (slot - first)
+    double* re;
+  } xr[4];
   // fused assembly (fz.enabled): the persistent kernel also runs K2/K3 over `as`
   FuseArgs fz;
   AsmArgs as;
@@ -100,6 +107,8 @@ const char* k1_unsupported_reason(int D, int N, int P, int mf, int mode);
 cudaError_t launch_k2(const AsmArgs& a, cudaStream_t s);  // Kt values
 cudaError_t launch_k3(const AsmArgs& a, cudaStream_t s);  // residual
 cudaError_t launch_k2s(const AsmArgs& a, cudaStream_t s); // Kt values from the destination-sorted staging
+cudaError_t launch_halo_scatter(const double* Ke, const unsigned* cpos, double* C, long long slot0, long long n_slots, int NPB,
+                                cudaStream_t s);
 int phi_reduce_partials();
 cudaError_t launch_phi_reduce(const double* phie, long long n, double* partials, double* phi, cudaStream_t s);
 cudaError_t launch_pattern(const AsmArgs& a, long long* colptr, long long* rowval, cudaStream_t s);

@@ -350,7 +350,7 @@ __device__ __forceinline__ void k1_phase1(const MatDev* mat, int q, bool valid, 
 template <int D, int N, int PT>
 __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active, bool want_K, bool staged, const double* recs,
                                           const double* gS, double* kout_s, double* rout_s, double* kout_g, double* rout_g,
-                                          const unsigned* cpos_e, double* C) {
+                                          const unsigned* cpos_e, double* C, const K1Args& a, long long slot) {
   constexpr int NO = N / 2 + 1, DD = D * D;
   // destination-sorted staging: this lane's block positions, fetched now so that the loads fly during the contraction
   unsigned cp[NO];
@@ -400,6 +400,16 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
         }
 #pragma unroll
         for (int j = 0; j < D; j++) rout_g[q * D + j] = rq[j];
+        // interface element of a partitioned run: element-major copy for the owner rank (peer memory, or the local Ke
+        // that the send/recv exchange reads).  Looked up here, after the contraction, to keep phase 2 lean.
+        for (int x = 0; x < a.n_xr; x++) {
+          const long long k = slot - a.xr[x].first;
+          if (k >= 0 && k < a.xr[x].count) {
+            column_u_store<D, N>(q, acc, a.xr[x].ke + k * (long long)(n_pair_blocks(N) * DD));
+#pragma unroll
+            for (int j = 0; j < D; j++) (a.xr[x].re + k * (long long)(N * D))[q * D + j] = rq[j];
+          }
+        }
       }
       if (kout_s) bulk_commit();
     }
@@ -670,12 +680,12 @@ __global__ void __launch_bounds__(256, 1)
       k1_phase2<D, N, PTC>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS,
                            (sorted && !sorted_tma) ? nullptr : reinterpret_cast<double*>(stg),
                            reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
-                           a.re + slot * (long long)(N * D), cpos_e, a.C);
+                           a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot);
     else
       k1_phase2<D, N, 0>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS,
                          (sorted && !sorted_tma) ? nullptr : reinterpret_cast<double*>(stg),
                          reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
-                         a.re + slot * (long long)(N * D), cpos_e, a.C);
+                         a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot);
     if (valid && q == 0) {  // ϕ_e = Σ_gp w ψ, in Gauss-point order (elasticelements.jl:199-206)
       double ssum = 0.0;
       for (int gp = 0; gp < P; gp++) ssum += psiS[gp];
@@ -692,6 +702,13 @@ __global__ void __launch_bounds__(256, 1)
           const unsigned src = smem_u32(ws + (size_t)i * L.kout_el);
           bulk_store(a.Ke + sl * (long long)(NPB * DD), src, (unsigned)(NPB * DD * 8));
           bulk_store(a.re + sl * (long long)(N * D), src + L.re_off, (unsigned)(N * D * 8));
+          for (int x = 0; x < a.n_xr; x++) {  // interface element: the same bytes go to the owner rank over NVLink
+            const long long k = sl - a.xr[x].first;
+            if (k >= 0 && k < a.xr[x].count) {
+              bulk_store(a.xr[x].ke + k * (long long)(NPB * DD), src, (unsigned)(NPB * DD * 8));
+              bulk_store(a.xr[x].re + k * (long long)(N * D), src + L.re_off, (unsigned)(N * D * 8));
+            }
+          }
         }
         bulk_commit();
       }
@@ -720,6 +737,9 @@ __global__ void __launch_bounds__(256, 1)
       bulk_wait_all();
       __threadfence();
       red_release_add(a.fz.done + (n_it - 1), 1u);
+    } else if (a.n_xr) {
+      bulk_wait_all();  // peer stores must be complete, not only read, when the kernel ends
+      __threadfence_system();
     } else {
       bulk_wait_read_all();  // shared memory must outlive the last bulk stores
     }
@@ -1069,6 +1089,36 @@ cudaError_t launch_k2s(const AsmArgs& a, cudaStream_t s) {
   cudaError_t err = cudaMemsetAsync(a.n_zero, 0, sizeof(unsigned long long), s);
   if (err != cudaSuccess) return err;
   k2s_kernel3<<<(unsigned)((a.n_pairs + K2S_THREADS - 1) / K2S_THREADS), K2S_THREADS, 0, s>>>(a);
+  return cudaGetLastError();
+}
+// ---- partitioned runs with destination-sorted staging: the HALO elements' blocks arrive element-major (exchange /
+// peer stores) and are moved to their sorted slots, transposed where the canonical orientation asks for it.
+__global__ void __launch_bounds__(256) halo_scatter_kernel3(const double* Ke, const unsigned* cpos, double* C, long long slot0,
+                                                            long long n_slots, int NPB) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_slots * NPB) return;
+  const long long g = slot0 * NPB + t;
+  const unsigned code = __ldg(cpos + g);
+  const double* B = Ke + g * 9;
+  double v[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) v[i] = B[i];
+  double* dst = C + (long long)(code >> 1) * CBLK3;
+  if (code & 1u) {
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) dst[j * 3 + l] = v[l * 3 + j];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; i++) dst[i] = v[i];
+  }
+  dst[9] = 0.0;
+}
+cudaError_t launch_halo_scatter(const double* Ke, const unsigned* cpos, double* C, long long slot0, long long n_slots, int NPB,
+                                cudaStream_t s) {
+  const long long n = n_slots * NPB;
+  if (n > 0) halo_scatter_kernel3<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(Ke, cpos, C, slot0, n_slots, NPB);
   return cudaGetLastError();
 }
 cudaError_t launch_k3(const AsmArgs& a, cudaStream_t s) {

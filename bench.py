@@ -175,7 +175,7 @@ def run_ours(args):
         runner = None
     else:
         from ad4sm_b200 import dist as D
-        runner = D.SlabRunner(n, n, rank, world, device=local)
+        runner = D.SlabRunner(n, n, rank, world, device=local, peer_staging=args.peer_staging)
         plan, batch, u = runner.plan, runner.batch, runner.u_local
     t_build = time.perf_counter() - t_build0
     ne_local = batch.ne
@@ -297,6 +297,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": f"C2 Hex8 NeoHooke {n}x{n}x{n * world} ({ne_total} elements), 2x2x2 Gauss, one makeϕrKt per step",
                    "elements_per_gpu": ne_local, "partition": "single GPU" if world == 1 else f"z-slabs over {world} ranks",
+                   "interface": None if world == 1 else ("K1 bulk stores into the owner's staging over NVLink peer memory + barrier"
+                                                         if runner.peer else "NCCL send/recv of staged element blocks"),
                    "l2": "working set (∇N 1.5 GB + staging 2.6 GB + Kt 2.0 GB per GPU) >> 126 MB L2; no flush needed",
                    "plan_build_s": t_build},
         "clocks": dict(clk.summary(), note="sampled every 50 ms over the timed region and ~0.4 s more of the same load"),
@@ -323,6 +325,9 @@ def main():
     ap.add_argument("--n", type=int, default=100, help="elements per direction per GPU (100 -> 1M Hex8)")
     ap.add_argument("--cpu-sample", type=int, default=56, help="edge of the CPU sample block (56 -> 175616 elements, a few seconds on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--peer-staging", action="store_true",
+                    help="multi-GPU: K1 writes interface staging into the owner's memory over NVLink (CUDA IPC) instead of the "
+                         "NCCL send/recv exchange (default: NCCL + destination-sorted staging, measured faster)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -150,6 +150,25 @@ int ad4sm_device_view_get(ad4sm_plan* plan, int32_t field, ad4sm_device_view* vi
  * assemble: K2/K3 over ALL batches' staging + the ϕ reduction (HALO slots contribute 0 to ϕ). */
 int ad4sm_eval_elements_device(ad4sm_plan* plan, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev);
 int ad4sm_eval_assemble_device(ad4sm_plan* plan, int32_t mode);
+/* Peer staging (fused compute + communication): instead of a send/recv after the element stage, K1's bulk-store
+ * epilogue writes the staged blocks / residuals of interface elements ALSO into the owner rank's HALO slots, through
+ * peer-mapped memory over NVLink (CUDA IPC handles), while it computes.  The ranks then only need a barrier between
+ * the element and assembly stages.  Links are contiguous slot ranges (z-slabs and other contiguous partitions). */
+#define AD4SM_PEER_HANDLE_BYTES 128 /* two cudaIpcMemHandle_t: Ke and re staging */
+typedef struct ad4sm_peer_link {
+  int64_t first_slot;         /* first local (own) staging slot of the range */
+  int64_t count;              /* slots in the range */
+  int64_t remote_first_slot;  /* where the range starts in the peer plan's staging (its HALO slots) */
+  const void* peer_handles;   /* AD4SM_PEER_HANDLE_BYTES bytes exported by the peer's ad4sm_peer_export */
+} ad4sm_peer_link;
+#define AD4SM_MAX_PEER_LINKS 4
+int ad4sm_peer_export(ad4sm_plan* plan, void* handles_out /* AD4SM_PEER_HANDLE_BYTES */);
+int ad4sm_peer_attach(ad4sm_plan* plan, int32_t n_links, const ad4sm_peer_link* links);
+/* Without peer memory: the slot ranges whose element-major staging (Ke_dev / re_dev of ad4sm_staging_view_get) the
+ * caller will read between the stages (the rows it sends).  Declaring them -- even zero of them -- lets the element
+ * stage use the destination-sorted staging for everything else; undeclared, the whole staging is element-major. */
+int ad4sm_export_ranges(ad4sm_plan* plan, int32_t n_ranges, const int64_t* first_slot, const int64_t* count);
+
 typedef struct ad4sm_staging_view {
   int64_t n_slots;       /* elements of all batches, in batch order (slot = position in that concatenation) */
   int64_t ke_width;      /* doubles per slot in Ke_dev: N(N+1)/2 node-pair blocks of DB*DB (DB = D for FIELD_U, 1 for FIELD_D) */
