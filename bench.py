@@ -270,12 +270,18 @@ def run_ours(args):
     fp64_peak = tf.value
     k1_tflops = W_ALG_FLOP * ne_local / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
     k2_gbs = B_ALG_K2 * ne_local / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+    # DRAM traffic per launch from the committed ncu --set full capture of this same command (profiles/
+    # r01_ncu_k1_k3_k2s_sorted_path.txt): dram__bytes_read.sum + dram__bytes_write.sum, 1M-element workload only
+    at_profiled_size = (n == 100)
     roof_k1 = {"kernel": "k1_u_kernel<3,8,8,NEO> (element energy/gradient/Hessian)", "bound": "fp64", "achieved": k1_tflops,
-               "peak": fp64_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+               "peak": fp64_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak if fp64_peak else None,
+               "traffic": (1.919151e9 + 3.124979e9) if at_profiled_size else None, "traffic_unit": "bytes/launch (ncu)",
+               "algorithmic_bytes_per_launch": (32 + 1536 + 64 + 24.7 + 144 + 36 * 80 + 192 + 8) * ne_local,
                "ms_per_launch": k1_ms, "peak_source": "DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
                "algorithmic_flop_per_element": W_ALG_FLOP}
-    roof_k2 = {"kernel": "k2_kernel<3> + k3_kernel (deterministic assembly)", "bound": "hbm", "achieved": k2_gbs,
-               "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": k2_gbs / peaks["hbm_gbs"], "traffic": None,
+    roof_k2 = {"kernel": "k3_kernel + k2s_kernel3 (deterministic assembly from the destination-sorted staging)", "bound": "hbm",
+               "achieved": k2_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": k2_gbs / peaks["hbm_gbs"],
+               "traffic": (3.296006e9 + 2.079615e9) if at_profiled_size else None, "traffic_unit": "bytes/launch (ncu, k2s_kernel3)",
                "ms_per_launch": k2_ms, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "algorithmic_bytes_per_element": B_ALG_K2}
     dominant = roof_k1 if k1_ms >= k2_ms else roof_k2
     # whole-path roofline: binding time per element = max(W_alg / FP64 peak, B_alg / HBM peak)
@@ -299,7 +305,7 @@ def run_ours(args):
                    "elements_per_gpu": ne_local, "partition": "single GPU" if world == 1 else f"z-slabs over {world} ranks",
                    "interface": None if world == 1 else ("K1 bulk stores into the owner's staging over NVLink peer memory + barrier"
                                                          if runner.peer else "NCCL send/recv of staged element blocks"),
-                   "l2": "working set (∇N 1.5 GB + staging 2.6 GB + Kt 2.0 GB per GPU) >> 126 MB L2; no flush needed",
+                   "l2": "working set (∇N 1.5 GB + staging 2.9 GB + Kt 2.0 GB per GPU) >> 126 MB L2; no flush needed",
                    "plan_build_s": t_build},
         "clocks": dict(clk.summary(), note="sampled every 50 ms over the timed region and ~0.4 s more of the same load"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
