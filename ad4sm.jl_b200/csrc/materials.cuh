@@ -432,26 +432,31 @@ template <int D> AD4SM_DI void pfneo_tangent(const MatDev& m, const double* F, d
 // differences of x^(α/2) and x^((α−2)/2) in x = λ², evaluated without cancellation -- repeated stretches (u = 0:
 // λ = (1,1,1)) are regular points of these formulas, and any orthonormal eigenbasis may be used there.
 // ---------------------------------------------------------------------------------------------
-// (x_i^p − x_j^p)/(x_i − x_j) for x > 0
-AD4SM_DI double divdiff_pow(double xi, double xj, double p) {
+// (x_i^p − x_j^p)/(x_i − x_j) for x > 0, given xip = x_i^p and xjp = x_j^p (no further pow calls)
+AD4SM_DI double divdiff_pow(double xi, double xj, double xip, double xjp, double p) {
   const double t = (xi - xj) / xj;
-  const double xjp1 = pow(xj, p - 1.0);
   if (fabs(t) < 2e-3) {  // series of ((1+t)^p − 1)/t, truncation error t^5/720·|p…(p−5)| < 1e-16
-    return xjp1 * p *
+    return (xjp / xj) * p *
            (1.0 + (p - 1.0) * t / 2.0 *
                       (1.0 + (p - 2.0) * t / 3.0 * (1.0 + (p - 3.0) * t / 4.0 * (1.0 + (p - 4.0) * t / 5.0))));
   }
-  return xjp1 * (pow(1.0 + t, p) - 1.0) / t;
+  return (xip - xjp) / (xi - xj);  // cancellation error <= eps / 2e-3
 }
 
-// Eigen-decomposition of a symmetric DxD matrix S (full storage, destroyed): cyclic Jacobi with a fixed number of
-// sweeps (deterministic, robust for repeated eigenvalues).  V columns = eigenvectors, S diagonal = eigenvalues.
+// Eigen-decomposition of a symmetric DxD matrix S (full storage, destroyed): cyclic Jacobi, at most 8 sweeps, stopped
+// when the off-diagonal mass is below 1e-30 of the diagonal (deterministic; robust for repeated eigenvalues).
+// V columns = eigenvectors, S diagonal = eigenvalues.
 template <int D> AD4SM_DI void jacobi_eig(double* S, double* V) {
 #pragma unroll
   for (int i = 0; i < D; i++)
 #pragma unroll
     for (int j = 0; j < D; j++) V[i * D + j] = (i == j) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < (D == 2 ? 1 : 6); sweep++) {
+  for (int sweep = 0; sweep < (D == 2 ? 1 : 8); sweep++) {
+    if (D == 3) {
+      const double off = S[1] * S[1] + S[2] * S[2] + S[5] * S[5];
+      const double dg = S[0] * S[0] + S[4] * S[4] + S[8] * S[8];
+      if (off <= 1e-30 * dg) break;
+    }
 #pragma unroll
     for (int p = 0; p < D - 1; p++)
 #pragma unroll
@@ -484,12 +489,13 @@ template <int D> AD4SM_DI void jacobi_eig(double* S, double* V) {
   }
 }
 
-// energy on duals of the D in-plane stretches (the third stretch of the 2-D embedding is a function of them)
-template <int D> AD4SM_DI Dual2<D> ogden_energy(const MatDev& m, const Dual2<D>* lam, double& s_out) {
+// energy on duals of the D in-plane stretches (the third stretch of the 2-D embedding is a function of them).
+// lam_a[i] = λ_i^α is supplied by the caller (one exp/log pair per stretch for everything in this material).
+template <int D> AD4SM_DI Dual2<D> ogden_energy(const MatDev& m, const Dual2<D>* lam, const double* lam_a, double& s_out) {
   const double alpha = m.p[0], mu = m.p[1], K = m.p[2];
-  Dual2<D> S = d2_pow(lam[0], alpha);
+  Dual2<D> S = d2_pow_given(lam[0], alpha, lam_a[0]);
 #pragma unroll
-  for (int i = 1; i < D; i++) S = S + d2_pow(lam[i], alpha);
+  for (int i = 1; i < D; i++) S = S + d2_pow_given(lam[i], alpha, lam_a[i]);
   Dual2<D> J = lam[0];
 #pragma unroll
   for (int i = 1; i < D; i++) J = J * lam[i];
@@ -501,6 +507,14 @@ template <int D> AD4SM_DI Dual2<D> ogden_energy(const MatDev& m, const Dual2<D>*
   const Dual2<D> sc = d2_pow(J, -alpha / 3.0);  // 3-D: J = λ1λ2λ3; 2-D (K >= 0): λ3 = 1, J = λ1λ2
   s_out = sc.v;
   return (mu / alpha) * (S * sc - 3.0) + K * d2_sq(J - 1.0);
+}
+
+// A += c · sym(x yᵀ) restricted to the packed upper triangle:  A[pk(I,J)] += x[I]·y[J]   (caller makes it symmetric)
+template <int DD> AD4SM_DI void rank1_packed(double* A, const double* x, const double* y) {
+#pragma unroll
+  for (int J = 0; J < DD; J++)
+#pragma unroll
+    for (int I = 0; I <= J; I++) A[pk(I, J)] += x[I] * y[J];
 }
 
 template <int D> AD4SM_DI void ogden_tangent(const MatDev& m, const double* F, Tangent<D>& t) {
@@ -518,14 +532,17 @@ template <int D> AD4SM_DI void ogden_tangent(const MatDev& m, const double* F, T
       C[a * D + b] = C[b * D + a] = c;
     }
   jacobi_eig<D>(C, V);
-  double lam[D], x[D];
+  double lam[D], x[D], lam_a[D];
 #pragma unroll
   for (int i = 0; i < D; i++) {
     x[i] = C[i * D + i];
     lam[i] = sqrt(x[i]);
+    lam_a[i] = exp(0.5 * alpha * log(x[i]));  // λ^α = x^(α/2); x^((α−2)/2) = λ^α / x
   }
-  // n_i = F N_i / λ_i;  E_ij[(k, j')] = n_i[j'] N_j[k] in the F[k*D+j'] addressing
-  double U[DD];
+  // n_i = F N_i / λ_i
+  double U[DD], ilam[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) ilam[i] = 1.0 / lam[i];
 #pragma unroll
   for (int i = 0; i < D; i++)
 #pragma unroll
@@ -533,46 +550,57 @@ template <int D> AD4SM_DI void ogden_tangent(const MatDev& m, const double* F, T
       double a = 0.0;
 #pragma unroll
       for (int k = 0; k < D; k++) a += F[k * D + r] * V[k * D + i];
-      U[r * D + i] = a / lam[i];
+      U[r * D + i] = a * ilam[i];
     }
   Dual2<D> dl[D];
 #pragma unroll
   for (int i = 0; i < D; i++) dl[i] = d2_var<D>(lam[i], i);
   double s;
-  const Dual2<D> f = ogden_energy<D>(m, dl, s);
+  const Dual2<D> f = ogden_energy<D>(m, dl, lam_a, s);
   t.psi = f.v;
-  const double c0 = lam[0] * f.g[0] - mu * s * pow(lam[0], alpha);  // λ_i f_i = μ s λ_i^α + c0 for every i
+  const double c0 = lam[0] * f.g[0] - mu * s * lam_a[0];  // λ_i f_i = μ s λ_i^α + c0 for every i
 #pragma unroll
   for (int I = 0; I < DD; I++) t.P[I] = 0.0;
 #pragma unroll
   for (int I = 0; I < Tangent<D>::NA; I++) t.A[I] = 0.0;
-  auto E = [&](int i, int j, int I) { return U[(I % D) * D + i] * V[(I / D) * D + j]; };  // (n_i ⊗ N_j)[I]
+  // q_ij[I] = (n_i ⊗ N_j)[I] = n_i[j'] N_j[k] in the F[k*D+j'] addressing, I = k*D + j'
+  auto qvec = [&](int i, int j, double* q) {
+#pragma unroll
+    for (int I = 0; I < DD; I++) q[I] = U[(I % D) * D + i] * V[(I / D) * D + j];
+  };
+  // diagonal part: A += Σ_i q_ii w_iᵀ with w_i = Σ_j f_ij q_jj  (f symmetric, so the sum is symmetric);  P = Σ f_i q_ii.
+  // q_jj is recomputed from U, V inside the sums instead of being held (27 doubles fewer live next to A).
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    double qi[DD], w[DD];
+    qvec(i, i, qi);
+#pragma unroll
+    for (int I = 0; I < DD; I++) {
+      double a = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; j++) a += f.h[pk(i, j)] * (U[(I % D) * D + j] * V[(I / D) * D + j]);
+      w[I] = a;
+      t.P[I] += f.g[i] * qi[I];
+    }
+    rank1_packed<DD>(t.A, qi, w);
+  }
+  // pair part: A += q1 (a q1 + b q2)ᵀ + q2 (a q2 + b q1)ᵀ,  q1 = q_ij, q2 = q_ji
 #pragma unroll
   for (int i = 0; i < D; i++)
 #pragma unroll
-    for (int I = 0; I < DD; I++) t.P[I] += f.g[i] * E(i, i, I);
+    for (int j = i + 1; j < D; j++) {
+      const double a = mu * s * divdiff_pow(x[i], x[j], lam_a[i], lam_a[j], 0.5 * alpha);
+      const double b = mu * s * lam[i] * lam[j] * divdiff_pow(x[i], x[j], lam_a[i] / x[i], lam_a[j] / x[j], 0.5 * alpha - 1.0) -
+                       c0 / (lam[i] * lam[j]);
+      double q1[DD], q2[DD], y[DD];
+      qvec(i, j, q1);
+      qvec(j, i, q2);
 #pragma unroll
-  for (int i = 0; i < D; i++)
+      for (int I = 0; I < DD; I++) y[I] = a * q1[I] + b * q2[I];
+      rank1_packed<DD>(t.A, q1, y);
 #pragma unroll
-    for (int j = 0; j < D; j++) {
-      if (i == j || true) {
-        const double fij = f.h[pk(i, j)];
-#pragma unroll
-        for (int J = 0; J < DD; J++)
-#pragma unroll
-          for (int I = 0; I <= J; I++) t.A[pk(I, J)] += fij * E(i, i, I) * E(j, j, J);
-      }
-      if (i < j) {
-        const double a = mu * s * divdiff_pow(x[i], x[j], 0.5 * alpha);
-        const double b = mu * s * lam[i] * lam[j] * divdiff_pow(x[i], x[j], 0.5 * alpha - 1.0) - c0 / (lam[i] * lam[j]);
-#pragma unroll
-        for (int J = 0; J < DD; J++)
-#pragma unroll
-          for (int I = 0; I <= J; I++) {
-            const double eijI = E(i, j, I), eijJ = E(i, j, J), ejiI = E(j, i, I), ejiJ = E(j, i, J);
-            t.A[pk(I, J)] += a * (eijI * eijJ + ejiI * ejiJ) + b * (eijI * ejiJ + ejiI * eijJ);
-          }
-      }
+      for (int I = 0; I < DD; I++) y[I] = a * q2[I] + b * q1[I];
+      rank1_packed<DD>(t.A, q2, y);
     }
 }
 

@@ -101,10 +101,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_workload(n, nz, jitter=0.0, seed=20261021):
-    from ad4sm_b200 import Elements as El, Materials as Ma, mesh
+def material(name):
+    from ad4sm_b200 import Materials as Ma
+    return {"neohooke": lambda: Ma.NeoHooke(1000.0, 5000.0),          # config C2 (README.md:150-151 parameters)
+            "ogden": lambda: Ma.Ogden(3.0, 1000.0, 5000.0)}[name]()    # config C5 (SURVEY §8d suggestion)
+
+
+def build_workload(n, nz, jitter=0.0, seed=20261021, mat="neohooke"):
+    from ad4sm_b200 import Elements as El, mesh
     coords, conn = mesh.hex_block(n, n, nz, jitter=jitter, seed=seed)
-    batch = El.Hex08_batch(conn, coords, Ma.NeoHooke(1000.0, 5000.0))
+    batch = El.Hex08_batch(conn, coords, material(mat))
     u = mesh.random_u(len(coords), 3, 1.0 / n, a=0.02, seed=seed + 2)
     return batch, u
 
@@ -170,12 +176,12 @@ def run_ours(args):
     n = args.n
     t_build0 = time.perf_counter()
     if world == 1:
-        batch, u = build_workload(n, n)
+        batch, u = build_workload(n, args.nz or n, mat=args.material)
         plan = El.Plan(batch, u.shape[1], 3, device=local)
         runner = None
     else:
         from ad4sm_b200 import dist as D
-        runner = D.SlabRunner(n, n, rank, world, device=local, peer_staging=args.peer_staging)
+        runner = D.SlabRunner(n, args.nz or n, rank, world, device=local, peer_staging=args.peer_staging, mat=material(args.material))
         plan, batch, u = runner.plan, runner.batch, runner.u_local
     t_build = time.perf_counter() - t_build0
     ne_local = batch.ne
@@ -272,7 +278,7 @@ def run_ours(args):
     k2_gbs = B_ALG_K2 * ne_local / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
     # DRAM traffic per launch from the committed ncu --set full capture of this same command (profiles/
     # r01_ncu_k1_k3_k2s_sorted_path.txt): dram__bytes_read.sum + dram__bytes_write.sum, 1M-element workload only
-    at_profiled_size = (n == 100)
+    at_profiled_size = (n == 100 and (args.nz or n) == 100 and args.material == "neohooke")
     roof_k1 = {"kernel": "k1_u_kernel<3,8,8,NEO> (element energy/gradient/Hessian)", "bound": "fp64", "achieved": k1_tflops,
                "peak": fp64_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak if fp64_peak else None,
                "traffic": (1.919151e9 + 3.124979e9) if at_profiled_size else None, "traffic_unit": "bytes/launch (ncu)",
@@ -301,7 +307,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"C2 Hex8 NeoHooke {n}x{n}x{n * world} ({ne_total} elements), 2x2x2 Gauss, one makeϕrKt per step",
+        "config": {"workload": f"{'C2' if args.material == 'neohooke' else 'C5'} Hex8 {'NeoHooke' if args.material == 'neohooke' else 'Ogden'} "
+                               f"{n}x{n}x{(args.nz or n) * world} ({ne_total} elements), 2x2x2 Gauss, one makeϕrKt per step",
                    "elements_per_gpu": ne_local, "partition": "single GPU" if world == 1 else f"z-slabs over {world} ranks",
                    "interface": None if world == 1 else ("K1 bulk stores into the owner's staging over NVLink peer memory + barrier"
                                                          if runner.peer else "NCCL send/recv of staged element blocks"),
@@ -328,7 +335,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=100, help="elements per direction per GPU (100 -> 1M Hex8)")
+    ap.add_argument("--n", type=int, default=100, help="elements per x/y direction (100 -> 1M Hex8 per GPU with --nz 100)")
+    ap.add_argument("--nz", type=int, default=0, help="element layers per GPU (default: --n); config C5 = --n 200 --nz 25 on 8 GPUs")
+    ap.add_argument("--material", default="neohooke", choices=["neohooke", "ogden"])
     ap.add_argument("--cpu-sample", type=int, default=56, help="edge of the CPU sample block (56 -> 175616 elements, a few seconds on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--peer-staging", action="store_true",
