@@ -335,8 +335,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=100, help="elements per x/y direction (100 -> 1M Hex8 per GPU with --nz 100)")
-    ap.add_argument("--nz", type=int, default=0, help="element layers per GPU (default: --n); config C5 = --n 200 --nz 25 on 8 GPUs")
+    ap.add_argument("--mesh-n", "--n", dest="n", type=int, default=100, help="elements per x/y direction (100 -> 1M Hex8 per GPU with --nz 100)")
+    ap.add_argument("--mesh-nz", "--nz", dest="nz", type=int, default=0, help="element layers per GPU (default: --n); config C5 = --mesh-n 200 --mesh-nz 25 --material ogden on 8 GPUs (torchrun swallows a bare --n)")
     ap.add_argument("--material", default="neohooke", choices=["neohooke", "ogden"])
     ap.add_argument("--cpu-sample", type=int, default=56, help="edge of the CPU sample block (56 -> 175616 elements, a few seconds on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
