@@ -37,31 +37,41 @@ def raw(path):
 def stalls(path, blk=80):
     out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr = rows[1]
-    ix = {h: i for i, h in enumerate(hdr)}
-    data = rows[2:]
+    # one section per profiled launch: a "Kernel Name" row, a header row, then the instructions
+    sections, cur = [], None
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1] if len(r) > 1 else "?", "hdr": None, "data": []}
+            sections.append(cur)
+        elif cur is not None and cur["hdr"] is None:
+            cur["hdr"] = r
+        elif cur is not None:
+            cur["data"].append(r)
+    for sec in sections:
+        hdr, data = sec["hdr"], sec["data"]
+        ix = {h: i for i, h in enumerate(hdr)}
 
-    def f(r, k):
-        try:
-            return float(r[ix[k]])
-        except Exception:
-            return 0.0
-    tot = sum(f(r, "# Samples") for r in data) or 1.0
-    print(f"## stall samples over the SASS listing ({int(tot)} samples, {len(data)} instructions)")
-    for s in range(0, len(data), blk):
-        seg = data[s:s + blk]
-        sm = sum(f(r, "# Samples") for r in seg)
-        if sm < 0.003 * tot:
-            continue
-        ops = {}
-        for r in seg:
-            t = r[ix["Source"]].strip().split()
-            op = (t[1] if t and t[0].startswith("@") else t[0]).split(".")[0] if t else "?"
-            ops[op] = ops.get(op, 0) + 1
-        top = ",".join(f"{k}:{v}" for k, v in sorted(ops.items(), key=lambda x: -x[1])[:4])
-        print(f"  sass[{s:4d}..] {100 * sm / tot:5.1f}%  long_sb={sum(f(r, 'stall_long_sb') for r in seg):6.0f} "
-              f"short_sb={sum(f(r, 'stall_short_sb') for r in seg):6.0f} wait={sum(f(r, 'stall_wait') for r in seg):6.0f} "
-              f"math={sum(f(r, 'stall_math') for r in seg):6.0f} selected={sum(f(r, 'stall_selected') for r in seg):6.0f}  [{top}]")
+        def f(r, k):
+            try:
+                return float(r[ix[k]])
+            except Exception:
+                return 0.0
+        tot = sum(f(r, "# Samples") for r in data) or 1.0
+        print(f"## stall samples over the SASS listing of {sec['name'][:90]} ({int(tot)} samples, {len(data)} instructions)")
+        for s0 in range(0, len(data), blk):
+            seg = data[s0:s0 + blk]
+            sm = sum(f(r, "# Samples") for r in seg)
+            if sm < 0.003 * tot:
+                continue
+            ops = {}
+            for r in seg:
+                t = r[ix["Source"]].strip().split()
+                op = (t[1] if t and t[0].startswith("@") else t[0]).split(".")[0] if t else "?"
+                ops[op] = ops.get(op, 0) + 1
+            top = ",".join(f"{k}:{v}" for k, v in sorted(ops.items(), key=lambda x: -x[1])[:4])
+            print(f"  sass[{s0:4d}..] {100 * sm / tot:5.1f}%  long_sb={sum(f(r, 'stall_long_sb') for r in seg):6.0f} "
+                  f"short_sb={sum(f(r, 'stall_short_sb') for r in seg):6.0f} wait={sum(f(r, 'stall_wait') for r in seg):6.0f} "
+                  f"math={sum(f(r, 'stall_math') for r in seg):6.0f} selected={sum(f(r, 'stall_selected') for r in seg):6.0f}  [{top}]")
 
 
 if __name__ == "__main__":
