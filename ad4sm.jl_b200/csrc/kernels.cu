@@ -1031,8 +1031,9 @@ cudaError_t launch_k2(const AsmArgs& a, cudaStream_t s) {
 // ---- K2s: Kt values from the destination-sorted staging.  One thread per unordered node pair {i <= p}: its
 // contributions are contiguous (streaming 16-byte loads, no source-map indirection, neighbouring threads read
 // neighbouring memory), summed in `elems` order like K2; the sum is written to block (i, p) and, transposed, to
-// block (p, i) -- both triangles carry the same bits.  (A CTA-cooperative variant that streams the range through
-// shared memory was measured slower: 1.58 vs 1.44 ms.)
+// block (p, i) -- both triangles carry the same bits.  Measured alternatives, all bitwise-equal: a CTA-cooperative
+// variant streaming the range through shared memory (1.58 ms), five threads per pair with fully coalesced 16-byte
+// chunks and 30 registers (1.38 ms) -- the kernel is insensitive to how the reads are organised.
 #define AD4SM_K2S_MINB 4
 #define AD4SM_K2S_UNROLL2 1  // measured: 1.39 ms vs 1.43 ms rolled; occupancy variants (40 / 32 registers) were no faster
 constexpr int K2S_THREADS = 256;
