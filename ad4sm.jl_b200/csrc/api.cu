@@ -683,6 +683,9 @@ static AsmArgs asm_args(ad4sm_plan* p, int field) {
   a.out_lo = p->out_lo;
   a.nn_pack = p->nn_pack;
   a.C = p->C;
+  static int skip = -1;
+  if (skip < 0) skip = getenv("AD4SM_EXP_SKIP_MIRROR") ? 1 : 0;
+  a.skip_mirror = skip;
   return a;
 }
 

@@ -31,6 +31,7 @@ struct AsmArgs {
   const unsigned* out_up;       // [n_pairs] nzval offset of block (i, p)
   const unsigned* out_lo;       // [n_pairs] nzval offset of block (p, i)   (== out_up for i == p)
   const unsigned* nn_pack;      // [n_pairs] row lengths: nn(i) | nn(p) << 16
+  int skip_mirror;              // TIMING EXPERIMENT ONLY (AD4SM_EXP_SKIP_MIRROR): K2s leaves the lower triangle unwritten
   const double* C;              // [ne*NPB][CBLK] contribution blocks, canonical orientation (row node <= col node)
 };
 constexpr int CBLK3 = 10;       // doubles per 3x3 contribution block: 9 + 1 pad = 80 B, 16-byte aligned

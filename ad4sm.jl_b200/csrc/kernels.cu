@@ -1076,7 +1076,7 @@ __global__ void __launch_bounds__(K2S_THREADS, AD4SM_K2S_MINB) k2s_kernel3(const
       a.nzval[oup + j * su + l] = acc[j * 3 + l];
       nz += (acc[j * 3 + l] == 0.0);
     }
-  if (olo != oup) {
+  if (olo != oup && !a.skip_mirror) {
 #pragma unroll
     for (int j = 0; j < 3; j++)
 #pragma unroll
