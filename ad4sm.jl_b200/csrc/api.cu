@@ -473,7 +473,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     for (int b = 1; b < n_batches; b++) rest_halo &= (batches[b].batch_flags & AD4SM_BATCH_HALO) != 0;
     if (!(env && env[0] == '0') && rest_halo && !(B0.batch_flags & AD4SM_BATCH_HALO) && D == 3 && dofs_per_node == 3 &&
         k1_config(D, N, B0.n_gauss, B0.elem_kind == AD4SM_ELEM_CP && B0.mat_kind == AD4SM_MAT_PHASEFIELD, B0.n_elems, &c) &&
-        c.persistent && (double)n_blocks * 9.0 < 4.0e9) {
+        c.persistent && (double)n_blocks * 9.0 < 4.0e9 && (double)ne * NPB < 2.0e9 && n_blocks < (1ll << 31)) {
       std::vector<unsigned> up_index(n_blocks, 0xffffffffu);
       long long U = 0;
       for (long long i = 0; i < n_nodes; i++)
