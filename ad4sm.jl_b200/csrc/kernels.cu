@@ -355,14 +355,8 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
   // destination-sorted staging: this lane's block positions, fetched now so that the loads fly during the contraction
   unsigned cp[NO];
   if (cpos_e) {
-    // volatile asm: the compiler must not sink these loads to their use after the contraction (it did, and the
-    // epilogue then stalled on them)
 #pragma unroll
-    for (int o = 0; o < NO; o++) {
-      cp[o] = 0xffffffffu;
-      if (active && o < n_offsets(N, q))
-        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(cp[o]) : "l"(cpos_e + o * N + q));
-    }
+    for (int o = 0; o < NO; o++) cp[o] = (active && o < n_offsets(N, q)) ? __ldg(cpos_e + o * N + q) : 0xffffffffu;
   }
   double acc[NO][DD], rq[D];
   column_u_acc<D, N, PT, VecMem>(q, P, recs, rstride, gS, N, (PT ? PT : P) * N, want_K, acc, rq);
@@ -550,7 +544,9 @@ __device__ __forceinline__ void fused_sorted_step(const K1Args& a, int t, int gw
 }
 
 // ---- K1, u-dual, persistent, LP lanes per element, TMA-staged inputs ------------------------------
-template <int D, int N, int LP, int MF, bool PF>
+// FUSE: compile the in-kernel assembly (fused modes) in.  Kept out of the default instantiation: the extra code (the
+// kernel grows from ~2 600 to ~8 500 SASS instructions) costs the plain path ~4 % even when it is never executed.
+template <int D, int N, int LP, int MF, bool PF, bool FUSE>
 __global__ void __launch_bounds__(256, 1)
     k1_u_kernel(const __grid_constant__ K1Args a, const WarpLayout L, const int warps_per_cta) {
   using R = GpRec<D>;
@@ -598,8 +594,8 @@ __global__ void __launch_bounds__(256, 1)
     tma_load_1d(smem_u32(ws + (L.n_off + (s) * L.n_stg)), a.nodes + e0 * N, nbytes, bar0 + 16 + 8 * s);
   };
 
-  const bool fused = a.fz.enabled == 1;   // element-major staging, K2 + K3 inside the kernel
-  const bool fused2 = a.fz.enabled == 2;  // destination-sorted staging, K2s inside the kernel
+  const bool fused = FUSE && a.fz.enabled == 1;   // element-major staging, K2 + K3 inside the kernel
+  const bool fused2 = FUSE && a.fz.enabled == 2;  // destination-sorted staging, K2s inside the kernel
   unsigned kphase = 0;
   const int gwarp = blockIdx.x * warps_per_cta + warp;  // global warp id = its first element group
   int verified = 0;                                      // steps [0, verified) are known to be published (fused path)
@@ -714,6 +710,7 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
     __syncwarp();
+    if constexpr (FUSE) {
     if (fused && it >= a.fz.lag) fused_assemble_step<D>(a, it - a.fz.lag, gwarp, (int)gstep, lane, verified, nzero);
     if (fused2 && a.sorted_tma) {  // the record area is about to receive K2s batches: its bulk stores must have read it
       bulk_wait_read_all();
@@ -721,6 +718,7 @@ __global__ void __launch_bounds__(256, 1)
     }
     if (fused2 && it >= a.fz.lag)
       fused_sorted_step(a, it - a.fz.lag, gwarp, (int)gstep, lane, ws, bar0 + 32, kphase, verified, nzero);
+    }
     n_it = it + 1;
   }
   if (a.cpos && a.sorted_tma) {
@@ -744,21 +742,23 @@ __global__ void __launch_bounds__(256, 1)
       bulk_wait_read_all();  // shared memory must outlive the last bulk stores
     }
   }
-  if (fused) {  // the steps this warp has not assembled yet (its last `lag` ones, and any it had no elements in)
-    __syncwarp();
-    int t = n_it - a.fz.lag;
-    if (t < 0) t = 0;
-    for (; t < a.fz.n_steps; t++) fused_assemble_step<D>(a, t, gwarp, (int)gstep, lane, verified, nzero);
-    for (int o = 16; o > 0; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
-    if (lane == 0 && nzero) atomicAdd(a.as.n_zero, (unsigned long long)nzero);
-  }
-  if (fused2) {
-    __syncwarp();
-    int t = n_it - a.fz.lag;
-    if (t < 0) t = 0;
-    for (; t < a.fz.n_steps; t++) fused_sorted_step(a, t, gwarp, (int)gstep, lane, ws, bar0 + 32, kphase, verified, nzero);
-    for (int o = 16; o > 0; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
-    if (lane == 0 && nzero) atomicAdd(a.as.n_zero, (unsigned long long)nzero);
+  if constexpr (FUSE) {
+    if (fused) {  // the steps this warp has not assembled yet (its last `lag` ones, and any it had no elements in)
+      __syncwarp();
+      int t = n_it - a.fz.lag;
+      if (t < 0) t = 0;
+      for (; t < a.fz.n_steps; t++) fused_assemble_step<D>(a, t, gwarp, (int)gstep, lane, verified, nzero);
+      for (int o = 16; o > 0; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
+      if (lane == 0 && nzero) atomicAdd(a.as.n_zero, (unsigned long long)nzero);
+    }
+    if (fused2) {
+      __syncwarp();
+      int t = n_it - a.fz.lag;
+      if (t < 0) t = 0;
+      for (; t < a.fz.n_steps; t++) fused_sorted_step(a, t, gwarp, (int)gstep, lane, ws, bar0 + 32, kphase, verified, nzero);
+      for (int o = 16; o > 0; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
+      if (lane == 0 && nzero) atomicAdd(a.as.n_zero, (unsigned long long)nzero);
+    }
   }
 }
 
@@ -931,7 +931,11 @@ template <int D, int N, int LP, int MF, bool PF> static cudaError_t launch_u_t(c
     const WarpLayout L = k1p_layout(D, N, a.P, LP, PF);
     const int smem_max = 227 * 1024;
     const size_t smem = (size_t)c.warps * L.bytes;
-    auto kern = k1_u_kernel<D, N, LP, MF, PF>;
+    constexpr bool CAN_FUSE = (D == 3 && N == 8 && !PF);  // the in-kernel assembly is compiled for Hex8 elastic only
+    if (a.fz.enabled) {
+      if constexpr (!CAN_FUSE) return cudaErrorInvalidValue;
+    }
+    auto kern = (a.fz.enabled && CAN_FUSE) ? k1_u_kernel<D, N, LP, MF, PF, CAN_FUSE> : k1_u_kernel<D, N, LP, MF, PF, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err != cudaSuccess) return err;
     if (a.fz.enabled) {
