@@ -329,3 +329,29 @@ def test_sorted_staging_matches_element_major_staging(make):
     assert np.array_equal(s[2].nzval, e[2].nzval)
     Kd = s[2].to_scipy()
     assert abs(Kd - Kd.T).max() == 0.0
+
+
+def test_isolated_nodes_and_shuffled_elements():
+    """Nodes that no element touches give empty CSC columns and zero residual entries; a shuffled `elems` order changes
+    only the summation order (results still match the oracle evaluated in that same order)."""
+    b, u = K.hex_case((4, 3, 3))
+    extra = 5
+    u2 = np.asfortranarray(np.concatenate([u, np.full((3, extra), 0.123)], axis=1))   # 5 unused trailing nodes
+    perm = np.random.default_rng(3).permutation(b.ne)
+    bs = El.ElemBatch("CE", 3, b.nodes[perm], b.gradN[perm], b.wgt[perm], b.mat)
+    got = El.Plan(bs, u2.shape[1], 3).makeϕrKt(u2)
+    ref = K.oracle_eval(bs, u2)
+    K.assert_parity(got, ref)
+    n0 = u.shape[1] * 3
+    assert np.all(got[1][n0:] == 0.0)
+    assert np.all(np.diff(got[2].colptr[n0:]) == 0), "untouched dofs must have empty columns"
+
+
+def test_ragged_element_list_is_rejected():
+    """All elements must have the same number of dofs (elasticelements.jl:212-214)."""
+    from ad4sm_b200 import mesh
+    bh, u = K.hex_case((2, 2, 2))
+    coords, conn = mesh.tet_kuhn(2, 2, 2)
+    bt = El.Tet04_batch(conn, coords, K.nh())
+    with pytest.raises(capi.AD4SMError):
+        El.Plan([bh, bt], max(u.shape[1], len(coords)), 3)
