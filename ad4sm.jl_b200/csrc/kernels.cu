@@ -568,7 +568,9 @@ __global__ void __launch_bounds__(256, 1)
   __syncwarp();
   unsigned char* const ws = ws0;
 
-  // lane 0: TMA bulk copies of one element group into stage s (∇N per element, wgt, N)
+  // TMA bulk copies of one element group into stage s (∇N per element, wgt, N).  Called by the whole warp: lane 0
+  // announces the byte count, then lanes 0..cnt-1 issue one ∇N copy each and lanes EW, EW+1 the small arrays -- the
+  // address arithmetic of the 4-6 copies runs in parallel instead of serially on one lane.
   auto issue = [&](long long grp, int s) {
     const long long e0 = grp * EW;
     const int cnt = (int)((a.ne - e0) < EW ? (a.ne - e0) : EW);
@@ -576,12 +578,21 @@ __global__ void __launch_bounds__(256, 1)
     const unsigned gbytes = (unsigned)(D * P * N * 8);
     const unsigned wbytes = (unsigned)((cnt * P * 8 + 15) & ~15);
     const unsigned vbytes = PF ? (unsigned)((cnt * P * N * 8 + 15) & ~15) : 0u;
-    fence_proxy_async();
-    mbar_expect_tx(bar, cnt * gbytes + wbytes + vbytes);
-    for (int i = 0; i < cnt; i++)
-      tma_load_1d(smem_u32(ws + (L.g_off + (s) * L.g_stg) + i * L.g_el), a.gradN + (e0 + i) * (long long)(D * P * N), gbytes, bar);
-    tma_load_1d(smem_u32(ws + (L.w_off + (s) * L.w_stg)), a.wgt + e0 * P, wbytes, bar);
-    if (PF) tma_load_1d(smem_u32(ws + (L.v_off + (s) * L.v_stg)), a.Nval + e0 * (long long)(P * N), vbytes, bar);
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(bar, cnt * gbytes + wbytes + vbytes);
+    }
+    __syncwarp();
+    if (lane < cnt) {
+      fence_proxy_async();
+      tma_load_1d(smem_u32(ws + (L.g_off + (s) * L.g_stg) + lane * L.g_el), a.gradN + (e0 + lane) * (long long)(D * P * N), gbytes, bar);
+    } else if (lane == EW) {
+      fence_proxy_async();
+      tma_load_1d(smem_u32(ws + (L.w_off + (s) * L.w_stg)), a.wgt + e0 * P, wbytes, bar);
+    } else if (PF && lane == EW + 1) {
+      fence_proxy_async();
+      tma_load_1d(smem_u32(ws + (L.v_off + (s) * L.v_stg)), a.Nval + e0 * (long long)(P * N), vbytes, bar);
+    }
   };
   // lane 0: node ids of group grp into id stage s.  They run one group further ahead than the rest, so that the
   // u gather of group i+1 can start at the beginning of iteration i.
@@ -602,8 +613,8 @@ __global__ void __launch_bounds__(256, 1)
   int nzero = 0, n_it = 0;
   long long grp = gwarp;
   if (grp < n_groups) {
+    issue(grp, 0);
     if (lane == 0) {
-      issue(grp, 0);
       issue_ids(grp, 0);
       if (grp + gstep < n_groups) issue_ids(grp + gstep, 1);
     }
@@ -621,10 +632,8 @@ __global__ void __launch_bounds__(256, 1)
   for (int it = 0; grp < n_groups; grp += gstep, it++) {
     const int s = it & 1;
     const bool has_next = grp + gstep < n_groups;
-    if (lane == 0) {
-      if (has_next) issue(grp + gstep, s ^ 1);
-      if (grp + 2 * gstep < n_groups) issue_ids(grp + 2 * gstep, s);  // id stage s held this group's ids: gather done
-    }
+    if (has_next) issue(grp + gstep, s ^ 1);
+    if (lane == 31 && grp + 2 * gstep < n_groups) issue_ids(grp + 2 * gstep, s);  // id stage s held this group's ids: gather done
     mbar_wait(bar0 + 8 * s, (unsigned)((it >> 1) & 1));                        // this group's ∇N, wgt, N
     if (has_next) mbar_wait(bar0 + 16 + 8 * (s ^ 1), (unsigned)(((it + 1) >> 1) & 1));  // next group's node ids
     cp_async_wait_all();                                                        // this group's u
