@@ -367,13 +367,10 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
 #pragma unroll
         for (int o = 0; o < NO; o++) {
           if (cp[o] != 0xffffffffu) {
-            const bool tr = cp[o] & 1u;
             double v[10];
 #pragma unroll
-            for (int j = 0; j < 3; j++)
-#pragma unroll
-              for (int l = 0; l < 3; l++) v[j * 3 + l] = tr ? acc[o][l * 3 + j] : acc[o][j * 3 + l];
-            v[9] = 0.0;
+            for (int i = 0; i < 9; i++) v[i] = acc[o][i];
+            v[9] = (cp[o] & 1u) ? 1.0 : 0.0;  // "stored transposed": the consumer (K2s) flips it
             if (kout_s) {  // via shared memory + one 80-byte bulk copy (TMA) per block: no store burst through the LSU
               double2* st = reinterpret_cast<double2*>(kout_s + (o * N + q) * CBLK3);
 #pragma unroll
@@ -1050,10 +1047,21 @@ cudaError_t launch_k2(const AsmArgs& a, cudaStream_t s) {
 #define AD4SM_K2S_MINB 4
 #define AD4SM_K2S_UNROLL2 1  // measured: 1.39 ms vs 1.43 ms rolled; occupancy variants (40 / 32 registers) were no faster
 constexpr int K2S_THREADS = 256;
+// acc += block, in canonical orientation.  The 10th double of a contribution block says whether the producer stored
+// it transposed (K1 stores its blocks as computed and leaves the transposition to the memory-bound consumer).
 __device__ __forceinline__ void k2s_add(double* acc, const double2* B) {
   const double2 v0 = B[0], v1 = B[1], v2 = B[2], v3 = B[3], v4 = B[4];
-  acc[0] += v0.x, acc[1] += v0.y, acc[2] += v1.x, acc[3] += v1.y, acc[4] += v2.x;
-  acc[5] += v2.y, acc[6] += v3.x, acc[7] += v3.y, acc[8] += v4.x;
+  const bool tr = v4.y != 0.0;
+  // stored entries e = 3j + l: (v0.x v0.y v1.x | v1.y v2.x v2.y | v3.x v3.y v4.x)
+  acc[0] += v0.x;
+  acc[1] += tr ? v1.y : v0.y;
+  acc[2] += tr ? v3.x : v1.x;
+  acc[3] += tr ? v0.y : v1.y;
+  acc[4] += v2.x;
+  acc[5] += tr ? v3.y : v2.y;
+  acc[6] += tr ? v1.x : v3.x;
+  acc[7] += tr ? v2.y : v3.y;
+  acc[8] += v4.x;
 }
 __global__ void __launch_bounds__(K2S_THREADS, AD4SM_K2S_MINB) k2s_kernel3(const AsmArgs a) {
   const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1068,12 +1076,11 @@ __global__ void __launch_bounds__(K2S_THREADS, AD4SM_K2S_MINB) k2s_kernel3(const
   unsigned c = c0;
   for (; c + 1 < c1; c += 2) {  // two blocks in flight; still folded in ascending (`elems`) order
     const double2* B = C2 + (long long)c * (CBLK3 / 2);
-    const double2 v0 = B[0], v1 = B[1], v2 = B[2], v3 = B[3], v4 = B[4];
-    const double2 w0 = B[5], w1 = B[6], w2 = B[7], w3 = B[8], w4 = B[9];
-    acc[0] += v0.x, acc[1] += v0.y, acc[2] += v1.x, acc[3] += v1.y, acc[4] += v2.x;
-    acc[5] += v2.y, acc[6] += v3.x, acc[7] += v3.y, acc[8] += v4.x;
-    acc[0] += w0.x, acc[1] += w0.y, acc[2] += w1.x, acc[3] += w1.y, acc[4] += w2.x;
-    acc[5] += w2.y, acc[6] += w3.x, acc[7] += w3.y, acc[8] += w4.x;
+    double2 w[10];
+#pragma unroll
+    for (int t = 0; t < 10; t++) w[t] = B[t];
+    k2s_add(acc, w);
+    k2s_add(acc, w + 5);
   }
   if (c < c1) k2s_add(acc, C2 + (long long)c * (CBLK3 / 2));
 #else
@@ -1118,16 +1125,9 @@ __global__ void __launch_bounds__(256) halo_scatter_kernel3(const double* Ke, co
 #pragma unroll
   for (int i = 0; i < 9; i++) v[i] = B[i];
   double* dst = C + (long long)(code >> 1) * CBLK3;
-  if (code & 1u) {
 #pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int l = 0; l < 3; l++) dst[j * 3 + l] = v[l * 3 + j];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 9; i++) dst[i] = v[i];
-  }
-  dst[9] = 0.0;
+  for (int i = 0; i < 9; i++) dst[i] = v[i];
+  dst[9] = (code & 1u) ? 1.0 : 0.0;
 }
 cudaError_t launch_halo_scatter(const double* Ke, const unsigned* cpos, double* C, long long slot0, long long n_slots, int NPB,
                                 cudaStream_t s) {
