@@ -792,8 +792,7 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
   // it reads (export ranges / peer links) gets the sorted path, with K1 materialising exactly those ranges
   const bool kmode_ok = want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U);
   const bool sorted_ok = kmode_ok && p->sorted_built && p->sorted_on && (internal || p->dist_aware);
-  if (!internal && !sorted_ok && p->dist_aware && p->n_xr_local)
-    return fail(AD4SM_ESTATE, "export ranges are only served by the sorted path");
+
   const bool fuse2 = internal && sorted_ok && p->fuse_allowed && p->batch_rec != nullptr;  // K1 + K2s in one kernel
   const bool fuse = internal && !fuse2 && kmode_ok && p->fz.enabled && p->fuse_allowed;   // K1 + K2 + K3 in one kernel
   const bool sorted = sorted_ok && !fuse;
@@ -813,7 +812,9 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
     a.Ke = p->Ke;
     a.re = p->re;
     a.phie = p->phie;
-    if (p->n_xr && !internal) {  // two-stage API of a partitioned run: K1 also writes the interface rows for the owners
+    // two-stage API of a partitioned run: K1 also writes the interface rows for the owners (peer memory), or -- on the
+    // sorted path -- materialises the declared local ranges element-major (the element-major path writes everything so)
+    if (p->n_xr && !internal && (sorted || !p->n_xr_local)) {
       if (b.k.slot0 == 0) {
         a.n_xr = p->n_xr;
         for (int x = 0; x < p->n_xr; x++) a.xr[x] = p->xr[x];

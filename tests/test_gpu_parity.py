@@ -178,14 +178,20 @@ def test_cuda_path_reproduces_golden_vectors(path):
     _golden.compare(_golden.run_product(case), case, tol=K.TOL)
 
 
-def test_two_rank_halo_exchange_single_gpu():
+@pytest.mark.parametrize("shape", ["hex8", "tet4"])
+def test_two_rank_halo_exchange_single_gpu(shape):
     """Mesh-partitioned evaluation (dist.py) emulated on ONE GPU: two in-process plans with HALO batches, the
     interface staging copied between them where NCCL send/recv would carry it.  Owned rows must be BITWISE equal to
-    the single-plan result (same contributions, same `elems` order)."""
+    the single-plan result (same contributions, same `elems` order).  hex8 runs on the destination-sorted path with
+    export ranges + HALO scatter, tet4 (one Gauss point) on the element-major path."""
     import torch
     from ad4sm_b200 import dist as AD, mesh
-    coords, conn = mesh.hex_block(4, 3, 6, jitter=0.1, seed=21)
-    b = El.Hex08_batch(conn, coords, K.nh())
+    if shape == "hex8":
+        coords, conn = mesh.hex_block(4, 3, 6, jitter=0.1, seed=21)
+        b = El.Hex08_batch(conn, coords, K.nh())
+    else:
+        coords, conn = mesh.tet_kuhn(3, 3, 4, jitter=0.1, seed=21)
+        b = El.Tet04_batch(conn, coords, Ma.MooneyRivlin(800.0, 200.0, 5000.0))
     u = mesh.random_u(len(coords), 3, 1 / 6, seed=22)
     phi0, r0, Kt0 = El.Plan(b, u.shape[1], 3).makeϕrKt(u)
     world = 2
@@ -195,6 +201,7 @@ def test_two_rank_halo_exchange_single_gpu():
     for p in parts:
         own = El.ElemBatch("CE", 3, p.local_conn(conn[p.own_elems]), b.gradN[p.own_elems], b.wgt[p.own_elems], b.mat)
         backs.append(AD.GpuBackend(own, p.local_conn(conn[p.halo_elems]), p, 3))
+    assert all(be.plan.info(capi.INFO_SORTED) == (2 if shape == "hex8" else 0) for be in backs)
     for p, be in zip(parts, backs):
         ul = torch.from_numpy(np.ascontiguousarray(u[:, p.local_nodes - 1].T)).cuda()
         be.eval_elements(ul)
