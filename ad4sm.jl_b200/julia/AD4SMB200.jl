@@ -44,6 +44,7 @@ matdesc(m::Hooke)                   = (MAT_HOOKE,        Int32(0), m.small ? F_S
 matdesc(m::Hooke2D{T,P}) where {T,P} = (MAT_HOOKE2D,      Int32(0), (m.small ? F_SMALL : UInt32(0)) | (P == :plane_stress ? F_PLANE_STRESS : UInt32(0)), (m.E, m.ν))
 matdesc(m::NeoHooke)                = (MAT_NEOHOOKE,     Int32(0), UInt32(0), (m.C1, m.K))
 matdesc(m::MooneyRivlin)            = (MAT_MOONEYRIVLIN, Int32(0), UInt32(0), (m.C1, m.C2, m.K))
+matdesc(m::Ogden)                   = (MAT_OGDEN,        Int32(0), UInt32(0), (m.α, m.μ, m.K))
 function matdesc(m::PhaseField{M,AT}; intended_grad=false, nh2d=false) where {M,AT}
   kind, _, flags, p = matdesc(m.mat)
   flags |= (AT == :DHn ? F_DHN : UInt32(0)) | (intended_grad ? F_PF_GRAD_INTENDED : UInt32(0)) | (nh2d ? F_NH2D_EXT : UInt32(0))
