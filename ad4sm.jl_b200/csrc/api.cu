@@ -683,9 +683,11 @@ static AsmArgs asm_args(ad4sm_plan* p, int field) {
   a.out_lo = p->out_lo;
   a.nn_pack = p->nn_pack;
   a.C = p->C;
-  static int skip = -1;
-  if (skip < 0) skip = getenv("AD4SM_EXP_SKIP_MIRROR") ? 1 : 0;
-  a.skip_mirror = skip;
+  static int k2s_exp = -1, k2s_direct = -1;
+  if (k2s_exp < 0) k2s_exp = getenv("AD4SM_EXP_K2S") ? atoi(getenv("AD4SM_EXP_K2S")) : 0;
+  if (k2s_direct < 0) k2s_direct = getenv("AD4SM_K2S_DIRECT") ? atoi(getenv("AD4SM_K2S_DIRECT")) : 0;
+  a.k2s_exp = k2s_exp;
+  a.k2s_direct = k2s_direct;
   return a;
 }
 

@@ -31,7 +31,8 @@ struct AsmArgs {
   const unsigned* out_up;       // [n_pairs] nzval offset of block (i, p)
   const unsigned* out_lo;       // [n_pairs] nzval offset of block (p, i)   (== out_up for i == p)
   const unsigned* nn_pack;      // [n_pairs] row lengths: nn(i) | nn(p) << 16
-  int skip_mirror;              // TIMING EXPERIMENT ONLY (AD4SM_EXP_SKIP_MIRROR): K2s leaves the lower triangle unwritten
+  int k2s_direct;               // K2s with per-thread loads instead of the TMA-staged reads (AD4SM_K2S_DIRECT=1)
+  int k2s_exp;                  // TIMING EXPERIMENT ONLY (AD4SM_EXP_K2S): 1 K2s leaves the lower triangle unwritten, 2 writes nothing
   const double* C;              // [ne*NPB][CBLK] contribution blocks, canonical orientation (row node <= col node)
 };
 constexpr int CBLK3 = 10;       // doubles per 3x3 contribution block: 9 + 1 pad = 80 B, 16-byte aligned

@@ -1039,14 +1039,20 @@ cudaError_t launch_k2(const AsmArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 // ---- K2s: Kt values from the destination-sorted staging.  One thread per unordered node pair {i <= p}: its
-// contributions are contiguous (streaming 16-byte loads, no source-map indirection, neighbouring threads read
-// neighbouring memory), summed in `elems` order like K2; the sum is written to block (i, p) and, transposed, to
-// block (p, i) -- both triangles carry the same bits.  Measured alternatives, all bitwise-equal: a CTA-cooperative
-// variant streaming the range through shared memory (1.58 ms), five threads per pair with fully coalesced 16-byte
-// chunks and 30 registers (1.38 ms) -- the kernel is insensitive to how the reads are organised.
+// contributions are contiguous in C and are summed in `elems` order like K2; the sum is written to block (i, p) and,
+// transposed, to block (p, i) -- both triangles carry the same bits.
+// What bounds it (measured, 1 M Hex8): not DRAM bytes but L1 wavefronts = instructions x distinct 128-byte lines.  With
+// per-thread 16-byte loads every instruction touches 32 lines (reads alone 0.64 ms); so the 32 pairs of a warp fetch
+// their one contiguous range of C (about 6.6 KB on a hex mesh) with a single TMA bulk copy into the warp's
+// shared-memory slice -- no LSU work for the global reads, 0.50 ms = 6.5 TB/s read-only -- and each lane folds its
+// blocks out of shared memory.  The 24-byte runs of the CSC output go out as one 16-byte and one 8-byte store
+// (k2s_store3: 12 store instructions per pair instead of 18, -0.16 ms).  Left: the writes cost 0.22 ms (upper) and
+// 0.30 ms (transposed copy, 24-byte pieces scattered over 13 columns) per GB where DRAM alone would take 0.16.
+// Alternatives measured, all bitwise equal: streaming / write-through store hints (no change), a CTA-cooperative
+// shared-memory stream with LDG (1.58 ms), five threads per pair (1.38 ms), smaller slices / more warps (slower).
 #define AD4SM_K2S_MINB 4
-#define AD4SM_K2S_UNROLL2 1  // measured: 1.39 ms vs 1.43 ms rolled; occupancy variants (40 / 32 registers) were no faster
 constexpr int K2S_THREADS = 256;
+constexpr int K2T_WARPS = 4, K2T_BLOCKS = 128;  // staged kernel: warps per CTA, blocks per warp slice (10 KB)
 // acc += block, in canonical orientation.  The 10th double of a contribution block says whether the producer stored
 // it transposed (K1 stores its blocks as computed and leaves the transposition to the memory-bound consumer).
 __device__ __forceinline__ void k2s_add(double* acc, const double2* B) {
@@ -1063,7 +1069,39 @@ __device__ __forceinline__ void k2s_add(double* acc, const double2* B) {
   acc[7] += tr ? v2.y : v3.y;
   acc[8] += v4.x;
 }
-__global__ void __launch_bounds__(K2S_THREADS, AD4SM_K2S_MINB) k2s_kernel3(const AsmArgs a) {
+// three consecutive doubles at an 8-byte-aligned address as one 16-byte and one 8-byte store (lane-dependent split, no
+// divergence)
+__device__ __forceinline__ void k2s_store3(double* p, double v0, double v1, double v2) {
+  const bool odd = (reinterpret_cast<unsigned long long>(p) & 8ull) != 0;
+  *reinterpret_cast<double2*>(p + (odd ? 1 : 0)) = odd ? make_double2(v1, v2) : make_double2(v0, v1);
+  p[odd ? 0 : 2] = odd ? v0 : v2;
+}
+// Block (i, p) and its transpose into the CSC values.  EXP is a TIMING EXPERIMENT switch (AD4SM_EXP_K2S; the results
+// are wrong): 1 leaves the lower triangle unwritten, 2 writes nothing.
+template <int EXP>
+__device__ __forceinline__ void k2s_write(const AsmArgs& a, const double* acc, unsigned oup, unsigned olo, unsigned nn) {
+  const long long su = 3ll * (nn & 0xffffu), sl = 3ll * (nn >> 16);  // column lengths of the two destinations
+  if (EXP == 2) {  // keep the loads alive
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 9; j++) t += acc[j];
+    if (t == 1.2345e300) a.nzval[oup] = t;
+    return;
+  }
+  int nz = 0;
+#pragma unroll
+  for (int j = 0; j < 9; j++) nz += (acc[j] == 0.0);
+#pragma unroll
+  for (int j = 0; j < 3; j++) k2s_store3(a.nzval + oup + j * su, acc[j * 3], acc[j * 3 + 1], acc[j * 3 + 2]);
+  if (olo != oup && EXP != 1) {
+#pragma unroll
+    for (int l = 0; l < 3; l++) k2s_store3(a.nzval + olo + l * sl, acc[l], acc[3 + l], acc[6 + l]);
+    nz *= 2;
+  }
+  if (nz) atomicAdd(a.n_zero, (unsigned long long)nz);  // integer atomic: order-independent
+}
+// direct-load variant (AD4SM_K2S_DIRECT=1; also what ranges too large for a slice fall back to, per warp)
+template <int EXP> __global__ void __launch_bounds__(K2S_THREADS, AD4SM_K2S_MINB) k2s_kernel3(const AsmArgs a) {
   const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= a.n_pairs) return;
   const unsigned c0 = __ldg(a.cptr + u), c1 = __ldg(a.cptr + u + 1);
@@ -1072,7 +1110,6 @@ __global__ void __launch_bounds__(K2S_THREADS, AD4SM_K2S_MINB) k2s_kernel3(const
 #pragma unroll
   for (int t = 0; t < 9; t++) acc[t] = 0.0;
   const double2* C2 = reinterpret_cast<const double2*>(a.C);
-#ifdef AD4SM_K2S_UNROLL2
   unsigned c = c0;
   for (; c + 1 < c1; c += 2) {  // two blocks in flight; still folded in ascending (`elems`) order
     const double2* B = C2 + (long long)c * (CBLK3 / 2);
@@ -1083,33 +1120,61 @@ __global__ void __launch_bounds__(K2S_THREADS, AD4SM_K2S_MINB) k2s_kernel3(const
     k2s_add(acc, w + 5);
   }
   if (c < c1) k2s_add(acc, C2 + (long long)c * (CBLK3 / 2));
-#else
-  for (unsigned c = c0; c < c1; c++) k2s_add(acc, C2 + (long long)c * (CBLK3 / 2));
-#endif
-  const int dpn = 3;
-  const long long su = (long long)dpn * (nn & 0xffffu), sl = (long long)dpn * (nn >> 16);
-  int nz = 0;
-#pragma unroll
-  for (int j = 0; j < 3; j++)
-#pragma unroll
-    for (int l = 0; l < 3; l++) {
-      a.nzval[oup + j * su + l] = acc[j * 3 + l];
-      nz += (acc[j * 3 + l] == 0.0);
-    }
-  if (olo != oup && !a.skip_mirror) {
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int l = 0; l < 3; l++) a.nzval[olo + l * sl + j] = acc[j * 3 + l];
-    nz *= 2;
+  k2s_write<EXP>(a, acc, oup, olo, nn);
+}
+template <int EXP> __global__ void __launch_bounds__(K2T_WARPS * 32) k2s_tma_kernel3(const AsmArgs a) {
+  __shared__ __align__(128) double2 buf[K2T_WARPS][K2T_BLOCKS * (CBLK3 / 2)];
+  __shared__ __align__(8) unsigned long long bars[K2T_WARPS];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long u = ((long long)blockIdx.x * K2T_WARPS + w) * 32 + lane;
+  if (u - lane >= a.n_pairs) return;  // whole warp; no CTA-wide barrier below
+  const bool valid = u < a.n_pairs;
+  const unsigned c0 = __ldg(a.cptr + (valid ? u : a.n_pairs)), c1 = valid ? __ldg(a.cptr + u + 1) : c0;
+  const unsigned w0 = __shfl_sync(0xffffffffu, c0, 0), w1 = __shfl_sync(0xffffffffu, c1, 31);  // the warp's range of C
+  const unsigned nb = w1 - w0;
+  const bool staged = nb <= (unsigned)K2T_BLOCKS && nb > 0;
+  const unsigned bar = smem_u32(&bars[w]);
+  if (staged && lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(bar, nb * (unsigned)(CBLK3 * sizeof(double)));
+    tma_load_1d(smem_u32(buf[w]), a.C + (long long)w0 * CBLK3, nb * (unsigned)(CBLK3 * sizeof(double)), bar);
   }
-  if (nz) atomicAdd(a.n_zero, (unsigned long long)nz);
+  const long long um = valid ? u : 0;  // destinations: fetched while the copy flies
+  const unsigned oup = __ldg(a.out_up + um), olo = __ldg(a.out_lo + um), nn = __ldg(a.nn_pack + um);
+  double acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; t++) acc[t] = 0.0;
+  __syncwarp();
+  if (staged) {
+    mbar_wait(bar, 0);
+    const double2* B = buf[w] + (c0 - w0) * (CBLK3 / 2);
+    for (unsigned c = c0; c < c1; c++, B += CBLK3 / 2) k2s_add(acc, B);
+  } else {
+    const double2* C2 = reinterpret_cast<const double2*>(a.C);
+    for (unsigned c = c0; c < c1; c++) k2s_add(acc, C2 + (long long)c * (CBLK3 / 2));
+  }
+  if (valid) k2s_write<EXP>(a, acc, oup, olo, nn);
 }
 cudaError_t launch_k2s(const AsmArgs& a, cudaStream_t s) {
   if (a.DB != 3 || a.dpn != 3 || a.n_pairs <= 0) return cudaErrorInvalidValue;
   cudaError_t err = cudaMemsetAsync(a.n_zero, 0, sizeof(unsigned long long), s);
   if (err != cudaSuccess) return err;
-  k2s_kernel3<<<(unsigned)((a.n_pairs + K2S_THREADS - 1) / K2S_THREADS), K2S_THREADS, 0, s>>>(a);
+  if (a.k2s_direct) {
+    const unsigned grid = (unsigned)((a.n_pairs + K2S_THREADS - 1) / K2S_THREADS);
+    switch (a.k2s_exp) {
+      case 1: k2s_kernel3<1><<<grid, K2S_THREADS, 0, s>>>(a); break;
+      case 2: k2s_kernel3<2><<<grid, K2S_THREADS, 0, s>>>(a); break;
+      default: k2s_kernel3<0><<<grid, K2S_THREADS, 0, s>>>(a); break;
+    }
+  } else {
+    const unsigned grid = (unsigned)((a.n_pairs + K2T_WARPS * 32 - 1) / (K2T_WARPS * 32));
+    switch (a.k2s_exp) {
+      case 1: k2s_tma_kernel3<1><<<grid, K2T_WARPS * 32, 0, s>>>(a); break;
+      case 2: k2s_tma_kernel3<2><<<grid, K2T_WARPS * 32, 0, s>>>(a); break;
+      default: k2s_tma_kernel3<0><<<grid, K2T_WARPS * 32, 0, s>>>(a); break;
+    }
+  }
   return cudaGetLastError();
 }
 // ---- partitioned runs with destination-sorted staging: the HALO elements' blocks arrive element-major (exchange /
