@@ -338,6 +338,32 @@ def test_sorted_staging_matches_element_major_staging(make):
     assert abs(Kd - Kd.T).max() == 0.0
 
 
+def test_pipelined_upload_matches_single_copy(monkeypatch):
+    """Host API on a mesh large enough for the pipelined upload (u in node chunks, K1 in element slices): same bits as
+    one copy + one launch, for the elastic path and for the phase-field d-phase with history."""
+    from ad4sm_b200 import mesh
+    b, u = K.hex_case((41, 41, 41))
+    piped = El.Plan(b, u.shape[1], 3).makeϕrKt(u)
+    monkeypatch.setenv("AD4SM_H2D_SLICES", "0")
+    plain_plan = El.Plan(b, u.shape[1], 3)
+    monkeypatch.delenv("AD4SM_H2D_SLICES")
+    plain = plain_plan.makeϕrKt(u)
+    assert piped[0] == plain[0] and np.array_equal(piped[1], plain[1]) and np.array_equal(piped[2].nzval, plain[2].nzval)
+    coords, conn = mesh.quad_grid(260, 260, jitter=0.1, seed=7)
+    pf = Ma.PhaseField(0.01, 100.0, Ma.Hooke2D(210000.0, 0.3, plane_stress=False), 2)
+    bq = El.QuadP_batch(conn, coords, pf)
+    uq = mesh.random_u(len(coords), 2, 1 / 260, a=0.3, seed=8)
+    d = K.random_d(uq.shape[1], seed=9)
+    h1, h2 = np.zeros((bq.ne, bq.P, 2)), np.zeros((bq.ne, bq.P, 2))
+    g1 = El.Plan(bq, uq.shape[1], 2).makeϕrKt_d(uq, d, h1)
+    monkeypatch.setenv("AD4SM_H2D_SLICES", "0")
+    plain_plan = El.Plan(bq, uq.shape[1], 2)
+    monkeypatch.delenv("AD4SM_H2D_SLICES")
+    g2 = plain_plan.makeϕrKt_d(uq, d, h2)
+    assert g1[0] == g2[0] and np.array_equal(g1[1], g2[1]) and np.array_equal(g1[2].nzval, g2[2].nzval)
+    assert np.array_equal(h1, h2) and h1.max() > 0.0
+
+
 def test_isolated_nodes_and_shuffled_elements():
     """Nodes that no element touches give empty CSC columns and zero residual entries; a shuffled `elems` order changes
     only the summation order (results still match the oracle evaluated in that same order)."""
