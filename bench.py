@@ -281,13 +281,13 @@ def run_ours(args):
     at_profiled_size = (n == 100 and (args.nz or n) == 100 and args.material == "neohooke")
     roof_k1 = {"kernel": "k1_u_kernel<3,8,8,NEO> (element energy/gradient/Hessian)", "bound": "fp64", "achieved": k1_tflops,
                "peak": fp64_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak if fp64_peak else None,
-               "traffic": (1.912297e9 + 3.118890e9) if at_profiled_size else None, "traffic_unit": "bytes/launch (ncu)",
+               "traffic": (1.905480e9 + 3.114725e9) if at_profiled_size else None, "traffic_unit": "bytes/launch (ncu)",
                "algorithmic_bytes_per_launch": (32 + 1536 + 64 + 24.7 + 144 + 36 * 80 + 192 + 8) * ne_local,
                "ms_per_launch": k1_ms, "peak_source": "DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
                "algorithmic_flop_per_element": W_ALG_FLOP}
     roof_k2 = {"kernel": "k3_kernel + k2s_tma_kernel3 (deterministic assembly from the destination-sorted staging)", "bound": "hbm",
                "achieved": k2_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": k2_gbs / peaks["hbm_gbs"],
-               "traffic": (3.270127e9 + 2.055876e9) if at_profiled_size else None, "traffic_unit": "bytes/launch (ncu, k2s_tma_kernel3)",
+               "traffic": (3.202257e9 + 1.993955e9) if at_profiled_size else None, "traffic_unit": "bytes/launch (ncu, k2s_tma_kernel3)",
                "ms_per_launch": k2_ms, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "algorithmic_bytes_per_element": B_ALG_K2}
     dominant = roof_k1 if k1_ms >= k2_ms else roof_k2
     # whole-path roofline: binding time per element = max(W_alg / FP64 peak, B_alg / HBM peak)
