@@ -588,6 +588,29 @@ class Plan:
         capi.check(self._L.ad4sm_eval_elements_device(self._h, mode, C.c_void_p(u_ptr), C.c_void_p(d_ptr) if d_ptr else None,
                                                       C.c_void_p(hist_ptr) if hist_ptr else None))
 
+    def eval_elements_host(self, mode, u, d=None):
+        """Element stage with host inputs (numpy, column-major D x nNodes like `makeϕrKt`'s u): asynchronous upload --
+        chunked and overlapped with K1 on large plans -- then K1.  The arrays must stay untouched until `sync()`."""
+        u = np.asarray(u)
+        if u.dtype != np.float64 or not (u.flags.f_contiguous or u.flags.c_contiguous):
+            raise ValueError("u must be contiguous float64 memory laid out [node][component], i.e. a column-major "
+                             "D x nNodes matrix or its C-ordered transpose (no hidden copy on the asynchronous path)")
+        dp = None
+        if d is not None:
+            d = np.asarray(d)
+            if d.dtype != np.float64 or not (d.flags.c_contiguous or d.flags.f_contiguous):
+                raise ValueError("d must be a contiguous float64 array")
+            dp = C.c_void_p(d.ctypes.data)
+        capi.check(self._L.ad4sm_eval_elements_host(self._h, mode, C.c_void_p(u.ctypes.data), dp, None))
+
+    def fetch_phi_r_async(self, r_out, phi_out=None, field=capi.FIELD_U):
+        """Enqueue the device-to-host copy of r (and ϕ, a 1-element float64 array) of the last assembly; it starts as soon
+        as they are final and overlaps the Kt assembly.  Valid after `sync()`."""
+        if r_out.dtype != np.float64 or not r_out.flags.c_contiguous and not r_out.flags.f_contiguous:
+            raise ValueError("r_out must be a contiguous float64 array")
+        capi.check(self._L.ad4sm_fetch_phi_r_async(self._h, field, C.c_void_p(phi_out.ctypes.data) if phi_out is not None else None,
+                                                   C.c_void_p(r_out.ctypes.data)))
+
     def eval_assemble_device(self, mode):
         """K2/K3 + ϕ reduction over the staging of all batches (after any interface exchange)."""
         capi.check(self._L.ad4sm_eval_assemble_device(self._h, mode))

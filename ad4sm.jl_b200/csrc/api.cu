@@ -406,13 +406,16 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       return fail(AD4SM_ENODEV, "cudaStreamCreate/cudaEventCreate failed");
     }
   }
-  // pipelined upload (host API): a single ordinary batch whose node numbering follows the element order (structured /
+  // pipelined upload (host API): a single ordinary batch (HALO batches may follow it) whose node numbering follows the element order (structured /
   // bandwidth-reduced meshes).  Slices of 1/16, 1/4, 1/2 and all of the elements, on 32-element boundaries (keeps the
   // 16-byte alignment of every per-element array); each needs the nodes below its running maximum.
   {
     const char* env = getenv("AD4SM_H2D_SLICES");
     const bool want = !env || atoi(env) != 0;
-    if (want && n_batches == 1 && !(batches[0].batch_flags & AD4SM_BATCH_HALO) && ne >= 65536) {
+    int n_ord = 0;
+    for (int b = 0; b < n_batches; b++) n_ord += !(batches[b].batch_flags & AD4SM_BATCH_HALO);
+    const long long ne = (n_ord == 1 && !(batches[0].batch_flags & AD4SM_BATCH_HALO)) ? batches[0].n_elems : 0;  // shadows: own elements
+    if (want && ne >= 65536) {
       const long long frac16[ad4sm_plan::H2D_MAX] = {1, 4, 8, 16};
       long long mx = 0, e = 0;
       bool ok = true;
@@ -1065,6 +1068,7 @@ int ad4sm_sync(ad4sm_plan* p) {
   if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
   CK(cudaSetDevice(p->device));
   CK(cudaStreamSynchronize(p->stream));
+  if (p->copy_stream) CK(cudaStreamSynchronize(p->copy_stream));
   return AD4SM_OK;
 }
 
@@ -1087,9 +1091,11 @@ int ad4sm_device_view_get(ad4sm_plan* p, int32_t field, ad4sm_device_view* v) {
 }
 
 // host-pointer evaluation shared by the four reference-facing entry points
-static int eval_host(ad4sm_plan* p, int mode, const double* u, const double* d, double* const* hist, double* phi,
-                     double* r, int64_t* nnz_out) {
+// Host inputs -> device, asynchronously.  With a pipelined plan (n_h2d > 0) u and d travel in node chunks on the copy
+// stream, each followed by an event that the K1 launch of the matching element slice waits for (h2d_active).
+static int upload_inputs(ad4sm_plan* p, int mode, const double* u, const double* d, double* const* hist) {
   if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (mode < 0 || mode > 3) return fail(AD4SM_EINVAL, "mode must be 0..3");
   if (!u) return fail(AD4SM_EINVAL, "u is NULL");
   CK(cudaSetDevice(p->device));
   cudaStream_t s = p->stream;
@@ -1100,7 +1106,7 @@ static int eval_host(ad4sm_plan* p, int mode, const double* u, const double* d, 
   }
   if (hist)
     for (size_t b = 0; b < p->batches.size(); b++)
-      if (!hist[b]) return fail(AD4SM_EINVAL, "hist pointer of a batch is NULL");
+      if (!hist[b] && !p->batches[b].halo) return fail(AD4SM_EINVAL, "hist pointer of a batch is NULL");
   if (p->n_h2d > 0) {  // node chunks on the copy stream; K1 slice c waits for ev_h2d[c]
     CK(cudaEventRecord(p->ev_start, s));
     CK(cudaStreamWaitEvent(p->copy_stream, p->ev_start, 0));
@@ -1119,12 +1125,33 @@ static int eval_host(ad4sm_plan* p, int mode, const double* u, const double* d, 
   }
   if (hist)
     for (const BatchPlan& b : p->batches) {
+      if (b.halo) continue;
       const double* h = hist[&b - p->batches.data()];
-      if (!h) return fail(AD4SM_EINVAL, "hist pointer of a batch is NULL");
       CK(cudaMemcpyAsync(p->hist_dev + b.hist_off * 2, h, sizeof(double) * 2 * b.k.ne * b.k.P, cudaMemcpyHostToDevice, s));
     }
+  return AD4SM_OK;
+}
+// ϕ and r of the last assembly to the host on the copy stream, as soon as K3 and the ϕ reduction are done (the Kt
+// assembly keeps running on the main stream); the main stream then waits for the copy, so that a following evaluation
+// cannot overwrite r before it has left.
+static int download_phi_r(ad4sm_plan* p, int field, double* phi, double* r) {
+  FieldOut& f = p->field[field];
+  CK(cudaStreamWaitEvent(p->copy_stream, p->ev_r_ready, 0));
+  if (phi) CK(cudaMemcpyAsync(phi, p->phi_dev, sizeof(double), cudaMemcpyDeviceToHost, p->copy_stream));
+  if (r) CK(cudaMemcpyAsync(r, f.r, sizeof(double) * f.n_dof, cudaMemcpyDeviceToHost, p->copy_stream));
+  CK(cudaEventRecord(p->ev_copied, p->copy_stream));
+  CK(cudaStreamWaitEvent(p->stream, p->ev_copied, 0));
+  return AD4SM_OK;
+}
+
+static int eval_host(ad4sm_plan* p, int mode, const double* u, const double* d, double* const* hist, double* phi,
+                     double* r, int64_t* nnz_out) {
+  int rc = upload_inputs(p, mode, u, d, hist);
+  if (rc) return rc;
+  cudaStream_t s = p->stream;
+  const bool needs_d = (mode == MODE_PF_U || mode == MODE_PF_D);
   p->h2d_active = p->n_h2d > 0;
-  int rc = ad4sm_eval_device(p, mode, p->u_dev, needs_d ? p->d_dev : nullptr, hist ? p->hist_dev : nullptr);
+  rc = ad4sm_eval_device(p, mode, p->u_dev, needs_d ? p->d_dev : nullptr, hist ? p->hist_dev : nullptr);
   p->h2d_active = false;
   if (rc) {
     if (p->n_h2d > 0) cudaStreamSynchronize(p->copy_stream);  // the caller's buffers must not be in flight on return
@@ -1133,14 +1160,12 @@ static int eval_host(ad4sm_plan* p, int mode, const double* u, const double* d, 
   const int field = mode == MODE_PF_D ? AD4SM_FIELD_D : AD4SM_FIELD_U;
   FieldOut& f = p->field[field];
   unsigned long long nz = 0;
-  CK(cudaStreamWaitEvent(p->copy_stream, p->ev_r_ready, 0));
-  if (phi) CK(cudaMemcpyAsync(phi, p->phi_dev, sizeof(double), cudaMemcpyDeviceToHost, p->copy_stream));
-  if (r) CK(cudaMemcpyAsync(r, f.r, sizeof(double) * f.n_dof, cudaMemcpyDeviceToHost, p->copy_stream));
-  CK(cudaEventRecord(p->ev_copied, p->copy_stream));
-  CK(cudaStreamWaitEvent(s, p->ev_copied, 0));  // the next evaluation on `s` must not overwrite r before it has left
+  rc = download_phi_r(p, field, phi, r);
+  if (rc) return rc;
   if (mode != MODE_PHI_R) CK(cudaMemcpyAsync(&nz, p->n_zero_dev, sizeof(nz), cudaMemcpyDeviceToHost, s));
   if (hist)
     for (const BatchPlan& b : p->batches) {
+      if (b.halo) continue;
       double* h = hist[&b - p->batches.data()];
       CK(cudaMemcpyAsync(h, p->hist_dev + b.hist_off * 2, sizeof(double) * 2 * b.k.ne * b.k.P, cudaMemcpyDeviceToHost, s));
     }
@@ -1150,6 +1175,25 @@ static int eval_host(ad4sm_plan* p, int mode, const double* u, const double* d, 
     if (nnz_out) *nnz_out = f.nnz - f.n_zero;
   }
   return AD4SM_OK;
+}
+
+// mesh-partitioned runs with host-resident inputs / outputs: the two ends of the two-stage API
+int ad4sm_eval_elements_host(ad4sm_plan* p, int32_t mode, const double* u, const double* d, double* const* hist) {
+  int rc = upload_inputs(p, mode, u, d, hist);
+  if (rc) return rc;
+  const bool needs_d = (mode == MODE_PF_U || mode == MODE_PF_D);
+  p->h2d_active = p->n_h2d > 0;
+  rc = eval_elements_impl(p, mode, p->u_dev, needs_d ? p->d_dev : nullptr, hist ? p->hist_dev : nullptr, false);
+  p->h2d_active = false;
+  if (rc && p->n_h2d > 0) cudaStreamSynchronize(p->copy_stream);
+  return rc;
+}
+int ad4sm_fetch_phi_r_async(ad4sm_plan* p, int32_t field, double* phi, double* r) {
+  int rc = check_field(p, field);
+  if (rc) return rc;
+  if (!p->field[field].evaluated) return fail(AD4SM_ESTATE, "ad4sm_fetch_phi_r_async before any evaluation of this field");
+  CK(cudaSetDevice(p->device));
+  return download_phi_r(p, field, phi, r);
 }
 
 int ad4sm_eval(ad4sm_plan* p, const double* u, double* phi, double* r, int64_t* nnz_out) {

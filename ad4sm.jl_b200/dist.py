@@ -193,6 +193,12 @@ class GpuBackend:
         self.plan.eval_elements_device(self.mode, u_dev.data_ptr(), d_dev.data_ptr() if d_dev is not None else None,
                                        hist_dev.data_ptr() if hist_dev is not None else None)
 
+    def eval_elements_host(self, u_host, d_host=None):
+        self.plan.eval_elements_host(self.mode, u_host, d_host)
+
+    def fetch_r_async(self, r_host):
+        self.plan.fetch_phi_r_async(r_host, None, self.field_id)
+
     def staging(self):
         return self.Ke, self.re
 
@@ -255,11 +261,20 @@ class DistPlan:
         self.b, self.part = backend, part
         self._tok = None
 
-    def step(self, *eval_args):
+    def step_host(self, u_host, r_host, d_host=None):
+        """One evaluation with host-resident u (in) and r (out, this rank's local dofs): the upload overlaps K1, the
+        download of r overlaps the Kt assembly.  Returns the global ϕ as a 0-d tensor; r_host is valid after
+        `backend.plan.sync()`."""
+        return self.step(host=(u_host, r_host, d_host))
+
+    def step(self, *eval_args, host=None):
         """One evaluation, everything left on the device.  Returns the global ϕ as a 0-d tensor."""
         import torch
         import torch.distributed as D
-        self.b.eval_elements(*eval_args)
+        if host is not None:
+            self.b.eval_elements_host(host[0], host[2])
+        else:
+            self.b.eval_elements(*eval_args)
         if getattr(self.b, "peer", False):
             # the interface staging has been written into the owners' HALO slots by K1 itself: only a barrier is left
             if self._tok is None:
@@ -268,6 +283,8 @@ class DistPlan:
         else:
             exchange_staging(self.part, self.b.n_own, self.b.staging())
         self.b.assemble()
+        if host is not None:
+            self.b.fetch_r_async(host[1])
         phi = self.b.phi_tensor()
         if self.part.world == 1:
             return phi[0]
@@ -354,12 +371,7 @@ class SlabRunner:
 
     def step_host(self, u_host_np, r_host_np):
         """end to end: u from pinned host memory -> device, evaluation + exchange, ϕ and this rank's r back to the host"""
-        torch = self.torch
-        if self._u_dev is None:
-            self._u_dev = torch.empty(u_host_np.shape, dtype=torch.float64, device="cuda")
-            self._r_host = torch.from_numpy(r_host_np)
-        self._u_dev.copy_(torch.from_numpy(u_host_np), non_blocking=True)
-        phi = self.dplan.step(self._u_dev)
-        self._r_host.copy_(self.backend.r_tensor(), non_blocking=True)
-        val = float(phi.item())   # synchronises
+        phi = self.dplan.step_host(u_host_np, r_host_np)
+        val = float(phi.item())   # synchronises the main stream
+        self.plan.sync()          # and the copy stream that carries r
         return val

@@ -316,8 +316,12 @@ def run_ours(args):
                    "plan_build_s": t_build},
         "clocks": dict(clk.summary(), note="sampled every 50 ms over the timed region and ~0.4 s more of the same load"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "call": "ad4sm_eval(plan, u_host, &phi, r_host, &nnz): u H2D, ϕ and r D2H inside the timed region; Kt stays on the device "
-                        "(the reference's consumer, lu(Kt[ifree,ifree]), is out of scope)"},
+                "call": ("ad4sm_eval(plan, u_host, &phi, r_host, &nnz)" if world == 1 else
+                         "per rank: ad4sm_eval_elements_host(u_host) -> interface exchange -> ad4sm_eval_assemble_device -> "
+                         "ad4sm_fetch_phi_r_async(r_host) -> ϕ all-gather -> sync")
+                        + ": u H2D (node chunks, overlapped with K1), ϕ and r D2H (overlapped with the Kt assembly) inside the timed "
+                          "region, pinned host buffers; Kt stays on the device (the reference's consumer, lu(Kt[ifree,ifree]), is "
+                          "out of scope)"},
         "gpu_launches": int(sum(prof_n)),
         "roofline": dominant, "roofline_kernels": [roof_k1, roof_k2], "roofline_path": path,
         "kernel_ms": {"k1_element": k1_ms, "k2k3_assembly": k2_ms, "phi_reduce": red_ms,

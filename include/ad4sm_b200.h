@@ -150,6 +150,13 @@ int ad4sm_device_view_get(ad4sm_plan* plan, int32_t field, ad4sm_device_view* vi
  * assemble: K2/K3 over ALL batches' staging + the ϕ reduction (HALO slots contribute 0 to ϕ). */
 int ad4sm_eval_elements_device(ad4sm_plan* plan, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev);
 int ad4sm_eval_assemble_device(ad4sm_plan* plan, int32_t mode);
+/* The same two stages for callers whose u / r live in host memory (what makeϕrKt's arguments are, elasticelements.jl:
+ * 356-358): elements_host uploads u (d, hist) and runs the element stage -- on large single-batch plans the upload goes
+ * in node chunks and K1 starts on the element slice whose nodes have arrived; fetch_phi_r_async enqueues the copy of
+ * this rank's ϕ and r to the host as soon as they are final, while the Kt assembly is still running.  Both are
+ * asynchronous: the host buffers (pinned, to be truly asynchronous) must stay untouched until ad4sm_sync. */
+int ad4sm_eval_elements_host(ad4sm_plan* plan, int32_t mode, const double* u, const double* d, double* const* hist);
+int ad4sm_fetch_phi_r_async(ad4sm_plan* plan, int32_t field, double* phi, double* r);
 /* Peer staging (fused compute + communication): instead of a send/recv after the element stage, K1's bulk-store
  * epilogue writes the staged blocks / residuals of interface elements ALSO into the owner rank's HALO slots, through
  * peer-mapped memory over NVLink (CUDA IPC handles), while it computes.  The ranks then only need a barrier between

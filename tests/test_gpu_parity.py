@@ -364,6 +364,28 @@ def test_pipelined_upload_matches_single_copy(monkeypatch):
     assert np.array_equal(h1, h2) and h1.max() > 0.0
 
 
+@pytest.mark.parametrize("declare", [False, True], ids=["element-major", "sorted"])
+def test_two_stage_host_api_matches_makephirkt(declare):
+    """ad4sm_eval_elements_host -> ad4sm_eval_assemble_device -> ad4sm_fetch_phi_r_async (what a partitioned run with
+    host-resident u / r calls per rank) against the one-call host API, on a mesh large enough for the pipelined upload."""
+    import ctypes as C
+    b, u = K.hex_case((41, 41, 41))
+    ref = El.Plan(b, u.shape[1], 3).makeϕrKt(u)
+    plan = El.Plan(b, u.shape[1], 3)
+    if declare:   # a caller that reads no staging rows between the stages gets the destination-sorted path
+        capi.check(capi.lib().ad4sm_export_ranges(plan._h, 0, None, None))
+    r, phi = np.full(u.size, np.nan), np.full(1, np.nan)
+    for _ in range(2):   # twice: the second upload must wait for nothing stale
+        plan.eval_elements_host(capi.MODE_ELASTIC, u)
+        plan.eval_assemble_device(capi.MODE_ELASTIC)
+        plan.fetch_phi_r_async(r, phi)
+        plan.sync()
+        assert phi[0] == ref[0] and np.array_equal(r, ref[1])
+        r[:] = np.nan
+    Kt = plan.fetch_csc()
+    assert np.array_equal(Kt.nzval, ref[2].nzval) and np.array_equal(Kt.rowval, ref[2].rowval)
+
+
 def test_isolated_nodes_and_shuffled_elements():
     """Nodes that no element touches give empty CSC columns and zero residual entries; a shuffled `elems` order changes
     only the summation order (results still match the oracle evaluated in that same order)."""
