@@ -29,7 +29,7 @@ class Batch(C.Structure):
 
 
 BATCH_HALO = 1
-OPT_FUSED, OPT_FUSED_LAG, OPT_SORTED = 1, 2, 3
+OPT_FUSED, OPT_FUSED_LAG, OPT_SORTED, OPT_PEER_PUSH = 1, 2, 3, 4
 INFO_FUSED, INFO_FUSED_STEPS, INFO_SORTED = 1, 2, 3
 
 
@@ -42,7 +42,8 @@ PEER_HANDLE_BYTES = 128
 
 
 class PeerLink(C.Structure):
-    _fields_ = [("first_slot", C.c_int64), ("count", C.c_int64), ("remote_first_slot", C.c_int64), ("peer_handles", C.c_void_p)]
+    _fields_ = [("first_slot", C.c_int64), ("count", C.c_int64), ("remote_first_slot", C.c_int64), ("peer_handles", C.c_void_p),
+                ("remote_first_slot_b", C.c_int64)]
 
 
 class DeviceView(C.Structure):

@@ -75,6 +75,19 @@ struct ad4sm_plan {
   long long h2d_node[H2D_MAX + 1] = {0, 0, 0, 0, 0};  // slice s needs the nodes below h2d_node[s + 1]
   cudaEvent_t ev_h2d[H2D_MAX] = {nullptr, nullptr, nullptr, nullptr}, ev_start = nullptr;
   bool h2d_active = false;        // set by eval_host around the evaluation
+  // peer push (AD4SM_OPT_PEER_PUSH): export ranges leave by copy-engine P2P copies into double-buffered HALO rows
+  bool push_opt = false;          // option set: the next ad4sm_peer_attach builds push links
+  bool push_mode = false;         // links attached in push mode (a rank may have none of its own and still receive)
+  int n_push = 0;
+  struct PushLink {
+    long long first, count;       // local slots
+    long long remote[2];          // first row in the peer's staging, per receive buffer
+    double *ke, *re;              // peer staging bases (IPC-mapped)
+  } push[AD4SM_MAX_PEER_LINKS];
+  long long push_end = 0;         // elements [0, push_end) cover every pushed range: K1 runs them first
+  int send_parity = 0, recv_parity = 0;
+  long long n_halo = 0;           // HALO slots = rows of one receive buffer
+  cudaEvent_t ev_exports = nullptr, ev_pushed = nullptr;
   int N = 0, D = 0, dpn = 0;
   long long n_nodes = 0, ne = 0, n_blocks = 0, n_gp = 0;
   bool has_cp = false;
@@ -210,6 +223,8 @@ void ad4sm_plan_destroy(ad4sm_plan* p) {
   if (p->ev_r_ready) cudaEventDestroy(p->ev_r_ready);
   if (p->ev_copied) cudaEventDestroy(p->ev_copied);
   if (p->ev_start) cudaEventDestroy(p->ev_start);
+  if (p->ev_exports) cudaEventDestroy(p->ev_exports);
+  if (p->ev_pushed) cudaEventDestroy(p->ev_pushed);
   for (cudaEvent_t e : p->ev_h2d)
     if (e) cudaEventDestroy(e);
   if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
@@ -484,8 +499,14 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       h0 += B.n_elems * B.n_gauss;
     }
   }
-  TRY(dev_alloc(p, &p->Ke, (size_t)ne * NPB * D * D));
-  TRY(dev_alloc(p, &p->re, (size_t)ne * N * D));
+  {  // HALO slots get a second set of rows behind the staging (receive buffer B of the peer-push protocol)
+    long long nh = 0;
+    for (int b = 0; b < n_batches; b++)
+      if (batches[b].batch_flags & AD4SM_BATCH_HALO) nh += batches[b].n_elems;
+    p->n_halo = nh;
+  }
+  TRY(dev_alloc(p, &p->Ke, (size_t)(ne + p->n_halo) * NPB * D * D));
+  TRY(dev_alloc(p, &p->re, (size_t)(ne + p->n_halo) * N * D));
   TRY(dev_alloc(p, &p->phie, (size_t)ne));
   CK(cudaMemset(p->phie, 0, sizeof(double) * (size_t)ne));  // HALO slots stay 0: they add nothing to ϕ on this rank
   TRY(dev_alloc(p, &p->partials, (size_t)phi_reduce_partials()));
@@ -732,6 +753,8 @@ static AsmArgs asm_args(ad4sm_plan* p, int field) {
   if (k2s_direct < 0) k2s_direct = getenv("AD4SM_K2S_DIRECT") ? atoi(getenv("AD4SM_K2S_DIRECT")) : 0;
   a.k2s_exp = k2s_exp;
   a.k2s_direct = k2s_direct;
+  a.halo_adj0 = (unsigned long long)p->n_own_sorted * p->N;
+  a.halo_adj_shift = (p->push_mode && p->recv_parity) ? (unsigned long long)p->n_halo * p->N : 0ull;
   return a;
 }
 
@@ -842,6 +865,8 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
   const bool fuse2 = internal && sorted_ok && p->fuse_allowed && p->batch_rec != nullptr;  // K1 + K2s in one kernel
   const bool fuse = internal && !fuse2 && kmode_ok && p->fz.enabled && p->fuse_allowed;   // K1 + K2 + K3 in one kernel
   const bool sorted = sorted_ok && !fuse;
+  if (p->push_mode && !internal && !sorted)
+    return fail(AD4SM_ESTATE, "peer push is set up for Kt evaluations on the destination-sorted path only (modes 0 and 1)");
   p->fused_mode_last = fuse2 ? 2 : (fuse ? 1 : 0);
   p->fused_last = fuse;
   p->sorted_last = sorted;
@@ -892,22 +917,57 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
       a.fz.sb_ptr = p->sb_ptr;
       a.as = asm_args(p, AD4SM_FIELD_U);
     }
-    if (p->h2d_active && !fuse && !fuse2) {  // host API: one launch per element slice, each after its chunk of u
-      for (int c = 0; c < p->n_h2d; c++) {
-        const long long e0 = p->h2d_elem[c], e1 = p->h2d_elem[c + 1];
-        CK(cudaStreamWaitEvent(p->stream, p->ev_h2d[c], 0));
-        if (e1 <= e0) continue;
-        K1Args as = a;
-        as.ne = e1 - e0;
-        as.slot0 = a.slot0 + e0;
-        as.nodes = a.nodes + e0 * a.N;
-        as.gradN = a.gradN + e0 * (long long)(a.D * a.P * a.N);
-        as.wgt = a.wgt + e0 * a.P;
-        if (a.Nval) as.Nval = a.Nval + e0 * (long long)(a.P * a.N);
-        if (a.hist) as.hist = a.hist + e0 * (long long)(a.P * 2);
-        cudaError_t e = launch_k1(as, kmode, p->stream);
-        if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("K1 launch: ") + cudaGetErrorString(e));
-        launches++;
+    // Sub-launches over element slices of the batch: (i) host API -- slice c starts after chunk c of u has arrived;
+    // (ii) peer push -- the slices covering the pushed ranges run first, then the copy engine ships them while the
+    // rest of K1 runs.
+    const bool push = p->push_mode && !internal && sorted && b.k.slot0 == 0;
+    if ((p->h2d_active || push) && !fuse && !fuse2) {
+      long long cut[ad4sm_plan::H2D_MAX + 3];
+      int nc = 0;
+      cut[nc++] = 0;
+      if (p->h2d_active)
+        for (int c = 1; c < p->n_h2d; c++) cut[nc++] = p->h2d_elem[c];
+      if (push && p->push_end > 0 && p->push_end < a.ne) cut[nc++] = p->push_end;
+      cut[nc++] = a.ne;
+      std::sort(cut, cut + nc);
+      bool pushed = !push;
+      for (int k = 0; k + 1 < nc; k++) {
+        const long long e0 = cut[k], e1 = cut[k + 1];
+        if (p->h2d_active)
+          for (int c = 0; c < p->n_h2d; c++)
+            if (p->h2d_elem[c] < e1) CK(cudaStreamWaitEvent(p->stream, p->ev_h2d[c], 0));  // every chunk the slice may touch
+        if (e1 > e0) {
+          K1Args as = a;
+          as.ne = e1 - e0;
+          as.slot0 = a.slot0 + e0;
+          as.nodes = a.nodes + e0 * a.N;
+          as.gradN = a.gradN + e0 * (long long)(a.D * a.P * a.N);
+          as.wgt = a.wgt + e0 * a.P;
+          if (a.Nval) as.Nval = a.Nval + e0 * (long long)(a.P * a.N);
+          if (a.hist) as.hist = a.hist + e0 * (long long)(a.P * 2);
+          cudaError_t e = launch_k1(as, kmode, p->stream);
+          if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("K1 launch: ") + cudaGetErrorString(e));
+          launches++;
+        }
+        if (!pushed && e1 >= p->push_end) {  // the pushed ranges are staged: ship them on the copy stream
+          pushed = true;
+          const long long kw = (long long)n_pair_blocks(p->N) * p->D * p->D, rw = (long long)p->N * p->D;
+          CK(cudaEventRecord(p->ev_exports, p->stream));
+          CK(cudaStreamWaitEvent(p->copy_stream, p->ev_exports, 0));
+          for (int x = 0; x < p->n_push; x++) {
+            const ad4sm_plan::PushLink& L = p->push[x];
+            const long long row = L.remote[p->send_parity];
+            CK(cudaMemcpyAsync(L.ke + row * kw, p->Ke + L.first * kw, sizeof(double) * L.count * kw, cudaMemcpyDeviceToDevice,
+                               p->copy_stream));
+            CK(cudaMemcpyAsync(L.re + row * rw, p->re + L.first * rw, sizeof(double) * L.count * rw, cudaMemcpyDeviceToDevice,
+                               p->copy_stream));
+          }
+          CK(cudaEventRecord(p->ev_pushed, p->copy_stream));
+        }
+      }
+      if (push) {
+        CK(cudaStreamWaitEvent(p->stream, p->ev_pushed, 0));  // what follows on the stream (the barrier) sees the pushes done
+        p->send_parity ^= 1;
       }
       continue;
     }
@@ -938,8 +998,11 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   CK(cudaEventRecord(p->ev_r_ready, p->stream));
   if (!p->fused_last && p->fused_mode_last != 2 && want_K) {
     if (p->sorted_last) {
-      if (p->n_own_sorted < p->ne)
-        CK(launch_halo_scatter(p->Ke, p->cpos, p->C, p->n_own_sorted, p->ne - p->n_own_sorted, n_pair_blocks(p->N), p->stream));
+      if (p->n_own_sorted < p->ne) {
+        const long long kw = (long long)n_pair_blocks(p->N) * p->D * p->D;
+        const double* rows = p->Ke + ((p->push_mode && p->recv_parity) ? p->n_halo * kw : 0);  // receive buffer in use (peer push)
+        CK(launch_halo_scatter(rows, p->cpos, p->C, p->n_own_sorted, p->ne - p->n_own_sorted, n_pair_blocks(p->N), p->stream));
+      }
       CK(launch_k2s(asm_args(p, field), p->stream));
     }
     else CK(launch_k2(asm_args(p, field), p->stream));
@@ -952,6 +1015,7 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   }
   p->ev_cur = nullptr;
   p->elements_mode = -1;
+  if (p->push_mode) p->recv_parity ^= 1;  // the next evaluation's pushes land in the other receive buffer
   FieldOut& f = p->field[field];
   f.evaluated = true;
   f.have_K = want_K;
@@ -990,6 +1054,7 @@ int ad4sm_set_option(ad4sm_plan* p, int32_t option, int64_t value) {
   switch (option) {
     case AD4SM_OPT_FUSED: p->fuse_allowed = value != 0; return AD4SM_OK;
     case AD4SM_OPT_SORTED: p->sorted_on = value != 0; return AD4SM_OK;
+    case AD4SM_OPT_PEER_PUSH: p->push_opt = value != 0; return AD4SM_OK;
     case AD4SM_OPT_FUSED_LAG:
       if (value < 1 || value > 64) return fail(AD4SM_EINVAL, "lag must be in 1..64");
       p->fz.lag = (int)value;
@@ -1024,6 +1089,43 @@ int ad4sm_peer_attach(ad4sm_plan* p, int32_t n_links, const ad4sm_peer_link* lin
   CK(cudaSetDevice(p->device));
   const long long kw = (long long)n_pair_blocks(p->N) * p->D * p->D, rw = (long long)p->N * p->D;
   p->n_xr = 0;
+  p->n_push = 0;
+  p->push_mode = false;
+  if (p->push_opt) {  // copy-engine pushes of locally materialised ranges (header: AD4SM_OPT_PEER_PUSH)
+    if (!p->sorted_built) return fail(AD4SM_ESTATE, "AD4SM_OPT_PEER_PUSH needs a plan with destination-sorted staging");
+    if (!p->ev_exports) {
+      CK(cudaEventCreateWithFlags(&p->ev_exports, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&p->ev_pushed, cudaEventDisableTiming));
+    }
+    long long end = 0;
+    for (int i = 0; i < n_links; i++) {
+      const ad4sm_peer_link& L = links[i];
+      if (L.first_slot < 0 || L.count <= 0 || L.first_slot + L.count > p->n_own_sorted || !L.peer_handles || L.remote_first_slot_b <= L.remote_first_slot)
+        return fail(AD4SM_EINVAL, "peer link range outside the plan's own elements");
+      cudaIpcMemHandle_t h[2];
+      memcpy(h, L.peer_handles, sizeof(h));
+      void *ke = nullptr, *re = nullptr;
+      CK(cudaIpcOpenMemHandle(&ke, h[0], cudaIpcMemLazyEnablePeerAccess));
+      p->ipc_open.push_back(ke);
+      CK(cudaIpcOpenMemHandle(&re, h[1], cudaIpcMemLazyEnablePeerAccess));
+      p->ipc_open.push_back(re);
+      p->push[i] = {L.first_slot, L.count, {L.remote_first_slot, L.remote_first_slot_b}, (double*)ke, (double*)re};
+      // the range is materialised element-major in local memory by K1 (like ad4sm_export_ranges)
+      p->xr[i].first = L.first_slot;
+      p->xr[i].count = L.count;
+      p->xr[i].ke = p->Ke + L.first_slot * kw;
+      p->xr[i].re = p->re + L.first_slot * rw;
+      end = std::max<long long>(end, L.first_slot + L.count);
+    }
+    p->push_mode = true;
+    p->n_push = n_links;
+    p->n_xr = n_links;
+    p->n_xr_local = n_links;
+    p->push_end = std::min<long long>(p->n_own_sorted, (end + 31) & ~31ll);
+    p->send_parity = p->recv_parity = 0;
+    p->dist_aware = true;
+    return AD4SM_OK;
+  }
   for (int i = 0; i < n_links; i++) {
     const ad4sm_peer_link& L = links[i];
     if (L.first_slot < 0 || L.count <= 0 || L.first_slot + L.count > p->ne || !L.peer_handles)

@@ -34,6 +34,8 @@ struct AsmArgs {
   int k2s_direct;               // K2s with per-thread loads instead of the TMA-staged reads (AD4SM_K2S_DIRECT=1)
   int k2s_exp;                  // TIMING EXPERIMENT ONLY (AD4SM_EXP_K2S): 1 K2s leaves the lower triangle unwritten, 2 writes nothing
   const double* C;              // [ne*NPB][CBLK] contribution blocks, canonical orientation (row node <= col node)
+  // peer push (double-buffered HALO rows): adj entries >= halo_adj0 read their residual row halo_adj_shift entries later
+  unsigned long long halo_adj0, halo_adj_shift;
 };
 constexpr int CBLK3 = 10;       // doubles per 3x3 contribution block: 9 + 1 pad = 80 B, 16-byte aligned
 

@@ -230,7 +230,9 @@ template <bool CG> __device__ __forceinline__ void assemble_r_entry(const AsmArg
   if (j < a.DB) {
     const unsigned s0 = __ldg(a.adj_ptr + i), s1 = __ldg(a.adj_ptr + i + 1);
     for (unsigned s = s0; s < s1; s++) {
-      const double* p = a.re + (long long)__ldg(a.adj + s) * a.DB + j;
+      unsigned long long v = __ldg(a.adj + s);
+      if (v >= a.halo_adj0) v += a.halo_adj_shift;  // HALO rows of the receive buffer in use (peer push)
+      const double* p = a.re + v * a.DB + j;
       acc += CG ? __ldcg(p) : *p;
     }
   }

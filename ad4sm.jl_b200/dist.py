@@ -118,6 +118,7 @@ class GpuBackend:
         self.plan = El.Plan(batches, part.n_local_nodes, dofs_per_node, device=device, **plan_opts)
         self.n_own = own_batch.ne
         self.peer = False
+        self.push = False
         self._declare_exports(part)
         field_id = capi.FIELD_D if self.mode == capi.MODE_PF_D else capi.FIELD_U
         v = self.plan.staging_view(field_id)
@@ -143,11 +144,13 @@ class GpuBackend:
     def set_stream(self, stream):
         self.plan.set_stream(stream.cuda_stream)
 
-    def enable_peer_staging(self, part, dist=None):
-        """Fused compute + communication: K1's bulk-store epilogue writes the staging of interface elements straight
-        into the owner rank's HALO slots through peer-mapped memory (CUDA IPC over NVLink), so the exchange step
-        shrinks to a barrier.  Collective: every rank must call it; returns True only if ALL ranks attached their
-        links (otherwise everybody keeps the NCCL send/recv exchange)."""
+    def enable_peer_staging(self, part, dist=None, push=True):
+        """Interface rows through peer-mapped memory (CUDA IPC over NVLink) instead of NCCL send/recv; the exchange step
+        shrinks to a barrier.  push=True (default): K1 stays on the destination-sorted path, evaluates the interface
+        elements first and the COPY ENGINE pushes their rows into the owner's (double-buffered) HALO rows while the rest
+        of K1 runs.  push=False: K1's bulk-store epilogue writes them into the owner's memory itself (element-major
+        path).  Collective: every rank must call it; returns True only if ALL ranks attached their links (otherwise
+        everybody keeps the NCCL send/recv exchange)."""
         import ctypes as C
         import torch
         import torch.distributed as D
@@ -158,9 +161,10 @@ class GpuBackend:
         try:
             h = (C.c_ubyte * capi.PEER_HANDLE_BYTES)()
             capi.check(L.ad4sm_peer_export(self.plan._h, h))
-            mine = {"handles": bytes(h), "n_own": self.n_own, "recv": dict(part.recv)}
+            n_slots = int(self.plan.staging_view(self.field_id).n_slots)
+            mine = {"handles": bytes(h), "n_own": self.n_own, "n_slots": n_slots, "recv": dict(part.recv)}
         except Exception:
-            ok, mine = 0, {"handles": b"", "n_own": self.n_own, "recv": dict(part.recv)}
+            ok, mine = 0, {"handles": b"", "n_own": self.n_own, "n_slots": 0, "recv": dict(part.recv)}
         everyone = [None] * part.world
         dist.all_gather_object(everyone, mine)
         if ok:
@@ -173,19 +177,24 @@ class GpuBackend:
                     s, c = everyone[peer]["recv"][part.rank]
                     buf = C.create_string_buffer(everyone[peer]["handles"], capi.PEER_HANDLE_BYTES)
                     keep.append(buf)
-                    links.append(capi.PeerLink(int(ix[0]), len(ix), everyone[peer]["n_own"] + s, C.cast(buf, C.c_void_p)))
+                    links.append(capi.PeerLink(int(ix[0]), len(ix), everyone[peer]["n_own"] + s, C.cast(buf, C.c_void_p),
+                                               everyone[peer]["n_slots"] + s))
                 arr = (capi.PeerLink * max(1, len(links)))(*links)
+                self.plan.set_option(capi.OPT_PEER_PUSH, 1 if push else 0)
                 capi.check(L.ad4sm_peer_attach(self.plan._h, len(links), arr))
             except Exception:
                 ok = 0
         flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         self.peer = bool(int(flag.item()))
-        if self.peer:
+        self.push = self.peer and push
+        if self.peer and not push:
             # peer stores leave through K1's 2.6 KB-per-element bulk copies (TMA), which exist in the element-major
             # staging path; from the sorted epilogue they would be 8-byte stores over NVLink (measured: slower)
             self.plan.set_option(capi.OPT_SORTED, 0)
         if not self.peer:
+            self.plan.set_option(capi.OPT_PEER_PUSH, 0)
+            capi.check(L.ad4sm_peer_attach(self.plan._h, 0, None))   # drop any links this rank did attach
             self._declare_exports(part)   # back to the send/recv exchange of locally materialised rows
         return self.peer
 
@@ -271,11 +280,18 @@ class DistPlan:
         """One evaluation, everything left on the device.  Returns the global ϕ as a 0-d tensor."""
         import torch
         import torch.distributed as D
+        peer = getattr(self.b, "peer", False)
+        if peer and not getattr(self.b, "push", False):
+            # K1 itself writes into the owners' (single-buffered) HALO rows: nobody may start before every rank has
+            # finished assembling the previous evaluation
+            if self._tok is None:
+                self._tok = torch.zeros(1, device="cuda")
+            D.all_reduce(self._tok)
         if host is not None:
             self.b.eval_elements_host(host[0], host[2])
         else:
             self.b.eval_elements(*eval_args)
-        if getattr(self.b, "peer", False):
+        if peer:
             # the interface staging has been written into the owners' HALO slots by K1 itself: only a barrier is left
             if self._tok is None:
                 self._tok = torch.zeros(1, device="cuda")
@@ -363,8 +379,8 @@ class SlabRunner:
         self.dplan = DistPlan(self.backend, self.part)
         self._u_dev = None
         self.peer = False
-        if world > 1 and peer_staging:
-            self.peer = self.backend.enable_peer_staging(self.part)
+        if world > 1 and peer_staging:   # "push" (default for True) or "k1"
+            self.peer = self.backend.enable_peer_staging(self.part, push=(peer_staging != "k1"))
 
     def step_device(self, u_dev):
         return self.dplan.step(u_dev)

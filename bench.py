@@ -181,7 +181,8 @@ def run_ours(args):
         runner = None
     else:
         from ad4sm_b200 import dist as D
-        runner = D.SlabRunner(n, args.nz or n, rank, world, device=local, peer_staging=args.peer_staging, mat=material(args.material))
+        runner = D.SlabRunner(n, args.nz or n, rank, world, device=local, peer_staging=("k1" if args.peer_staging else (False if args.interface == "nccl" else args.interface)),
+                              mat=material(args.material))
         plan, batch, u = runner.plan, runner.batch, runner.u_local
     t_build = time.perf_counter() - t_build0
     ne_local = batch.ne
@@ -310,8 +311,11 @@ def run_ours(args):
         "config": {"workload": f"{'C2' if args.material == 'neohooke' else 'C5'} Hex8 {'NeoHooke' if args.material == 'neohooke' else 'Ogden'} "
                                f"{n}x{n}x{(args.nz or n) * world} ({ne_total} elements), 2x2x2 Gauss, one makeϕrKt per step",
                    "elements_per_gpu": ne_local, "partition": "single GPU" if world == 1 else f"z-slabs over {world} ranks",
-                   "interface": None if world == 1 else ("K1 bulk stores into the owner's staging over NVLink peer memory + barrier"
-                                                         if runner.peer else "NCCL send/recv of staged element blocks"),
+                   "interface": None if world == 1 else (
+                       "copy-engine push of the interface rows into the owner's double-buffered HALO rows over NVLink, overlapped "
+                       "with K1, + barrier" if runner.backend.push else
+                       "K1 bulk stores into the owner's staging over NVLink peer memory + barrier" if runner.peer else
+                       "NCCL send/recv of staged element blocks"),
                    "l2": "working set (∇N 1.5 GB + staging 2.9 GB + Kt 2.0 GB per GPU) >> 126 MB L2; no flush needed",
                    "plan_build_s": t_build},
         "clocks": dict(clk.summary(), note="sampled every 50 ms over the timed region and ~0.4 s more of the same load"),
@@ -344,9 +348,11 @@ def main():
     ap.add_argument("--material", default="neohooke", choices=["neohooke", "ogden"])
     ap.add_argument("--cpu-sample", type=int, default=56, help="edge of the CPU sample block (56 -> 175616 elements, a few seconds on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--peer-staging", action="store_true",
-                    help="multi-GPU: K1 writes interface staging into the owner's memory over NVLink (CUDA IPC) instead of the "
-                         "NCCL send/recv exchange (default: NCCL + destination-sorted staging, measured faster)")
+    ap.add_argument("--interface", default="push", choices=["nccl", "push", "k1"],
+                    help="multi-GPU interface transport: nccl = send/recv of the staged rows after K1; push = the copy engine "
+                         "pushes them into the owner's HALO rows over NVLink (CUDA IPC) while K1 still runs; k1 = K1's own "
+                         "bulk stores into the owner's memory (element-major path)")
+    ap.add_argument("--peer-staging", action="store_true", help="alias of --interface k1 (round-1 name)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

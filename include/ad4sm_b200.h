@@ -167,8 +167,17 @@ typedef struct ad4sm_peer_link {
   int64_t count;              /* slots in the range */
   int64_t remote_first_slot;  /* where the range starts in the peer plan's staging (its HALO slots) */
   const void* peer_handles;   /* AD4SM_PEER_HANDLE_BYTES bytes exported by the peer's ad4sm_peer_export */
+  int64_t remote_first_slot_b; /* AD4SM_OPT_PEER_PUSH: where the range starts in the peer's SECOND receive buffer, which
+                                * lies behind its staging: peer n_slots + (remote_first_slot - peer's first HALO slot);
+                                * ignored otherwise */
 } ad4sm_peer_link;
 #define AD4SM_MAX_PEER_LINKS 4
+/* AD4SM_OPT_PEER_PUSH (set before ad4sm_peer_attach; sorted-staging plans only): K1 keeps the destination-sorted fast
+ * path, evaluates the linked ranges FIRST (element-major copies in local memory) and the copy engine then pushes them
+ * into the peer's HALO rows over NVLink while the rest of K1 runs -- no SM is spent on communication and no rank waits
+ * for its neighbour's K1.  The HALO rows are double-buffered (a push for evaluation n+1 can never overwrite rows a slow
+ * peer still reads for evaluation n), alternating with every ad4sm_eval_elements_* / ad4sm_eval_assemble_device pair,
+ * so all ranks must issue those calls in lockstep, separated by a barrier between the two stages. */
 int ad4sm_peer_export(ad4sm_plan* plan, void* handles_out /* AD4SM_PEER_HANDLE_BYTES */);
 int ad4sm_peer_attach(ad4sm_plan* plan, int32_t n_links, const ad4sm_peer_link* links);
 /* Without peer memory: the slot ranges whose element-major staging (Ke_dev / re_dev of ad4sm_staging_view_get) the
@@ -195,6 +204,7 @@ int ad4sm_sync(ad4sm_plan* plan);
 #define AD4SM_OPT_FUSED 1
 #define AD4SM_OPT_FUSED_LAG 2     /* steps between staging a group and assembling the rows it completes */
 #define AD4SM_OPT_SORTED 3        /* destination-sorted staging + streaming assembly (K2s); default on where available */
+#define AD4SM_OPT_PEER_PUSH 4    /* 1: ad4sm_peer_attach sets up copy-engine pushes instead of K1 peer stores (see there) */
 #define AD4SM_INFO_FUSED 1
 #define AD4SM_INFO_FUSED_STEPS 2
 #define AD4SM_INFO_SORTED 3       /* 0 = not available for this plan, 1 = available but off, 2 = on */

@@ -1,7 +1,8 @@
 """Real multi-GPU checks (need >= 2 GPUs; the driver's single-GPU `-m gpu` run skips them, `gpurun --gpus 2` runs them).
-Two NCCL ranks evaluate a partitioned Hex8 mesh with (a) the NCCL send/recv interface exchange and (b) peer staging
-(K1 writes interface elements' staging into the owner's HALO slots over NVLink); owned rows of both must be bitwise
-equal to a single-GPU evaluation of the whole mesh."""
+Two NCCL ranks evaluate a partitioned Hex8 mesh with (a) the NCCL send/recv interface exchange, (b) peer push (the copy
+engine ships the interface rows into the owner's double-buffered HALO rows while K1 runs) and (c) K1 peer stores (K1
+writes them into the owner's memory itself); owned rows of all must be bitwise equal to a single-GPU evaluation of the
+whole mesh, after several evaluations with changing inputs."""
 import os
 import socket
 
@@ -32,21 +33,25 @@ def _worker(rank, world, port, out):
         u = mesh.random_u(len(coords), 3, 1 / 16, seed=32)
         p = AD.build_partition(conn, AD.contiguous_elem_ranks(len(conn), world), rank, world)
         res = {}
-        for mode in ("nccl", "peer"):
+        for mode in ("nccl", "push", "peerk1"):
             own = El.ElemBatch("CE", 3, p.local_conn(conn[p.own_elems]), b.gradN[p.own_elems], b.wgt[p.own_elems], b.mat)
             be = AD.GpuBackend(own, p.local_conn(conn[p.halo_elems]), p, 3, device=rank)
             stream = torch.cuda.Stream()
             torch.cuda.set_stream(stream)
             be.set_stream(stream)
-            if mode == "peer":
-                assert be.enable_peer_staging(p), "peer staging (CUDA IPC) not available"
+            if mode != "nccl":
+                assert be.enable_peer_staging(p, push=(mode == "push")), "peer staging (CUDA IPC) not available"
+                assert be.push == (mode == "push")
             dp = AD.DistPlan(be, p)
             ul = torch.from_numpy(np.ascontiguousarray(u[:, p.local_nodes - 1].T)).cuda()
-            for _ in range(2):
-                phi = dp.step(ul)
-            torch.cuda.synchronize()
-            Kt = be.plan.fetch_csc()
-            res[mode] = (float(phi.item()), be.r_tensor().cpu().numpy(), Kt)
+            # evaluations with other inputs first: a stale or wrong-parity HALO row would show in the last one.  The push
+            # mode alternates two receive buffers: 2 evaluations end on buffer B, 5 on buffer A.
+            for tag, seq in ((mode, (0.5, 1.0)), (mode + "_b", (0.25, 0.5, 1.0))):
+                for f in seq:
+                    phi = dp.step(ul * f)
+                torch.cuda.synchronize()
+                Kt = be.plan.fetch_csc()
+                res[tag] = (float(phi.item()), be.r_tensor().cpu().numpy(), Kt)
         np.savez(os.path.join(out, f"r{rank}.npz"), local_nodes=p.local_nodes, owned=p.owned,
                  **{f"{m}_{k}": v for m, (ph, r, Kt) in res.items()
                     for k, v in dict(phi=ph, r=r, cp=Kt.colptr, rv=Kt.rowval, nz=Kt.nzval).items()})
@@ -69,13 +74,13 @@ def test_two_gpu_partition_nccl_and_peer_staging(tmp_path):
     for g in range(world):
         z = np.load(tmp_path / f"r{g}.npz")
         ln = z["local_nodes"]
-        for mode in ("nccl", "peer"):
+        for mode in ("nccl", "nccl_b", "push", "push_b", "peerk1", "peerk1_b"):
             assert abs(float(z[f"{mode}_phi"]) - phi0) <= 1e-13 * abs(phi0)
             cp, rv, nz, r = z[f"{mode}_cp"], z[f"{mode}_rv"], z[f"{mode}_nz"], z[f"{mode}_r"]
             for loc in np.where(z["owned"])[0]:
                 gn = ln[loc]
                 for c in range(3):
                     lc, gc = loc * 3 + c, (gn - 1) * 3 + c
-                    assert r[lc] == r0[gc]
+                    assert r[lc] == r0[gc], (mode, g, gn)
                     ls, gs = slice(cp[lc] - 1, cp[lc + 1] - 1), slice(Kt0.colptr[gc] - 1, Kt0.colptr[gc + 1] - 1)
                     assert np.array_equal(nz[ls], Kt0.nzval[gs]), (mode, g, gn)
