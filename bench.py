@@ -223,17 +223,17 @@ def run_ours(args):
         ms_total = e0.elapsed_time(e1)
         prof_ms, prof_n = plan.profile_read()
         plan.profile_enable(False)
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / args.steps
         # the timed region above lasts tens of ms: keep the same load running (untimed) for ~0.4 s so that the 50 ms
-        # clock sampler records the clocks / throttle reasons this workload runs at
-        t_end = time.perf_counter() + 0.4
-        while time.perf_counter() < t_end:
+        # clock sampler records the clocks / throttle reasons this workload runs at.  The step count comes from the
+        # all-reduced time, so every rank runs the same number of (collective) steps.
+        for _ in range(max(1, int(400.0 / max(ms_step, 1e-3) / 5))):
             for _ in range(5):
                 step_device()
             torch.cuda.synchronize()
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
     value = ne_total / (ms_step * 1e-3)
 
     # ---- end-to-end through the reference-facing call with host buffers (e2e) -------------------
