@@ -364,12 +364,12 @@ def test_pipelined_upload_matches_single_copy(monkeypatch):
     assert np.array_equal(h1, h2) and h1.max() > 0.0
 
 
+@pytest.mark.parametrize("n", [(41, 41, 41), (6, 5, 4)], ids=["pipelined-upload", "single-copy"])
 @pytest.mark.parametrize("declare", [False, True], ids=["element-major", "sorted"])
-def test_two_stage_host_api_matches_makephirkt(declare):
+def test_two_stage_host_api_matches_makephirkt(declare, n):
     """ad4sm_eval_elements_host -> ad4sm_eval_assemble_device -> ad4sm_fetch_phi_r_async (what a partitioned run with
     host-resident u / r calls per rank) against the one-call host API, on a mesh large enough for the pipelined upload."""
-    import ctypes as C
-    b, u = K.hex_case((41, 41, 41))
+    b, u = K.hex_case(n)
     ref = El.Plan(b, u.shape[1], 3).makeϕrKt(u)
     plan = El.Plan(b, u.shape[1], 3)
     if declare:   # a caller that reads no staging rows between the stages gets the destination-sorted path
