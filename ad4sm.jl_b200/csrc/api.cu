@@ -429,13 +429,13 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     const bool want = !env || atoi(env) != 0;
     int n_ord = 0;
     for (int b = 0; b < n_batches; b++) n_ord += !(batches[b].batch_flags & AD4SM_BATCH_HALO);
-    const long long ne = (n_ord == 1 && !(batches[0].batch_flags & AD4SM_BATCH_HALO)) ? batches[0].n_elems : 0;  // shadows: own elements
-    if (want && ne >= 65536) {
+    const long long ne_ord = (n_ord == 1 && !(batches[0].batch_flags & AD4SM_BATCH_HALO)) ? batches[0].n_elems : 0;
+    if (want && ne_ord >= 65536) {
       const long long frac16[ad4sm_plan::H2D_MAX] = {1, 4, 8, 16};
       long long mx = 0, e = 0;
       bool ok = true;
       for (int c = 0; c < ad4sm_plan::H2D_MAX; c++) {
-        const long long e1 = c == ad4sm_plan::H2D_MAX - 1 ? ne : ((ne * frac16[c] / 16) & ~31ll);
+        const long long e1 = c == ad4sm_plan::H2D_MAX - 1 ? ne_ord : ((ne_ord * frac16[c] / 16) & ~31ll);
         for (; e < e1; e++)
           for (int a = 0; a < N; a++) mx = std::max<long long>(mx, nodes0[(size_t)e * N + a] + 1);
         p->h2d_elem[c + 1] = e1;
