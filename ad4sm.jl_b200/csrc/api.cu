@@ -85,7 +85,8 @@ struct ad4sm_plan {
     double *ke, *re;              // peer staging bases (IPC-mapped)
   } push[AD4SM_MAX_PEER_LINKS];
   long long push_end = 0;         // elements [0, push_end) cover every pushed range: K1 runs them first
-  int send_parity = 0, recv_parity = 0;
+  int parity = 0;                 // receive buffer of the current evaluation (same on every rank: they evaluate in lockstep)
+  bool push_pending = false;      // the element stage of the current evaluation pushed: its assembly reads buffer `parity`
   long long n_halo = 0;           // HALO slots = rows of one receive buffer
   cudaEvent_t ev_exports = nullptr, ev_pushed = nullptr;
   int N = 0, D = 0, dpn = 0;
@@ -754,7 +755,7 @@ static AsmArgs asm_args(ad4sm_plan* p, int field) {
   a.k2s_exp = k2s_exp;
   a.k2s_direct = k2s_direct;
   a.halo_adj0 = (unsigned long long)p->n_own_sorted * p->N;
-  a.halo_adj_shift = (p->push_mode && p->recv_parity) ? (unsigned long long)p->n_halo * p->N : 0ull;
+  a.halo_adj_shift = (p->push_pending && p->parity) ? (unsigned long long)p->n_halo * p->N : 0ull;
   return a;
 }
 
@@ -956,7 +957,7 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
           CK(cudaStreamWaitEvent(p->copy_stream, p->ev_exports, 0));
           for (int x = 0; x < p->n_push; x++) {
             const ad4sm_plan::PushLink& L = p->push[x];
-            const long long row = L.remote[p->send_parity];
+            const long long row = L.remote[p->parity];
             CK(cudaMemcpyAsync(L.ke + row * kw, p->Ke + L.first * kw, sizeof(double) * L.count * kw, cudaMemcpyDeviceToDevice,
                                p->copy_stream));
             CK(cudaMemcpyAsync(L.re + row * rw, p->re + L.first * rw, sizeof(double) * L.count * rw, cudaMemcpyDeviceToDevice,
@@ -967,7 +968,7 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
       }
       if (push) {
         CK(cudaStreamWaitEvent(p->stream, p->ev_pushed, 0));  // what follows on the stream (the barrier) sees the pushes done
-        p->send_parity ^= 1;
+        p->push_pending = true;
       }
       continue;
     }
@@ -1000,7 +1001,7 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
     if (p->sorted_last) {
       if (p->n_own_sorted < p->ne) {
         const long long kw = (long long)n_pair_blocks(p->N) * p->D * p->D;
-        const double* rows = p->Ke + ((p->push_mode && p->recv_parity) ? p->n_halo * kw : 0);  // receive buffer in use (peer push)
+        const double* rows = p->Ke + ((p->push_pending && p->parity) ? p->n_halo * kw : 0);  // receive buffer in use (peer push)
         CK(launch_halo_scatter(rows, p->cpos, p->C, p->n_own_sorted, p->ne - p->n_own_sorted, n_pair_blocks(p->N), p->stream));
       }
       CK(launch_k2s(asm_args(p, field), p->stream));
@@ -1015,7 +1016,10 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   }
   p->ev_cur = nullptr;
   p->elements_mode = -1;
-  if (p->push_mode) p->recv_parity ^= 1;  // the next evaluation's pushes land in the other receive buffer
+  if (p->push_pending) {  // the next evaluation's pushes land in the other receive buffer
+    p->parity ^= 1;
+    p->push_pending = false;
+  }
   FieldOut& f = p->field[field];
   f.evaluated = true;
   f.have_K = want_K;
@@ -1122,7 +1126,8 @@ int ad4sm_peer_attach(ad4sm_plan* p, int32_t n_links, const ad4sm_peer_link* lin
     p->n_xr = n_links;
     p->n_xr_local = n_links;
     p->push_end = std::min<long long>(p->n_own_sorted, (end + 31) & ~31ll);
-    p->send_parity = p->recv_parity = 0;
+    p->parity = 0;
+    p->push_pending = false;
     p->dist_aware = true;
     return AD4SM_OK;
   }
