@@ -526,6 +526,20 @@ class Plan:
                                                C.byref(nnz)))
         return phi.value, r, (self._fetch(u.size, nnz.value) if fetch else None)
 
+    def assemble_duals(self, Phi, fetch=True):
+        """makeϕrKt(Φ, elems, u) (elements.toolkit.jl:169-203): assemble caller-supplied element duals.  `Phi` is a
+        C-contiguous float64 array [ne][stride >= 1+n+m] whose rows are (v | g[n] | packed upper-triangle h[m]) -- the
+        memory of Julia's Vector{D2{n,m,Float64}} -- in `elems` order."""
+        Phi = np.ascontiguousarray(Phi, dtype=np.float64)
+        if Phi.ndim != 2 or Phi.shape[0] != sum(b.ne for b in self.batches):
+            raise ValueError("Phi must have one row per element")
+        phi, nnz = C.c_double(), C.c_int64()
+        ndof = self.n_nodes * self.dpn
+        r = np.empty(ndof)
+        capi.check(self._L.ad4sm_assemble_duals(self._h, C.c_void_p(Phi.ctypes.data), Phi.shape[1], C.byref(phi),
+                                                C.c_void_p(r.ctypes.data), C.byref(nnz)))
+        return phi.value, r, (self._fetch(ndof, nnz.value) if fetch else None)
+
     def makeϕr(self, u):
         u = self._u(u)
         phi = C.c_double()
@@ -697,6 +711,25 @@ def makeϕr(elems, u, **opts):
     return _plan_for(elems, u, **opts).makeϕr(u)
 
 
+def assemble_ϕrKt(Φ, elems, u, **opts):
+    """The reference's 3-argument `makeϕrKt(Φ, elems, u)` (elements.toolkit.jl:169-203; what `Solvers.solvestep!` calls,
+    solvers.jl:213-216): Φ = element duals, rows (v | g | packed h) like a Julia Vector{D2{n,m,Float64}}; only the
+    assembly runs on the device."""
+    return _plan_for(elems, u, **opts).assemble_duals(Φ)
+
+
+def pack_duals(val, grad, hess):
+    """(val[ne], grad[ne][n], hess[ne][n][n]) -> Φ rows (v | g | h packed upper triangle, entry (i<=j) at j(j+1)/2+i,
+    0-based: adiff.jl:26,84)."""
+    val, grad, hess = np.asarray(val), np.asarray(grad), np.asarray(hess)
+    n = grad.shape[1]
+    jj, ii = np.triu_indices(n)          # pairs (ii >= jj) ...
+    order = np.lexsort((jj, ii))          # ... sorted by column ii, then row jj: index ii(ii+1)/2 + jj
+    rows, cols = jj[order], ii[order]
+    return np.ascontiguousarray(np.concatenate([val[:, None], grad, hess[:, rows, cols]], axis=1))
+
+
 make_phi_r_Kt = makeϕrKt
 make_phi_r_Kt_d = makeϕrKt_d
 make_phi_r = makeϕr
+assemble_phi_r_Kt = assemble_ϕrKt

@@ -75,6 +75,7 @@ struct ad4sm_plan {
   long long h2d_node[H2D_MAX + 1] = {0, 0, 0, 0, 0};  // slice s needs the nodes below h2d_node[s + 1]
   cudaEvent_t ev_h2d[H2D_MAX] = {nullptr, nullptr, nullptr, nullptr}, ev_start = nullptr;
   bool h2d_active = false;        // set by eval_host around the evaluation
+  long long* key_dev = nullptr;   // [ne] position of each slot in `elems` (orig_index), nullptr = identity (assembly-only entry)
   // peer push (AD4SM_OPT_PEER_PUSH): export ranges leave by copy-engine P2P copies into double-buffered HALO rows
   bool push_opt = false;          // option set: the next ad4sm_peer_attach builds push links
   bool push_mode = false;         // links attached in push mode (a rank may have none of its own and still receive)
@@ -455,6 +456,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       }
     }
   }
+  if (keyed) TRY(dev_upload(p, &p->key_dev, key.data(), key.size()));
   TRY(dev_upload(p, &p->blk_row, blk_row.data(), blk_row.size()));
   TRY(dev_upload(p, &p->nbr_ptr, nbr_ptr.data(), nbr_ptr.size()));
   TRY(dev_upload(p, &p->nbr, nbr.data(), nbr.size()));
@@ -1315,6 +1317,51 @@ int ad4sm_eval_pf_u(ad4sm_plan* p, const double* u, const double* d, double* phi
 int ad4sm_eval_pf_d(ad4sm_plan* p, const double* u, const double* d, double* const* hist, double* phi, double* r,
                     int64_t* nnz_out) {
   return eval_host(p, MODE_PF_D, u, d, hist, phi, r, nnz_out);
+}
+
+// makeϕrKt(Φ, elems, u) (elements.toolkit.jl:169-203): assembly of caller-supplied element duals
+int ad4sm_assemble_duals(ad4sm_plan* p, const void* Phi, int64_t stride, double* phi, double* r, int64_t* nnz_out) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (!Phi) return fail(AD4SM_EINVAL, "Phi is NULL");
+  const long long n = (long long)p->N * p->D, m = n * (n + 1) / 2;
+  if (p->dpn != p->D) return fail(AD4SM_EINVAL, "ad4sm_assemble_duals needs size(u,1) == element dimension");
+  if (stride < 1 + n + m) return fail(AD4SM_EINVAL, "stride smaller than 1 + n + n(n+1)/2 doubles (D2{n,m,Float64})");
+  for (const BatchPlan& b : p->batches)
+    if (b.halo) return fail(AD4SM_EINVAL, "ad4sm_assemble_duals on a plan with HALO batches");
+  CK(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  double* dPhi = nullptr;
+  const size_t bytes = sizeof(double) * (size_t)p->ne * (size_t)stride;
+  cudaError_t e = cudaMalloc(&dPhi, bytes);
+  if (e != cudaSuccess) return fail(AD4SM_ENOMEM, std::string("cudaMalloc of the element duals: ") + cudaGetErrorString(e));
+  auto done = [&](int rc) {
+    cudaStreamSynchronize(s);
+    cudaFree(dPhi);
+    return rc;
+  };
+  if (cudaMemcpyAsync(dPhi, Phi, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return done(fail(AD4SM_ENODEV, "upload of the element duals failed"));
+  if (launch_duals_to_staging(dPhi, stride, p->key_dev, p->ne, p->N, p->D, p->Ke, p->re, p->phie, s) != cudaSuccess)
+    return done(fail(AD4SM_ENODEV, "duals_to_staging launch failed"));
+  const bool sorted = p->sorted_built && p->sorted_on;
+  if (sorted && launch_halo_scatter(p->Ke, p->cpos, p->C, 0, p->n_own_sorted, n_pair_blocks(p->N), s) != cudaSuccess)
+    return done(fail(AD4SM_ENODEV, "staging scatter launch failed"));
+  p->ev_cur = nullptr;
+  p->fused_last = false;
+  p->fused_mode_last = 0;
+  p->sorted_last = sorted;
+  p->elements_mode = MODE_ELASTIC;
+  int rc = ad4sm_eval_assemble_device(p, MODE_ELASTIC);
+  if (rc) return done(rc);
+  FieldOut& f = p->field[AD4SM_FIELD_U];
+  unsigned long long nz = 0;
+  rc = download_phi_r(p, AD4SM_FIELD_U, phi, r);
+  if (rc) return done(rc);
+  if (cudaMemcpyAsync(&nz, p->n_zero_dev, sizeof(nz), cudaMemcpyDeviceToHost, s) != cudaSuccess) return done(fail(AD4SM_ENODEV, "copy failed"));
+  if (cudaStreamSynchronize(s) != cudaSuccess) return done(fail(AD4SM_ENODEV, "assembly failed"));
+  cudaFree(dPhi);
+  f.n_zero = (long long)nz;
+  if (nnz_out) *nnz_out = f.nnz - f.n_zero;
+  return AD4SM_OK;
 }
 
 int ad4sm_fetch_csc(ad4sm_plan* p, int64_t* colptr, int64_t* rowval, double* nzval) {

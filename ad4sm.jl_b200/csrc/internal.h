@@ -117,6 +117,10 @@ int phi_reduce_partials();
 cudaError_t launch_phi_reduce(const double* phie, long long n, double* partials, double* phi, cudaStream_t s);
 cudaError_t launch_pattern(const AsmArgs& a, long long* colptr, long long* rowval, cudaStream_t s);
 // exact-zero compaction (dropzeros, elements.toolkit.jl:202); tmp must hold n_dof+1 long longs
+// assembly-only entry: element duals [ne][stride] = (v | g[n] | h[n(n+1)/2] packed upper triangle, column-major) -> the
+// element-major staging (Ke blocks, re, phie); `index`: record of each slot (nullptr = identity)
+cudaError_t launch_duals_to_staging(const double* Phi, long long stride, const long long* index, long long n_slots, int N, int D,
+                                    double* Ke, double* re, double* phie, cudaStream_t s);
 cudaError_t launch_dropzeros(long long n_dof, const long long* colptr, const long long* rowval, const double* nzval,
                              long long* colptr_out, long long* rowval_out, double* nzval_out, void* cub_tmp,
                              size_t cub_tmp_bytes, cudaStream_t s);

@@ -1202,6 +1202,35 @@ cudaError_t launch_halo_scatter(const double* Ke, const unsigned* cpos, double* 
   if (n > 0) halo_scatter_kernel3<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(Ke, cpos, C, slot0, n_slots, NPB);
   return cudaGetLastError();
 }
+// ---- assembly-only entry (makeϕrKt(Φ, elems, u), elements.toolkit.jl:169-203): the caller's element duals -> staging.
+// One thread per (slot, node-pair block): block (q, o) of the cyclic storage holds K((q+o)%N, j),(q, l); the Hessian is
+// adiff's packed upper triangle, entry (i <= j), 0-based, at j(j+1)/2 + i (adiff.jl:26,84), local dof = comp + D*node.
+__global__ void __launch_bounds__(256) duals_to_staging_kernel(const double* Phi, long long stride, const long long* index,
+                                                               long long n_slots, int N, int D, double* Ke, double* re,
+                                                               double* phie) {
+  const int NPB = N * (N + 1) / 2, DD = D * D, n = N * D;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_slots * NPB) return;
+  const long long slot = t / NPB;
+  const int blk = (int)(t - slot * NPB), o = blk / N, q = blk - o * N;
+  const double* rec = Phi + (index ? index[slot] : slot) * stride;
+  const double* h = rec + 1 + n;
+  const int a = (q + o) % N;
+  for (int j = 0; j < D; j++)
+    for (int l = 0; l < D; l++) {
+      const int pr = a * D + j, pc = q * D + l, hi = pr > pc ? pr : pc, lo = pr > pc ? pc : pr;
+      Ke[t * DD + j * D + l] = h[hi * (hi + 1) / 2 + lo];
+    }
+  if (blk < N)  // this thread also moves node blk's gradient entries, thread 0 the value
+    for (int j = 0; j < D; j++) re[slot * n + blk * D + j] = rec[1 + blk * D + j];
+  if (blk == 0) phie[slot] = rec[0];
+}
+cudaError_t launch_duals_to_staging(const double* Phi, long long stride, const long long* index, long long n_slots, int N, int D,
+                                    double* Ke, double* re, double* phie, cudaStream_t s) {
+  const long long n = n_slots * (N * (N + 1) / 2);
+  if (n > 0) duals_to_staging_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(Phi, stride, index, n_slots, N, D, Ke, re, phie);
+  return cudaGetLastError();
+}
 cudaError_t launch_k3(const AsmArgs& a, cudaStream_t s) {
   const long long nr = a.n_nodes * a.dpn;
   if (nr > 0) k3_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(a);

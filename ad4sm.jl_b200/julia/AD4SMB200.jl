@@ -9,6 +9,7 @@
 #
 # Methods re-defined (same signatures and return types as the reference):
 #   Elements.makeϕrKt(elems::AbstractVector{<:AbstractCElem}, u::AbstractMatrix)       src/elasticelements.jl:356-358
+#   Elements.makeϕrKt(Φ::Vector{<:adiff.D2}, elems::Vector, u)                         src/elements.toolkit.jl:169-203
 #   Elements.makeϕrKt(elems::Vector{<:CPElem}, u::Array, d::Array)                     src/phasefieldelements.jl:228-238
 #   Elements.makeϕrKt_d(elems, u, d) / makeϕrKt_d(elems, u, d, ϕmax)                   src/phasefieldelements.jl:239-262
 # `Solvers.solvestep!` builds Φ with a serial comprehension and calls the 3-argument assembly
@@ -19,6 +20,7 @@ module AD4SMB200
 using AD4SM
 using AD4SM.Elements: AbstractCElem, CEElem, CPElem
 using AD4SM.Materials
+using AD4SM: adiff
 using SparseArrays
 
 const lib = get(ENV, "AD4SM_B200_LIB", joinpath(@__DIR__, "..", "lib", "libad4sm_b200.so"))
@@ -118,6 +120,15 @@ function AD4SM.Elements.makeϕrKt(elems::AbstractVector{<:AbstractCElem}, u::Abs
   p = plan_for(elems, u); ϕ = Ref(0.0); nnz = Ref{Int64}(0); r = Vector{Float64}(undef, length(u))
   uc = Matrix{Float64}(u)                                          # dense column-major D x nNodes
   check(ccall((:ad4sm_eval, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ref{Int64}), p.h, uc, ϕ, r, nnz))
+  (ϕ[], r, fetch(p, length(u), nnz[]))
+end
+
+# Assembly only (elements.toolkit.jl:169-203; the method Solvers.solvestep! calls, solvers.jl:213-216): a
+# Vector{D2{N,M,Float64}} is a dense array of (v | g | h) records, passed as it lies in memory.
+function AD4SM.Elements.makeϕrKt(Φ::Vector{adiff.D2{N,M,Float64}}, elems::Vector, u::AbstractMatrix{Float64}) where {N,M}
+  p = plan_for(elems, u); ϕ = Ref(0.0); nnz = Ref{Int64}(0); r = Vector{Float64}(undef, length(u))
+  GC.@preserve Φ check(ccall((:ad4sm_assemble_duals, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Float64}, Ptr{Float64}, Ref{Int64}),
+                             p.h, pointer(Φ), 1 + N + M, ϕ, r, nnz))
   (ϕ[], r, fetch(p, length(u), nnz[]))
 end
 

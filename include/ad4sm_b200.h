@@ -133,6 +133,15 @@ int ad4sm_eval_pf_u(ad4sm_plan* plan, const double* u, const double* d, double* 
 int ad4sm_eval_pf_d(ad4sm_plan* plan, const double* u, const double* d, double* const* hist, double* phi, double* r,
                     int64_t* nnz_out);
 
+/* Assembly only: makeϕrKt(Φ::Vector{<:adiff.D2}, elems, u) -- elements.toolkit.jl:169-203, the method
+ * Solvers.solvestep! calls after building Φ itself (solvers.jl:213-216, 257-260).  `Phi`: ne records of `stride`
+ * doubles, record e = element e of `elems` = (v | g[n] | h[n(n+1)/2]): exactly the memory of a Julia
+ * Vector{D2{n,m,Float64}} (adiff.jl:29-42; stride = 1+n+m), n = N*size(u,1) local dofs ordered comp + size(u,1)*node
+ * (toolkit:183,187), h = packed upper triangle, entry (i<=j), 1-based, at (j-1)j/2+i (adiff.jl:26,84).  The library
+ * does what toolkit:182-202 does: ϕ = Σ v, r[idx] += g, Kt = dropzeros(sparse(...)) with duplicates summed in `elems`
+ * order.  Needs size(u,1) == element dimension and no HALO batch.  Results as ad4sm_eval (+ ad4sm_fetch_csc). */
+int ad4sm_assemble_duals(ad4sm_plan* plan, const void* Phi, int64_t stride, double* phi, double* r, int64_t* nnz_out);
+
 /* SparseMatrixCSC arrays of the last evaluation, after dropzeros (toolkit:202).  Any pointer may be NULL. */
 int ad4sm_fetch_csc(ad4sm_plan* plan, int64_t* colptr, int64_t* rowval, double* nzval);
 

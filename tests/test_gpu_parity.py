@@ -386,6 +386,30 @@ def test_two_stage_host_api_matches_makephirkt(declare, n):
     assert np.array_equal(Kt.nzval, ref[2].nzval) and np.array_equal(Kt.rowval, ref[2].rowval)
 
 
+@pytest.mark.parametrize("case", ["hex8", "quad4", "tet4", "hex8-keyed"])
+def test_assembly_only_entry_is_bit_exact(case):
+    """makeϕrKt(Φ, elems, u) (elements.toolkit.jl:169-203): element duals computed by the oracle, assembled by the GPU
+    (ad4sm_assemble_duals) and by the oracle's serial COO->CSC -- same contributions, same left fold in `elems` order,
+    so r and Kt must agree bit for bit (ϕ: the device sums a fixed tree, the reference a left fold)."""
+    b, u = {"hex8": lambda: K.hex_case((6, 5, 4)), "quad4": lambda: K.quad_case((9, 7)), "tet4": lambda: K.tet_case((4, 3, 3)),
+            "hex8-keyed": lambda: K.hex_case((5, 4, 3))}[case]()
+    val, g, H = X.elem_duals(b.kind, b.D, b.P, b.N, b.mat, b.nodes, b.gradN, b.wgt, b.Nval, X.M_ELASTIC, u)
+    nodes = b.nodes
+    if case == "hex8-keyed":   # the batch lists the elements in another order than `elems`: orig_index maps slots to elems
+        perm = np.random.default_rng(5).permutation(b.ne)
+        b = El.ElemBatch("CE", 3, b.nodes, b.gradN, b.wgt, b.mat, orig_index=perm.astype(np.int64))
+        inv = np.argsort(perm)
+        val, g, H, nodes = val[inv], g[inv], H[inv], nodes[inv]   # row k = element at position k of `elems`
+    phi0, r0, (cp0, rv0, nz0) = X.assemble(nodes, b.D, val, g, H, u.size)
+    plan = El.Plan(b, u.shape[1], b.D)
+    phi, r, Kt = plan.assemble_duals(El.pack_duals(val, g, H))
+    assert abs(phi - phi0) <= 1e-13 * max(1.0, abs(phi0))
+    assert np.array_equal(r, r0)
+    assert np.array_equal(Kt.colptr, cp0) and np.array_equal(Kt.rowval, rv0) and np.array_equal(Kt.nzval, nz0)
+    # and the assembled result is the one the full path gives (to 1e-12: other arithmetic inside the elements)
+    K.assert_parity(plan.makeϕrKt(u), (phi0, r0, (cp0, rv0, nz0)))
+
+
 def test_isolated_nodes_and_shuffled_elements():
     """Nodes that no element touches give empty CSC columns and zero residual entries; a shuffled `elems` order changes
     only the summation order (results still match the oracle evaluated in that same order)."""
