@@ -540,6 +540,17 @@ class Plan:
                                                 C.c_void_p(r.ctypes.data), C.byref(nnz)))
         return phi.value, r, (self._fetch(ndof, nnz.value) if fetch else None)
 
+    def assemble_duals_phi_r(self, Phi):
+        """makeϕr(Φ, elems, u) (elements.toolkit.jl:204-215): rows (v | g | ...), D1 or D2 records."""
+        Phi = np.ascontiguousarray(Phi, dtype=np.float64)
+        if Phi.ndim != 2 or Phi.shape[0] != sum(b.ne for b in self.batches):
+            raise ValueError("Phi must have one row per element")
+        phi = C.c_double()
+        r = np.empty(self.n_nodes * self.dpn)
+        capi.check(self._L.ad4sm_assemble_duals_phi_r(self._h, C.c_void_p(Phi.ctypes.data), Phi.shape[1], C.byref(phi),
+                                                      C.c_void_p(r.ctypes.data)))
+        return phi.value, r
+
     def makeϕr(self, u):
         u = self._u(u)
         phi = C.c_double()

@@ -82,6 +82,7 @@ SIGNATURES = {
     "ad4sm_device_view_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DeviceView)]),
     "ad4sm_eval_elements_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ad4sm_assemble_duals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ad4sm_assemble_duals_phi_r": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ad4sm_eval_elements_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ad4sm_fetch_phi_r_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ad4sm_eval_assemble_device": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -1320,12 +1320,14 @@ int ad4sm_eval_pf_d(ad4sm_plan* p, const double* u, const double* d, double* con
 }
 
 // makeϕrKt(Φ, elems, u) (elements.toolkit.jl:169-203): assembly of caller-supplied element duals
-int ad4sm_assemble_duals(ad4sm_plan* p, const void* Phi, int64_t stride, double* phi, double* r, int64_t* nnz_out) {
+static int assemble_duals_impl(ad4sm_plan* p, const void* Phi, int64_t stride, bool want_K, double* phi, double* r, int64_t* nnz_out) {
   if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
   if (!Phi) return fail(AD4SM_EINVAL, "Phi is NULL");
   const long long n = (long long)p->N * p->D, m = n * (n + 1) / 2;
-  if (p->dpn != p->D) return fail(AD4SM_EINVAL, "ad4sm_assemble_duals needs size(u,1) == element dimension");
-  if (stride < 1 + n + m) return fail(AD4SM_EINVAL, "stride smaller than 1 + n + n(n+1)/2 doubles (D2{n,m,Float64})");
+  if (p->dpn != p->D) return fail(AD4SM_EINVAL, "assembly of element duals needs size(u,1) == element dimension");
+  if (stride < 1 + n + (want_K ? m : 0))
+    return fail(AD4SM_EINVAL, want_K ? "stride smaller than 1 + n + n(n+1)/2 doubles (D2{n,m,Float64})"
+                                     : "stride smaller than 1 + n doubles (D1{n,Float64})");
   for (const BatchPlan& b : p->batches)
     if (b.halo) return fail(AD4SM_EINVAL, "ad4sm_assemble_duals on a plan with HALO batches");
   CK(cudaSetDevice(p->device));
@@ -1340,28 +1342,39 @@ int ad4sm_assemble_duals(ad4sm_plan* p, const void* Phi, int64_t stride, double*
     return rc;
   };
   if (cudaMemcpyAsync(dPhi, Phi, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return done(fail(AD4SM_ENODEV, "upload of the element duals failed"));
-  if (launch_duals_to_staging(dPhi, stride, p->key_dev, p->ne, p->N, p->D, p->Ke, p->re, p->phie, s) != cudaSuccess)
+  if (launch_duals_to_staging(dPhi, stride, p->key_dev, p->ne, p->N, p->D, want_K ? p->Ke : nullptr, p->re, p->phie, s) != cudaSuccess)
     return done(fail(AD4SM_ENODEV, "duals_to_staging launch failed"));
-  const bool sorted = p->sorted_built && p->sorted_on;
+  const bool sorted = want_K && p->sorted_built && p->sorted_on;
   if (sorted && launch_halo_scatter(p->Ke, p->cpos, p->C, 0, p->n_own_sorted, n_pair_blocks(p->N), s) != cudaSuccess)
     return done(fail(AD4SM_ENODEV, "staging scatter launch failed"));
   p->ev_cur = nullptr;
   p->fused_last = false;
   p->fused_mode_last = 0;
   p->sorted_last = sorted;
-  p->elements_mode = MODE_ELASTIC;
-  int rc = ad4sm_eval_assemble_device(p, MODE_ELASTIC);
+  const int mode = want_K ? MODE_ELASTIC : MODE_PHI_R;
+  p->elements_mode = mode;
+  int rc = ad4sm_eval_assemble_device(p, mode);
   if (rc) return done(rc);
   FieldOut& f = p->field[AD4SM_FIELD_U];
   unsigned long long nz = 0;
   rc = download_phi_r(p, AD4SM_FIELD_U, phi, r);
   if (rc) return done(rc);
-  if (cudaMemcpyAsync(&nz, p->n_zero_dev, sizeof(nz), cudaMemcpyDeviceToHost, s) != cudaSuccess) return done(fail(AD4SM_ENODEV, "copy failed"));
+  if (want_K && cudaMemcpyAsync(&nz, p->n_zero_dev, sizeof(nz), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    return done(fail(AD4SM_ENODEV, "copy failed"));
   if (cudaStreamSynchronize(s) != cudaSuccess) return done(fail(AD4SM_ENODEV, "assembly failed"));
   cudaFree(dPhi);
-  f.n_zero = (long long)nz;
-  if (nnz_out) *nnz_out = f.nnz - f.n_zero;
+  if (want_K) {
+    f.n_zero = (long long)nz;
+    if (nnz_out) *nnz_out = f.nnz - f.n_zero;
+  }
   return AD4SM_OK;
+}
+int ad4sm_assemble_duals(ad4sm_plan* p, const void* Phi, int64_t stride, double* phi, double* r, int64_t* nnz_out) {
+  return assemble_duals_impl(p, Phi, stride, true, phi, r, nnz_out);
+}
+// makeϕr(Φ, elems, u) (elements.toolkit.jl:204-215): records (v | g[n] | ...), D1 or D2
+int ad4sm_assemble_duals_phi_r(ad4sm_plan* p, const void* Phi, int64_t stride, double* phi, double* r) {
+  return assemble_duals_impl(p, Phi, stride, false, phi, r, nullptr);
 }
 
 int ad4sm_fetch_csc(ad4sm_plan* p, int64_t* colptr, int64_t* rowval, double* nzval) {

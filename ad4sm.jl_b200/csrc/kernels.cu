@@ -1216,11 +1216,12 @@ __global__ void __launch_bounds__(256) duals_to_staging_kernel(const double* Phi
   const double* rec = Phi + (index ? index[slot] : slot) * stride;
   const double* h = rec + 1 + n;
   const int a = (q + o) % N;
-  for (int j = 0; j < D; j++)
-    for (int l = 0; l < D; l++) {
-      const int pr = a * D + j, pc = q * D + l, hi = pr > pc ? pr : pc, lo = pr > pc ? pc : pr;
-      Ke[t * DD + j * D + l] = h[hi * (hi + 1) / 2 + lo];
-    }
+  if (Ke)  // nullptr: residual only (makeϕr, records may be D1: no h)
+    for (int j = 0; j < D; j++)
+      for (int l = 0; l < D; l++) {
+        const int pr = a * D + j, pc = q * D + l, hi = pr > pc ? pr : pc, lo = pr > pc ? pc : pr;
+        Ke[t * DD + j * D + l] = h[hi * (hi + 1) / 2 + lo];
+      }
   if (blk < N)  // this thread also moves node blk's gradient entries, thread 0 the value
     for (int j = 0; j < D; j++) re[slot * n + blk * D + j] = rec[1 + blk * D + j];
   if (blk == 0) phie[slot] = rec[0];

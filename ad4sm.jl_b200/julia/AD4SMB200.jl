@@ -132,6 +132,13 @@ function AD4SM.Elements.makeϕrKt(Φ::Vector{adiff.D2{N,M,Float64}}, elems::Vect
   (ϕ[], r, fetch(p, length(u), nnz[]))
 end
 
+function AD4SM.Elements.makeϕr(Φ::Vector{T}, elems::Vector, u::AbstractMatrix{Float64}) where {T<:Union{adiff.D1,adiff.D2}}   # toolkit:204-215
+  p = plan_for(elems, u); ϕ = Ref(0.0); r = Vector{Float64}(undef, length(u))
+  GC.@preserve Φ check(ccall((:ad4sm_assemble_duals_phi_r, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Float64}, Ptr{Float64}),
+                             p.h, pointer(Φ), sizeof(T) ÷ 8, ϕ, r))
+  (ϕ[], r)
+end
+
 function AD4SM.Elements.makeϕrKt(elems::Vector{<:CPElem}, u::Array{Float64}, d::Array{Float64})
   p = plan_for(elems, u); ϕ = Ref(0.0); nnz = Ref{Int64}(0); r = Vector{Float64}(undef, length(u))
   check(ccall((:ad4sm_eval_pf_u, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ref{Int64}),

@@ -141,6 +141,9 @@ int ad4sm_eval_pf_d(ad4sm_plan* plan, const double* u, const double* d, double* 
  * does what toolkit:182-202 does: ϕ = Σ v, r[idx] += g, Kt = dropzeros(sparse(...)) with duplicates summed in `elems`
  * order.  Needs size(u,1) == element dimension and no HALO batch.  Results as ad4sm_eval (+ ad4sm_fetch_csc). */
 int ad4sm_assemble_duals(ad4sm_plan* plan, const void* Phi, int64_t stride, double* phi, double* r, int64_t* nnz_out);
+/* makeϕr(Φ, elems, u) -- elements.toolkit.jl:204-215: ϕ and r only; records (v | g[n] | anything), i.e. a
+ * Vector{D1{n,Float64}} (stride 1+n) or Vector{D2{n,m,Float64}} (stride 1+n+m). */
+int ad4sm_assemble_duals_phi_r(ad4sm_plan* plan, const void* Phi, int64_t stride, double* phi, double* r);
 
 /* SparseMatrixCSC arrays of the last evaluation, after dropzeros (toolkit:202).  Any pointer may be NULL. */
 int ad4sm_fetch_csc(ad4sm_plan* plan, int64_t* colptr, int64_t* rowval, double* nzval);

@@ -406,6 +406,9 @@ def test_assembly_only_entry_is_bit_exact(case):
     assert abs(phi - phi0) <= 1e-13 * max(1.0, abs(phi0))
     assert np.array_equal(r, r0)
     assert np.array_equal(Kt.colptr, cp0) and np.array_equal(Kt.rowval, rv0) and np.array_equal(Kt.nzval, nz0)
+    # makeϕr(Φ, elems, u): D1-shaped records (v | g)
+    phi1, r1 = plan.assemble_duals_phi_r(np.ascontiguousarray(np.concatenate([val[:, None], g], axis=1)))
+    assert abs(phi1 - phi0) <= 1e-13 * max(1.0, abs(phi0)) and np.array_equal(r1, r0)
     # and the assembled result is the one the full path gives (to 1e-12: other arithmetic inside the elements)
     K.assert_parity(plan.makeϕrKt(u), (phi0, r0, (cp0, rv0, nz0)))
 
