@@ -139,6 +139,26 @@ def test_python_and_cxx_restatements_agree(name, make):
     assert np.abs(nz - nz2).max() <= 1e-13 * np.abs(nz).max()
 
 
+@pytest.mark.parametrize("make", [lambda: hex_mesh(), lambda: quad_mesh(mat=NH)], ids=["hex8", "quad4"])
+def test_element_dual_record_layout(make):
+    """Input format of the assembly-only entry points (ad4sm_assemble_duals): one record (v | g[n] | h[n(n+1)/2]) per element
+    -- the field order of `struct D2{N,M,T}` (adiff.jl:38-42) with h packed like adiff.jl:26,84.  The literal Python duals
+    carry exactly those three fields; `Elements.pack_duals` must build the same record from the C++ oracle's dense Hessian."""
+    from ad4sm_b200 import Elements as El
+    elems, X0 = make()
+    u = _u(X0, elems[0].D)
+    Phi = E.element_duals(elems, u)
+    rec_py = np.stack([np.concatenate([[p.v], p.g, p.h]) for p in Phi])          # D2 field order: v, g, h
+    b = _Batch(elems)
+    val, g, H = X.elem_duals(b.kind, b.D, b.P, b.N, b.mat, b.nodes, b.gradN, b.wgt, b.Nval, X.M_ELASTIC, u)
+    rec = El.pack_duals(val, g, H)
+    n = b.N * b.D
+    assert rec.shape == rec_py.shape == (len(elems), 1 + n + n * (n + 1) // 2)
+    assert np.abs(rec - rec_py).max() <= 1e-13 * np.abs(rec_py).max()
+    for i, j in ((0, 0), (1, 4), (4, 1), (n - 1, n - 1), (2, n - 1)):               # entry (i,j) of the Hessian sits at packed_index
+        assert rec[0, 1 + n + adiff.packed_index(i, j)] == H[0, i, j]
+
+
 def test_python_and_cxx_agree_phasefield():
     pf = M.PhaseField(0.01, 100.0, M.Hooke2D(210000.0, 0.3, plane_stress=False), 2)
     elems, X0 = quad_mesh((2, 2), mat=pf, ctor=E.QuadP)
