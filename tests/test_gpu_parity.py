@@ -413,6 +413,22 @@ def test_assembly_only_entry_is_bit_exact(case):
     K.assert_parity(plan.makeϕrKt(u), (phi0, r0, (cp0, rv0, nz0)))
 
 
+def test_sorted_assembly_with_many_contributions_per_pair():
+    """Every element listed 20 times (a legal `elems`): each node pair then has up to 160 contributions and a warp's range
+    of the sorted staging exceeds its shared-memory slice, so K2s takes its direct-load path.  Same bits as the
+    element-major assembly, and parity with the oracle."""
+    b, u = K.hex_case((3, 3, 2))
+    rep = np.repeat(np.arange(b.ne), 20)
+    bb = El.ElemBatch("CE", 3, b.nodes[rep], b.gradN[rep], b.wgt[rep], b.mat)
+    plan = El.Plan(bb, u.shape[1], 3)
+    assert plan.info(capi.INFO_SORTED) == 2
+    s = plan.makeϕrKt(u)
+    K.assert_parity(s, K.oracle_eval(bb, u))
+    plan.set_option(capi.OPT_SORTED, 0)
+    e = plan.makeϕrKt(u)
+    assert s[0] == e[0] and np.array_equal(s[1], e[1]) and np.array_equal(s[2].nzval, e[2].nzval)
+
+
 def test_isolated_nodes_and_shuffled_elements():
     """Nodes that no element touches give empty CSC columns and zero residual entries; a shuffled `elems` order changes
     only the summation order (results still match the oracle evaluated in that same order)."""
