@@ -5,6 +5,8 @@ import numpy as np
 from ad4sm_b200 import Elements as El, Materials as Ma, mesh
 from oracle import cxx_binding as X
 
+from _golden import assert_values_entrywise
+
 TOL = 1e-12  # north_star: values to relative 1e-12 in fp64
 
 
@@ -51,9 +53,16 @@ def oracle_eval(batches, u, mode=X.M_ELASTIC, d=None, hist=None, **kw):
     return X.make_phi_r_Kt(batches, u, mode=mode, d=d, hist=hist, **kw)
 
 
-def assert_parity(got, ref, tol=TOL):
-    """(ϕ, r, Kt) from the product vs the oracle: pattern bit-exact, values to `tol` of the matrix scale
-    and per entry to 100·tol of the entry (cancellation-prone small entries)."""
+def assert_parity(got, ref, tol=TOL, stats=None):
+    """(ϕ, r, Kt) from the product vs the oracle -- SURVEY.md §8(c), north_star "relative 1e-12":
+      (1) colptr / rowval identical integer for integer;
+      (2) every stored value: |a - b| <= tol * max(|a|, |b|).  An entry that is itself the result of cancellation
+          (|K_ij| far below the magnitude of the terms summed into it) cannot meet a relative bound whatever the
+          evaluation order -- 64 terms (8 elements x 8 Gauss points) of magnitude M carry ~64 eps M ~ 7e-15 M of
+          rounding -- so for those the bound is the FLOOR  0.1 * tol * sqrt(|K_ii| |K_jj|): one tenth of the tolerance
+          relative to the entry's natural scale (the diagonal bounds an SPD matrix's entries), i.e. still ten times
+          tighter than a matrix-scale comparison.  `stats`, if given, receives how many entries needed the floor;
+      (3) r per entry to tol of the residual scale, ϕ relative tol."""
     phi, r, Kt = got
     phi0, r0, (cp0, rv0, nz0) = ref
     assert abs(phi - phi0) <= tol * max(1.0, abs(phi0)), (phi, phi0)
@@ -61,9 +70,10 @@ def assert_parity(got, ref, tol=TOL):
     assert np.abs(r - r0).max() <= tol * rs, np.abs(r - r0).max() / rs
     assert np.array_equal(Kt.colptr, cp0), "colptr differs"
     assert np.array_equal(Kt.rowval, rv0), "rowval differs"
-    ks = np.abs(nz0).max()
-    err = np.abs(Kt.nzval - nz0)
-    assert err.max() <= tol * ks, err.max() / ks
+    n_floor, max_rel = assert_values_entrywise(Kt.nzval, nz0, cp0, rv0, tol)
+    if stats is not None:
+        stats["n_floor"] = n_floor
+        stats["max_rel"] = max_rel
 
 
 def csc_dense(Kt):
