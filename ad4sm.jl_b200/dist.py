@@ -119,6 +119,8 @@ class GpuBackend:
         self.n_own = own_batch.ne
         self.peer = False
         self.push = False
+        self._bound = None
+        self.bind_current_stream()
         self._declare_exports(part)
         field_id = capi.FIELD_D if self.mode == capi.MODE_PF_D else capi.FIELD_U
         v = self.plan.staging_view(field_id)
@@ -142,7 +144,19 @@ class GpuBackend:
         self.capi.check(self.capi.lib().ad4sm_export_ranges(self.plan._h, len(rng), first, count))
 
     def set_stream(self, stream):
-        self.plan.set_stream(stream.cuda_stream)
+        self.plan.set_stream(stream.cuda_stream or 1)
+        self._bound = stream.cuda_stream
+
+    def bind_current_stream(self):
+        """The library's kernels and torch.distributed's collectives must order on ONE stream: K1 -> send/recv or
+        barrier -> assembly -> ϕ all-gather.  A plan launches on a private non-blocking stream by default, which NCCL
+        (ordering on torch's current stream) would race with; so the backend binds the plan to torch's current stream at
+        construction and again whenever a step finds the current stream changed.  (Handle 0 is torch's legacy default
+        stream: passed as cudaStreamLegacy = 1, since NULL means "the plan's own stream" in the C ABI.)"""
+        cur = self.torch.cuda.current_stream().cuda_stream
+        if cur != self._bound:
+            self.plan.set_stream(cur or 1)
+            self._bound = cur
 
     def enable_peer_staging(self, part, dist=None, push=True):
         """Interface rows through peer-mapped memory (CUDA IPC over NVLink) instead of NCCL send/recv; the exchange step
@@ -280,6 +294,8 @@ class DistPlan:
         """One evaluation, everything left on the device.  Returns the global ϕ as a 0-d tensor."""
         import torch
         import torch.distributed as D
+        if hasattr(self.b, "bind_current_stream"):
+            self.b.bind_current_stream()   # no-op unless the caller switched torch streams since the last step
         peer = getattr(self.b, "peer", False)
         if peer and not getattr(self.b, "push", False):
             # K1 itself writes into the owners' (single-buffered) HALO rows: nobody may start before every rank has

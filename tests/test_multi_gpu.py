@@ -36,9 +36,10 @@ def _worker(rank, world, port, out):
         for mode in ("nccl", "push", "peerk1"):
             own = El.ElemBatch("CE", 3, p.local_conn(conn[p.own_elems]), b.gradN[p.own_elems], b.wgt[p.own_elems], b.mat)
             be = AD.GpuBackend(own, p.local_conn(conn[p.halo_elems]), p, 3, device=rank)
+            # no explicit be.set_stream: the backend binds the plan to torch's current stream by itself, also when that
+            # changes AFTER construction (the NCCL collectives order on it; ADVICE round 1: a silent race otherwise)
             stream = torch.cuda.Stream()
             torch.cuda.set_stream(stream)
-            be.set_stream(stream)
             if mode != "nccl":
                 assert be.enable_peer_staging(p, push=(mode == "push")), "peer staging (CUDA IPC) not available"
                 assert be.push == (mode == "push")
