@@ -907,6 +907,9 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
         tma = e ? atoi(e) : 0;  // measured: 36 x 80-byte bulk copies per element make K1 2.74 ms; plain STG.128 1.93 ms
       }
       a.sorted_tma = tma;
+      static int k1exp = -1;
+      if (k1exp < 0) k1exp = getenv("AD4SM_EXP_K1") ? atoi(getenv("AD4SM_EXP_K1")) : 0;
+      a.exp = k1exp;
     }
     if (fuse2) {
       a.fz = FuseArgs{};

@@ -82,6 +82,7 @@ struct K1Args {
   // destination-sorted staging: cpos[slot*NPB + block] = position << 1 | transposed; nullptr = element-major staging
   const unsigned* cpos;
   double* C;
+  int exp;              // TIMING EXPERIMENT ONLY (AD4SM_EXP_K1, wrong results): 1 = the sorted epilogue stores nothing
   int sorted_tma;       // sorted blocks leave through shared memory + one 80-byte bulk copy each (else plain STG.128)
   // peer staging: slots [first, first+count) are also written to the owner rank's staging over NVLink
   int n_xr;

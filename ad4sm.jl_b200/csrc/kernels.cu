@@ -356,7 +356,7 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
   constexpr int NO = N / 2 + 1, DD = D * D;
   // destination-sorted staging: this lane's block positions, fetched now so that the loads fly during the contraction
   unsigned cp[NO];
-  if (cpos_e) {
+  if (cpos_e && a.exp != 1) {
 #pragma unroll
     for (int o = 0; o < NO; o++) cp[o] = (active && o < n_offsets(N, q)) ? __ldg(cpos_e + o * N + q) : 0xffffffffu;
   }
@@ -365,6 +365,16 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
   if (cpos_e) {  // (D == 3 only) every block goes to its own sorted slot
     if constexpr (D == 3) {
       __syncwarp();  // all lanes are done reading the records: their area becomes the staging
+      if (a.exp == 1) {  // timing experiment: keep the accumulators alive, store (practically) nothing
+        double t = rq[0] + rq[1] + rq[2];
+#pragma unroll
+        for (int o = 0; o < NO; o++)
+#pragma unroll
+          for (int i = 0; i < 9; i++) t += acc[o][i];
+        if (t == 1.2345e300) C[0] = t;
+        __syncwarp();
+        return;
+      }
       if (active) {
 #pragma unroll
         for (int o = 0; o < NO; o++) {

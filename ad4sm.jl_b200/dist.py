@@ -331,13 +331,20 @@ class DistPlan:
 # ------------------------------------------------------------------------------------------------
 # structured z-slab workload for bench.py (weak scaling): built rank-locally, no global arrays
 # ------------------------------------------------------------------------------------------------
-def slab_hex_workload(n, nz_per_rank, rank, world, mat, seed=20261021):
-    """Rank-local pieces of an n x n x (nz_per_rank*world) Hex8 block partitioned into z-slabs:
-    returns (own ElemBatch with LOCAL node ids, halo connectivity in local ids, Partition, u_local [3, n_local])."""
+def slab_hex_workload(n, nz_per_rank, rank, world, mat, seed=20261021, nz_total=None):
+    """Rank-local pieces of an n x n x nzt Hex8 block partitioned into z-slabs.  Weak scaling: nzt = nz_per_rank*world
+    (every rank owns nz_per_rank layers); strong scaling: `nz_total` layers split as evenly as integers allow (rank g
+    owns layers [g*nzt//world, (g+1)*nzt//world)).
+    Returns (own ElemBatch with LOCAL node ids, halo connectivity in local ids, Partition, u_local [3, n_local])."""
     from . import Elements as El, mesh
-    nzt = nz_per_rank * world
     h = 1.0 / n
-    k0, k1 = rank * nz_per_rank, (rank + 1) * nz_per_rank     # own element layers [k0, k1)
+    if nz_total is None:
+        k0, k1 = rank * nz_per_rank, (rank + 1) * nz_per_rank     # own element layers [k0, k1)
+    else:
+        k0, k1 = (rank * nz_total) // world, ((rank + 1) * nz_total) // world
+        if k1 - k0 < 1:
+            raise ValueError("fewer element layers than ranks")
+        nz_per_rank = k1 - k0
     # owned nodes: planes k0+1..k1 (plus plane 0 on rank 0); the plane k1 is shared with rank+1 and owned here (lower
     # rank), so the halo is the first element layer of rank+1, and this rank's first layer is halo on rank-1.
     has_halo = rank + 1 < world
@@ -384,12 +391,12 @@ class SlabRunner:
     """bench.py's multi-GPU arm: config C2 weak-scaled -- every rank owns an n x n x nz Hex8 NeoHooke slab of an
     n x n x (nz*world) block."""
 
-    def __init__(self, n, nz_per_rank, rank, world, device=0, mat=None, peer_staging=False):
+    def __init__(self, n, nz_per_rank, rank, world, device=0, mat=None, peer_staging=False, nz_total=None):
         import torch
         from . import Materials as Ma
         self.torch = torch
         mat = mat or Ma.NeoHooke(1000.0, 5000.0)
-        self.batch, halo_conn, self.part, self.u_local = slab_hex_workload(n, nz_per_rank, rank, world, mat)
+        self.batch, halo_conn, self.part, self.u_local = slab_hex_workload(n, nz_per_rank, rank, world, mat, nz_total=nz_total)
         self.backend = GpuBackend(self.batch, halo_conn, self.part, 3, device=device)
         self.plan = self.backend.plan
         self.dplan = DistPlan(self.backend, self.part)

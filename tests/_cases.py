@@ -5,7 +5,7 @@ import numpy as np
 from ad4sm_b200 import Elements as El, Materials as Ma, mesh
 from oracle import cxx_binding as X
 
-from _golden import assert_values_entrywise
+from oracle.check import assert_result_parity
 
 TOL = 1e-12  # north_star: values to relative 1e-12 in fp64
 
@@ -64,13 +64,7 @@ def assert_parity(got, ref, tol=TOL, stats=None):
           tighter than a matrix-scale comparison.  `stats`, if given, receives how many entries needed the floor;
       (3) r per entry to tol of the residual scale, ϕ relative tol."""
     phi, r, Kt = got
-    phi0, r0, (cp0, rv0, nz0) = ref
-    assert abs(phi - phi0) <= tol * max(1.0, abs(phi0)), (phi, phi0)
-    rs = max(np.abs(r0).max(), 1e-300)
-    assert np.abs(r - r0).max() <= tol * rs, np.abs(r - r0).max() / rs
-    assert np.array_equal(Kt.colptr, cp0), "colptr differs"
-    assert np.array_equal(Kt.rowval, rv0), "rowval differs"
-    n_floor, max_rel = assert_values_entrywise(Kt.nzval, nz0, cp0, rv0, tol)
+    n_floor, max_rel = assert_result_parity(phi, r, Kt.colptr, Kt.rowval, Kt.nzval, ref, tol)
     if stats is not None:
         stats["n_floor"] = n_floor
         stats["max_rel"] = max_rel

@@ -5,6 +5,8 @@ import json
 
 import numpy as np
 
+from oracle.check import assert_values_entrywise  # noqa: F401  (re-exported for _cases)
+
 MODES = {"elastic": 0, "pf_u": 1, "pf_d": 2}
 
 
@@ -74,36 +76,6 @@ def run_product(c):
     else:
         phi, r, Kt = plan.makeϕrKt_d(c.u, c.d, hist)
     return phi, r, Kt.colptr, Kt.rowval, Kt.nzval, hist
-
-
-def _entry_scales(colptr, rowval, nzval):
-    """sqrt(|K_ii K_jj|) for every stored entry (i, j) of a CSC matrix: the natural magnitude of that entry (for a
-    positive-definite Kt it bounds |K_ij|), used as the floor of the per-entry comparison."""
-    n = len(colptr) - 1
-    col = np.repeat(np.arange(n, dtype=np.int64), np.diff(colptr))
-    row = rowval - 1
-    diag = np.zeros(n)
-    on = row == col
-    diag[row[on]] = np.abs(nzval[on])
-    return np.sqrt(diag[row] * diag[col])
-
-
-
-def assert_values_entrywise(nz, nz0, colptr, rowval, tol):
-    """every stored value |a - b| <= tol * max(|a|, |b|); entries that are themselves the result of
-    cancellation get the floor 0.1 * tol * sqrt(|K_ii| |K_jj|) (argued in _cases.assert_parity).  Returns (number of
-    entries that needed the floor, largest relative difference)."""
-    err = np.abs(nz - nz0)
-    mag = np.maximum(np.abs(nz), np.abs(nz0))
-    bad = err > tol * mag
-    n_floor = int(bad.sum())
-    if n_floor:
-        floor = 0.1 * tol * _entry_scales(colptr, rowval, nz0)
-        worst = (err[bad] / np.maximum(floor[bad], 1e-300)).max()
-        assert worst <= 1.0, f"{n_floor} entries beyond relative {tol}; worst is {worst:.2f} x the cancellation floor"
-        # the floor is for the occasional cancelling entry, not a second tolerance for everything
-        assert n_floor <= max(8, len(err) // 1000), f"{n_floor} of {len(err)} entries needed the cancellation floor"
-    return n_floor, (float((err / np.maximum(mag, 1e-300)).max()) if len(err) else 0.0)
 
 
 def compare(got, c, tol):
