@@ -600,6 +600,64 @@ class Plan:
                 hmax[i][...] = h[k]
             off += b.ne
 
+    # -- Newton-step glue on the device (Solvers.solvestep!, solvers.jl:183-184, 211-224, 257-291) ---------------
+    def newton_setup(self, bfree, field=capi.FIELD_U):
+        """`bfree` = bfreeu (bool, shaped like u or flat in u's column-major order).  Returns (nfree, ncnst, nnz_ff)."""
+        b = np.asarray(bfree)
+        b = np.ascontiguousarray(b.reshape(-1, order="F"), dtype=np.uint8)
+        n, _ = self.pattern_size(field)
+        if b.size != n:
+            raise ValueError(f"DimensionMismatch: bfree must have {n} entries")
+        a, c, z = C.c_int64(), C.c_int64(), C.c_int64()
+        capi.check(self._L.ad4sm_newton_setup(self._h, field, b.ctypes.data, C.byref(a), C.byref(c), C.byref(z)))
+        self._newton = {field: (a.value, c.value, z.value)}
+        self._newton_pat = {}
+        return a.value, c.value, z.value
+
+    def newton_pattern(self, field=capi.FIELD_U):
+        nfree, _, nnz = self._newton[field]
+        if field not in self._newton_pat:
+            cp = np.empty(nfree + 1, dtype=np.int64)
+            rv = np.empty(nnz, dtype=np.int64)
+            capi.check(self._L.ad4sm_newton_pattern(self._h, field, cp.ctypes.data, rv.ctypes.data))
+            self._newton_pat[field] = (cp, rv)
+        return self._newton_pat[field]
+
+    def newton_reduce(self, kind, fe=None, ducnst=None, want_K=True, field=capi.FIELD_U, out=None):
+        """After makeϕrKt on this plan: (res, Kt[ifree,ifree] or None, norm(res), norm(fi[icnst])).
+        kind 0 = predictor (res = fi[ifree] - fe[ifree] - Kt[ifree,icnst]*ducnst), 1 = corrector (res = fe[ifree] - fi[ifree]).
+        `out`: optional preallocated (res, nzval_ff) arrays (e.g. pinned)."""
+        nfree, ncnst, nnz = self._newton[field]
+        res = out[0] if out else np.empty(nfree)
+        nz = (out[1] if out else np.empty(nnz)) if want_K else None
+        norms = np.empty(2)
+        fe_p = None
+        if fe is not None:
+            fe = np.ascontiguousarray(np.asarray(fe, dtype=np.float64).reshape(-1, order="F"))
+            fe_p = fe.ctypes.data
+        du_p = None
+        if ducnst is not None:
+            ducnst = np.ascontiguousarray(ducnst, dtype=np.float64)
+            if ducnst.size != ncnst:
+                raise ValueError(f"DimensionMismatch: ducnst must have {ncnst} entries")
+            du_p = ducnst.ctypes.data
+        capi.check(self._L.ad4sm_newton_reduce(self._h, field, int(kind), fe_p, du_p, res.ctypes.data,
+                                               nz.ctypes.data if want_K else None, norms.ctypes.data))
+        Kff = None
+        if want_K:
+            cp, rv = self.newton_pattern(field)
+            Kff = SparseMatrixCSC(nfree, nfree, cp, rv, nz)
+        return res, Kff, float(norms[0]), float(norms[1])
+
+    def newton_reduce_device(self, kind, fe_ptr=None, du_ptr=None, field=capi.FIELD_U):
+        capi.check(self._L.ad4sm_newton_reduce_device(self._h, field, int(kind), C.c_void_p(fe_ptr) if fe_ptr else None,
+                                                      C.c_void_p(du_ptr) if du_ptr else None))
+
+    def newton_view(self, field=capi.FIELD_U):
+        v = capi.NewtonView()
+        capi.check(self._L.ad4sm_newton_view_get(self._h, field, C.byref(v)))
+        return v
+
     # -- device-resident API (bench / GPU-side callers) ------------------------------------------
     def set_stream(self, cuda_stream):
         capi.check(self._L.ad4sm_set_stream(self._h, C.c_void_p(cuda_stream)))

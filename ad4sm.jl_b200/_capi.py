@@ -54,6 +54,11 @@ class DeviceView(C.Structure):
     ]
 
 
+class NewtonView(C.Structure):
+    _fields_ = [("nfree", C.c_int64), ("ncnst", C.c_int64), ("nnz_ff", C.c_int64), ("res_dev", C.c_void_p),
+                ("nzval_ff_dev", C.c_void_p), ("norms_dev", C.c_void_p), ("colptr_ff_dev", C.c_void_p), ("rowval_ff_dev", C.c_void_p)]
+
+
 class AD4SMError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libad4sm_b200 error {code}: {msg}")
@@ -95,6 +100,11 @@ SIGNATURES = {
     "ad4sm_get_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "ad4sm_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "ad4sm_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
+    "ad4sm_newton_setup": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ad4sm_newton_pattern": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ad4sm_newton_reduce": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ad4sm_newton_reduce_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ad4sm_newton_view_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(NewtonView)]),
     "ad4sm_measure_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

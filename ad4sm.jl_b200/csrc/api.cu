@@ -54,6 +54,15 @@ struct FieldOut {
   double* dz_nzval = nullptr;
   long long dz_cap = 0;
   bool dz_valid = false;
+  // Newton-step glue (ad4sm_newton_*): free / constrained split of the field's dofs and the pattern of Kt[ifree,ifree]
+  struct Newton {
+    bool ready = false;
+    long long nfree = 0, ncnst = 0, nnz_ff = 0;
+    int *fidx = nullptr, *free_list = nullptr, *cnst_list = nullptr;
+    long long *colptr_ff = nullptr, *rowval_ff = nullptr;
+    double *nzval_ff = nullptr, *res = nullptr, *fc = nullptr, *fe = nullptr, *du = nullptr, *partials = nullptr, *norms = nullptr;
+    bool reduced = false;
+  } nw;
 };
 
 struct EvSet {
@@ -1427,6 +1436,177 @@ int ad4sm_fetch_csc(ad4sm_plan* p, int64_t* colptr, int64_t* rowval, double* nzv
   if (colptr) CK(cudaMemcpy(colptr, f.dz_colptr, sizeof(long long) * (f.n_dof + 1), cudaMemcpyDeviceToHost));
   if (rowval) CK(cudaMemcpy(rowval, f.dz_rowval, sizeof(long long) * nnz_out, cudaMemcpyDeviceToHost));
   if (nzval) CK(cudaMemcpy(nzval, f.dz_nzval, sizeof(double) * nnz_out, cudaMemcpyDeviceToHost));
+  return AD4SM_OK;
+}
+
+// ---- Newton-step glue (solvers.jl:183-184, 211-224, 257-291; kernels in newton.cu) ------------------------------------
+static NewtonArgs newton_args(ad4sm_plan* p, int field) {
+  FieldOut& f = p->field[field];
+  NewtonArgs a = {};
+  a.n_nodes = p->n_nodes;
+  a.nfree = f.nw.nfree;
+  a.dpn = f.dpn;
+  a.nbr_ptr = p->nbr_ptr;
+  a.nbr = p->nbr;
+  a.fidx = f.nw.fidx;
+  a.free_list = f.nw.free_list;
+  a.nzval = f.nzval;
+  return a;
+}
+
+int ad4sm_newton_setup(ad4sm_plan* p, int32_t field, const uint8_t* bfree, int64_t* nfree_out, int64_t* ncnst_out, int64_t* nnz_ff_out) {
+  int rc = check_field(p, field);
+  if (rc) return rc;
+  if (!bfree) return fail(AD4SM_EINVAL, "bfree is NULL");
+  FieldOut& f = p->field[field];
+  if (f.n_dof >= (1ll << 31)) return fail(AD4SM_EINVAL, "too many dofs for the 32-bit free/constrained index");
+  if (f.dpn > 8) return fail(AD4SM_EINVAL, "Newton glue supports up to 8 dofs per node");
+  CK(cudaSetDevice(p->device));
+  FieldOut::Newton& w = f.nw;
+  // ifreeu = findall(bfreeu[:]), icnstu = findall(.!bfreeu[:])   (solvers.jl:183-184)
+  std::vector<int> fidx(f.n_dof), fl, cl;
+  for (long long k = 0; k < f.n_dof; k++) {
+    if (bfree[k]) {
+      fidx[k] = (int)fl.size();
+      fl.push_back((int)k);
+    } else {
+      fidx[k] = -1 - (int)cl.size();
+      cl.push_back((int)k);
+    }
+  }
+  for (void* q : {(void*)w.fidx, (void*)w.free_list, (void*)w.cnst_list, (void*)w.colptr_ff, (void*)w.rowval_ff, (void*)w.nzval_ff, (void*)w.res,
+                  (void*)w.fc, (void*)w.fe, (void*)w.du, (void*)w.partials, (void*)w.norms})
+    if (q) {  // a previous split: release it
+      cudaFree(q);
+      p->allocs.erase(std::remove(p->allocs.begin(), p->allocs.end(), q), p->allocs.end());
+    }
+  w = FieldOut::Newton();
+  w.nfree = (long long)fl.size();
+  w.ncnst = (long long)cl.size();
+  rc = dev_upload(p, &w.fidx, fidx.data(), fidx.size());
+  if (!rc) rc = dev_upload(p, &w.free_list, fl.data(), fl.size());
+  if (!rc) rc = dev_upload(p, &w.cnst_list, cl.data(), cl.size());
+  if (!rc) rc = dev_alloc(p, &w.colptr_ff, (size_t)w.nfree + 1);
+  if (!rc) rc = dev_alloc(p, &w.res, (size_t)w.nfree);
+  if (!rc) rc = dev_alloc(p, &w.fc, (size_t)w.nfree);
+  if (!rc) rc = dev_alloc(p, &w.fe, (size_t)f.n_dof);
+  if (!rc) rc = dev_alloc(p, &w.du, (size_t)w.ncnst);
+  if (!rc) rc = dev_alloc(p, &w.partials, (size_t)2 * newton_partials());
+  if (!rc) rc = dev_alloc(p, &w.norms, 2);
+  if (rc) return rc;
+  // column counts of Kt[ifree,ifree] -> 1-based column pointers
+  CK(cudaMemsetAsync(w.colptr_ff, 0, sizeof(long long) * (w.nfree + 1), p->stream));
+  NewtonArgs a = newton_args(p, field);
+  a.cnt = w.colptr_ff;
+  CK(launch_newton_columns(a, p->stream));
+  void* tmp = nullptr;
+  const size_t tb = newton_scan_tmp_bytes(w.nfree + 1);
+  CK(cudaMalloc(&tmp, tb ? tb : 1));
+  cudaError_t e = launch_newton_colptr(w.colptr_ff, w.nfree, tmp, tb, p->stream);
+  long long last = 1;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&last, w.colptr_ff + w.nfree, sizeof(long long), cudaMemcpyDeviceToHost, p->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+  cudaFree(tmp);
+  CK(e);
+  w.nnz_ff = last - 1;
+  rc = dev_alloc(p, &w.nzval_ff, (size_t)std::max<long long>(w.nnz_ff, 1));
+  if (rc) return rc;
+  w.ready = true;
+  if (nfree_out) *nfree_out = w.nfree;
+  if (ncnst_out) *ncnst_out = w.ncnst;
+  if (nnz_ff_out) *nnz_ff_out = w.nnz_ff;
+  return AD4SM_OK;
+}
+
+static int newton_ensure_rowval(ad4sm_plan* p, int field) {
+  FieldOut::Newton& w = p->field[field].nw;
+  if (w.rowval_ff) return 0;
+  int rc = dev_alloc(p, &w.rowval_ff, (size_t)std::max<long long>(w.nnz_ff, 1));
+  if (rc) return rc;
+  NewtonArgs a = newton_args(p, field);
+  a.colptr_ff = w.colptr_ff;
+  a.rowval_ff = w.rowval_ff;
+  CK(launch_newton_columns(a, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+
+int ad4sm_newton_pattern(ad4sm_plan* p, int32_t field, int64_t* colptr_ff, int64_t* rowval_ff) {
+  int rc = check_field(p, field);
+  if (rc) return rc;
+  FieldOut::Newton& w = p->field[field].nw;
+  if (!w.ready) return fail(AD4SM_ESTATE, "ad4sm_newton_pattern before ad4sm_newton_setup");
+  CK(cudaSetDevice(p->device));
+  if (colptr_ff) CK(cudaMemcpy(colptr_ff, w.colptr_ff, sizeof(long long) * (w.nfree + 1), cudaMemcpyDeviceToHost));
+  if (rowval_ff) {
+    rc = newton_ensure_rowval(p, field);
+    if (rc) return rc;
+    CK(cudaMemcpy(rowval_ff, w.rowval_ff, sizeof(long long) * w.nnz_ff, cudaMemcpyDeviceToHost));
+  }
+  return AD4SM_OK;
+}
+
+int ad4sm_newton_reduce_device(ad4sm_plan* p, int32_t field, int32_t kind, const double* fe_dev, const double* ducnst_dev) {
+  int rc = check_field(p, field);
+  if (rc) return rc;
+  FieldOut& f = p->field[field];
+  FieldOut::Newton& w = f.nw;
+  if (!w.ready) return fail(AD4SM_ESTATE, "ad4sm_newton_reduce before ad4sm_newton_setup");
+  if (!f.evaluated || !f.have_K) return fail(AD4SM_ESTATE, "ad4sm_newton_reduce needs a Kt evaluation of this field first");
+  if (kind != 0 && kind != 1) return fail(AD4SM_EINVAL, "kind must be 0 (predictor) or 1 (corrector)");
+  CK(cudaSetDevice(p->device));
+  NewtonArgs a = newton_args(p, field);
+  a.colptr_ff = w.colptr_ff;
+  a.nzval_ff = w.nzval_ff;
+  const bool want_fc = kind == 0 && ducnst_dev && w.ncnst > 0;
+  if (want_fc) {
+    a.du = ducnst_dev;
+    a.fc = w.fc;
+  }
+  CK(launch_newton_columns(a, p->stream));
+  CK(launch_newton_res(w.nfree, w.free_list, f.r, fe_dev, want_fc ? w.fc : nullptr, kind, w.res, w.ncnst, w.cnst_list, w.partials,
+                       w.norms, p->stream));
+  w.reduced = true;
+  return AD4SM_OK;
+}
+
+int ad4sm_newton_reduce(ad4sm_plan* p, int32_t field, int32_t kind, const double* fe, const double* ducnst, double* res,
+                        double* nzval_ff, double* norms) {
+  int rc = check_field(p, field);
+  if (rc) return rc;
+  FieldOut& f = p->field[field];
+  FieldOut::Newton& w = f.nw;
+  if (!w.ready) return fail(AD4SM_ESTATE, "ad4sm_newton_reduce before ad4sm_newton_setup");
+  CK(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  if (fe) CK(cudaMemcpyAsync(w.fe, fe, sizeof(double) * f.n_dof, cudaMemcpyHostToDevice, s));
+  if (kind == 0 && ducnst && w.ncnst > 0) CK(cudaMemcpyAsync(w.du, ducnst, sizeof(double) * w.ncnst, cudaMemcpyHostToDevice, s));
+  rc = ad4sm_newton_reduce_device(p, field, kind, fe ? w.fe : nullptr, (kind == 0 && ducnst) ? w.du : nullptr);
+  if (rc) return rc;
+  if (res) CK(cudaMemcpyAsync(res, w.res, sizeof(double) * w.nfree, cudaMemcpyDeviceToHost, s));
+  if (norms) CK(cudaMemcpyAsync(norms, w.norms, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+  if (nzval_ff) CK(cudaMemcpyAsync(nzval_ff, w.nzval_ff, sizeof(double) * w.nnz_ff, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return AD4SM_OK;
+}
+
+int ad4sm_newton_view_get(ad4sm_plan* p, int32_t field, ad4sm_newton_view* v) {
+  int rc = check_field(p, field);
+  if (rc) return rc;
+  if (!v) return fail(AD4SM_EINVAL, "view is NULL");
+  FieldOut::Newton& w = p->field[field].nw;
+  if (!w.ready) return fail(AD4SM_ESTATE, "ad4sm_newton_view_get before ad4sm_newton_setup");
+  CK(cudaSetDevice(p->device));
+  rc = newton_ensure_rowval(p, field);
+  if (rc) return rc;
+  v->nfree = w.nfree;
+  v->ncnst = w.ncnst;
+  v->nnz_ff = w.nnz_ff;
+  v->res_dev = w.res;
+  v->nzval_ff_dev = w.nzval_ff;
+  v->norms_dev = w.norms;
+  v->colptr_ff_dev = (const int64_t*)w.colptr_ff;
+  v->rowval_ff_dev = (const int64_t*)w.rowval_ff;
   return AD4SM_OK;
 }
 

@@ -128,4 +128,27 @@ cudaError_t launch_dropzeros(long long n_dof, const long long* colptr, const lon
 size_t dropzeros_tmp_bytes(long long n_dof);
 cudaError_t launch_fp64_peak(double* tflops, double* mhz);
 
+// ---- Newton-step glue (newton.cu; solvers.jl:183-184, 211-224, 257-291) ----------------------------------------------
+struct NewtonArgs {
+  long long n_nodes, nfree;
+  int dpn;
+  const unsigned* nbr_ptr;      // node-block pattern of the field (AsmArgs)
+  const unsigned* nbr;
+  const int* fidx;              // [n_dof] >= 0: rank among the free dofs; < 0: -1 - rank among the constrained dofs
+  const int* free_list;         // [nfree] dof id of each free dof (ascending = findall(bfree[:]))
+  const double* nzval;          // structural CSC values of the last evaluation
+  const long long* colptr_ff;   // [nfree+1] 1-based column pointers of Kt[ifree,ifree] (nullptr in the counting pass)
+  long long* cnt;               // counting pass: [nfree] free rows per column
+  long long* rowval_ff;         // pattern pass
+  double* nzval_ff;             // value pass
+  const double* du;             // [ncnst] Δu of the constrained dofs, or nullptr
+  double* fc;                   // [nfree] (Kt[ifree,icnst]*Δucnst)
+};
+int newton_partials();
+cudaError_t launch_newton_columns(const NewtonArgs& a, cudaStream_t s);
+size_t newton_scan_tmp_bytes(long long n);
+cudaError_t launch_newton_colptr(long long* cnt, long long nfree, void* tmp, size_t tmp_bytes, cudaStream_t s);
+cudaError_t launch_newton_res(long long nfree, const int* free_list, const double* r, const double* fe, const double* fc, int kind,
+                              double* res, long long ncnst, const int* cnst_list, double* partials, double* norms, cudaStream_t s);
+
 }  // namespace ad4sm

@@ -52,7 +52,7 @@ CONFIGS = {
                b_elem=2 * (16 + 256 + 32 + 128 + 16.2 + 8) + 256, b_asm=(288.4 + 16.1) + (72.1 + 8.0), sample=(200, 200),
                k1="k1_u_kernel<2,4,4,PFNEO,PF> + k1_d_kernel<2,4,4>", asm="k3_kernel + k2_kernel<2> / <1> (u- and d-phase)"),
     "C5": dict(name="3-D Hex8 Ogden (200x200x25 slab per GPU; 8 GPUs = the 200^3 mesh)", shape="hex8", n=(200, 200, 25),
-               flop=40224.0, b_elem=32 + 1536 + 64 + 24.7, b_asm=1963.5 + 24.7, sample=(200, 200, 2),
+               flop=40224.0, b_elem=32 + 1536 + 64 + 24.7, b_asm=1963.5 + 24.7, sample=(200, 200, 1),
                k1="k1_u_kernel<3,8,8,OGDEN>", asm="k3_kernel + k2s_tma_kernel3"),
 }
 
@@ -622,10 +622,47 @@ def run_ours(args):
 
 
 def bench_newton(plan, w, u_np, timed, ne_total, torch):
-    """Newton-step glue on the device (solvers.jl:211-224, 257-291): with the bottom face clamped and the top
-    face displacement-driven, one iteration ships u up and brings back only res = -(r[ifree]), Kt[ifree,icnst]*Δu_cnst
-    folded into it, the values of Kt[ifree,ifree] and two norms."""
-    return None
+    """Newton-step glue on the device (solvers.jl:211-224, 257-291): bottom face clamped, top face
+    displacement-driven.  One corrector iteration = ad4sm_eval (u up; ϕ, r down) + ad4sm_newton_reduce (res, the VALUES of
+    Kt[ifree,ifree] and the two norms down, pinned): everything a host `lu(Kt[ifree,ifree]) \\ res` needs, with no host-side
+    sparse slicing.  Also the device time of the reduction alone."""
+    import ctypes as C
+    from ad4sm_b200 import _capi as capi
+    L = capi.lib()
+    nn = w.n_nodes
+    npl = (w.dims[0] + 1) * (w.dims[1] + 1)
+    bfree = np.ones((w.D, nn), dtype=np.uint8, order="F")
+    bfree[:, :npl] = 0            # bottom plane (nodes are numbered x-fastest, z-slowest): clamped
+    bfree[2, nn - npl:] = 0       # top plane: driven in z
+    t0 = time.perf_counter()
+    nfree, ncnst, nnz_ff = plan.newton_setup(bfree)
+    plan.newton_pattern()
+    t_setup = time.perf_counter() - t0
+    res = torch.empty(nfree, dtype=torch.float64).pin_memory().numpy()
+    nzff = torch.empty(nnz_ff, dtype=torch.float64).pin_memory().numpy()
+    norms = np.empty(2)
+    r_host = torch.empty(nn * w.D, dtype=torch.float64).pin_memory().numpy()
+    phi, nnz = C.c_double(), C.c_int64()
+
+    def step():
+        capi.check(L.ad4sm_eval(plan._h, u_np.ctypes.data, C.byref(phi), r_host.ctypes.data, C.byref(nnz)))
+        capi.check(L.ad4sm_newton_reduce(plan._h, capi.FIELD_U, 1, None, None, res.ctypes.data, nzff.ctypes.data, norms.ctypes.data))
+
+    t_it = timed(step, 4)
+    # device time of the reduction alone (gather of the values + res + norms), CUDA events on the plan's stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    plan.newton_reduce_device(1)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        plan.newton_reduce_device(1)
+    e1.record()
+    torch.cuda.synchronize()
+    return {"value": ne_total / t_it, "unit": UNIT, "ms_per_iteration": t_it * 1e3, "reduce_device_ms": e0.elapsed_time(e1) / 5,
+            "nfree": nfree, "ncnst": ncnst, "nnz_ff": nnz_ff, "setup_s": t_setup,
+            "d2h_bytes_per_iteration": int(res.nbytes + nzff.nbytes + 16 + r_host.nbytes + 16),
+            "call": "ad4sm_eval + ad4sm_newton_reduce(corrector): res, nzval of Kt[ifree,ifree], norm(res), norm(fi[icnst]) to pinned "
+                    "host memory; the sparse solve itself stays on the host (out of scope)"}
 
 
 def main():

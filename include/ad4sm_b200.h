@@ -148,6 +148,34 @@ int ad4sm_assemble_duals_phi_r(ad4sm_plan* plan, const void* Phi, int64_t stride
 /* SparseMatrixCSC arrays of the last evaluation, after dropzeros (toolkit:202).  Any pointer may be NULL. */
 int ad4sm_fetch_csc(ad4sm_plan* plan, int64_t* colptr, int64_t* rowval, double* nzval);
 
+/* ---- Newton-step glue on the device (Solvers.solvestep!, nEqs == 0 branch; solvers.jl:183-184, 211-224, 257-291) ----
+ * The reference slices the assembled Kt on the host after every makeϕrKt: Kt[ifreeu,ifreeu] for lu(), Kt[ifreeu,icnstu]*
+ * Δucnst for the predictor, fi[ifreeu] - fe[ifreeu] and two norms.  These entry points do that where Kt lives, so that
+ * only res, the norms and the VALUES of Kt[ifree,ifree] cross PCIe (its pattern is built once per plan).
+ *   setup   : `bfree` = bfreeu[:] (one byte per dof of the field, column-major order of u; non-zero = free).  Builds
+ *             ifree = findall(bfree), icnst = findall(!bfree) and the CSC pattern of Kt[ifree,ifree] (free numbering,
+ *             1-based, STRUCTURAL: exact zeros are kept -- nnz_out of the evaluation tells whether there are any).
+ *   pattern : colptr_ff [nfree+1], rowval_ff [nnz_ff].
+ *   reduce  : after an evaluation of `field`.  kind 0 (predictor, :220-221): res = fi[ifree] - fe[ifree] -
+ *             Kt[ifree,icnst]*ducnst;  kind 1 (corrector, :262): res = fe[ifree] - fi[ifree].  fe NULL = zeros(n_dof)
+ *             (the default of solvestep!); ducnst [ncnst] is read for kind 0 only (NULL = zeros).  Outputs (any may be
+ *             NULL): res [nfree], nzval_ff [nnz_ff], norms[2] = { norm(res), norm(fi[icnst]) } (:263-264). */
+int ad4sm_newton_setup(ad4sm_plan* plan, int32_t field, const uint8_t* bfree, int64_t* nfree, int64_t* ncnst, int64_t* nnz_ff);
+int ad4sm_newton_pattern(ad4sm_plan* plan, int32_t field, int64_t* colptr_ff, int64_t* rowval_ff);
+int ad4sm_newton_reduce(ad4sm_plan* plan, int32_t field, int32_t kind, const double* fe, const double* ducnst, double* res,
+                        double* nzval_ff, double* norms);
+/* the same on device-resident data (asynchronous on the plan's stream); results through ad4sm_newton_view_get */
+typedef struct ad4sm_newton_view {
+  int64_t nfree, ncnst, nnz_ff;
+  const double* res_dev;         /* [nfree] */
+  const double* nzval_ff_dev;    /* [nnz_ff] */
+  const double* norms_dev;       /* [2] */
+  const int64_t* colptr_ff_dev;  /* [nfree+1] 1-based */
+  const int64_t* rowval_ff_dev;  /* [nnz_ff]  1-based */
+} ad4sm_newton_view;
+int ad4sm_newton_reduce_device(ad4sm_plan* plan, int32_t field, int32_t kind, const double* fe_dev, const double* ducnst_dev);
+int ad4sm_newton_view_get(ad4sm_plan* plan, int32_t field, ad4sm_newton_view* view);
+
 /* ---- device-resident path (inputs/outputs stay in HBM; used by GPU-side callers and bench.py) ---- */
 int ad4sm_set_stream(ad4sm_plan* plan, void* cuda_stream); /* cudaStream_t; NULL = plan's own stream */
 /* mode: 0 = elastic (ad4sm_eval), 1 = PF u-phase, 2 = PF d-phase, 3 = elastic ϕ,r only.

@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <stdexcept>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -278,13 +279,73 @@ template <class T> static T phi_I(T I1, T I2, T I3, int kind, const double* p) {
   I1 = I1 * dpow(J, -2.0 / 3);
   return C1 * (I1 - 3.0) + K * sq(J - 1.0);
 }
+// Ogden (elasticmaterials.jl:148-172).  The reference defines only the scalar energy: λ_i = sqrt(svdvals(FᵀF)_i);
+//   K < 0: μ/α (Σ λ_i^α − 3);   else J = Π λ_i,  μ/α (Σ λ_i^α / J^(α/3) − 3) + K (J − 1)²
+// and cannot differentiate it (svdvals on duals).  The oracle therefore differentiates the SAME energy
+// through a smooth matrix function instead of an eigen-decomposition: Σ λ_i^α = tr(U^α), U = (FᵀF)^(1/2) by the Newton
+// iteration U <- (U + C U⁻¹)/2 from U = I (quadratic; ‖C − I‖ < 1/2 here), in the element's dual arithmetic -- which has
+// no singular point at repeated stretches and shares nothing with the product's spectral divided-difference tangent
+// (materials.cuh).  Integer α only (tr(U^α) by repeated multiplication); J = sqrt(det C).
+template <class T> static Mx<T, 3> inv3(const Mx<T, 3>& A) {
+  Mx<T, 3> B;
+  const T c00 = A.at(1, 1) * A.at(2, 2) - A.at(1, 2) * A.at(2, 1);
+  const T c01 = A.at(1, 2) * A.at(2, 0) - A.at(1, 0) * A.at(2, 2);
+  const T c02 = A.at(1, 0) * A.at(2, 1) - A.at(1, 1) * A.at(2, 0);
+  const T det = A.at(0, 0) * c00 + A.at(0, 1) * c01 + A.at(0, 2) * c02;
+  const T id = 1.0 / det;
+  B.at(0, 0) = c00 * id;
+  B.at(1, 0) = c01 * id;
+  B.at(2, 0) = c02 * id;
+  B.at(0, 1) = (A.at(0, 2) * A.at(2, 1) - A.at(0, 1) * A.at(2, 2)) * id;
+  B.at(1, 1) = (A.at(0, 0) * A.at(2, 2) - A.at(0, 2) * A.at(2, 0)) * id;
+  B.at(2, 1) = (A.at(0, 1) * A.at(2, 0) - A.at(0, 0) * A.at(2, 1)) * id;
+  B.at(0, 2) = (A.at(0, 1) * A.at(1, 2) - A.at(0, 2) * A.at(1, 1)) * id;
+  B.at(1, 2) = (A.at(0, 2) * A.at(1, 0) - A.at(0, 0) * A.at(1, 2)) * id;
+  B.at(2, 2) = (A.at(0, 0) * A.at(1, 1) - A.at(0, 1) * A.at(1, 0)) * id;
+  return B;
+}
+template <class T> static Mx<T, 3> mul3(const Mx<T, 3>& A, const Mx<T, 3>& B) {
+  Mx<T, 3> R;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) R.at(i, j) = A.at(i, 0) * B.at(0, j) + A.at(i, 1) * B.at(1, j) + A.at(i, 2) * B.at(2, j);
+  return R;
+}
+template <class T> static T phi_ogden3(const Mx<T, 3>& F, const double* p) {
+  const double alpha = p[0], mu = p[1], K = p[2];
+  const int ia = (int)alpha;
+  if ((double)ia != alpha || ia < 1 || ia > 8) throw std::runtime_error("oracle: Ogden needs an integer alpha in 1..8");
+  const Mx<T, 3> C = FtF<T, 3>(F);
+  Mx<T, 3> U;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) U.at(i, j) = Zero<T>::get() + (i == j ? 1.0 : 0.0);
+  for (int it = 0; it < 9; it++) {
+    const Mx<T, 3> W = mul3<T>(C, inv3<T>(U));
+    for (int k = 0; k < 9; k++) U.a[k] = 0.5 * (U.a[k] + W.a[k]);
+    for (int i = 0; i < 3; i++)  // keep the iterate symmetric (C and U commute in exact arithmetic)
+      for (int j = i + 1; j < 3; j++) {
+        const T s = 0.5 * (U.at(i, j) + U.at(j, i));
+        U.at(i, j) = s;
+        U.at(j, i) = s;
+      }
+  }
+  Mx<T, 3> Pw = U;
+  for (int k = 1; k < ia; k++) Pw = mul3<T>(Pw, U);
+  const T S = Pw.at(0, 0) + Pw.at(1, 1) + Pw.at(2, 2);  // Σ λ_i^α
+  if (K < 0) return (mu / alpha) * (S - 3.0);
+  T I1, I2, I3;
+  invariants3(C, I1, I2, I3);
+  const T J = dsqrt(I3);
+  return (mu / alpha) * (S * dpow(J, -alpha / 3) - 3.0) + K * sq(J - 1.0);
+}
 template <class T> static T phi_hyper(const Mx<T, 3>& F, int kind, const double* p) {  // :138-147
+  if (kind == OGDEN) return phi_ogden3<T>(F, p);
   Mx<T, 3> C = FtF<T, 3>(F);
   T I1, I2, I3;
   invariants3(C, I1, I2, I3);
   return phi_I(I1, I2, I3, kind, p);
 }
 template <class T> static T phi_hyper(const Mx<T, 2>& F, int kind, const double* p) {
+  if (kind == OGDEN) throw std::runtime_error("oracle: 2-D Ogden is not restated in C++ (use the Python oracle)");
   Mx<T, 2> C = FtF<T, 2>(F);
   const double K = kind == MOONEY ? p[2] : p[1];
   T L3 = K < 0 ? dpow(F(1) * F(4) - F(2) * F(3), -2.0) : (Zero<T>::get() + 1.0);

@@ -113,6 +113,9 @@ def elem_duals(kind, D, P, N, mat, nodes, gradN, wgt, Nval, mode, u, d=None, his
     ne = nodes.shape[0]
     n = N if mode == M_PF_D else D * N
     md, mp = mat_desc(mat, grad_term, nh2d_extension)
+    if type(mat).__name__ == "Ogden" and (D != 3 or float(mat.alpha) != int(mat.alpha) or not 1 <= mat.alpha <= 8):
+        # the C++ restatement differentiates Σλ^α = tr(U^α) through a matrix square root: 3-D, integer α only
+        raise ValueError("oracle (C++): Ogden is restated for 3-D elements and integer alpha in 1..8; use oracle/materials.py otherwise")
     val = np.empty(ne)
     g = np.empty((ne, n))
     H = np.empty((ne, n, n))

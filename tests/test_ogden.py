@@ -111,3 +111,33 @@ def test_ogden_alpha2_is_neohookean_limit():
         assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0])
         assert np.abs(a[1] - b[1]).max() <= 1e-11 * np.abs(b[1]).max()
         assert np.abs(a[2] - b[2]).max() <= 1e-11 * np.abs(b[2]).max()
+
+
+@pytest.mark.parametrize("K", [5000.0, -1.0], ids=["compressible", "K<0"])
+@pytest.mark.parametrize("alpha", [3.0, 2.0, 4.0])
+def test_ogden_element_against_matrix_sqrt_oracle(alpha, K):
+    """Two independent derivations of the SAME energy formula, on whole Hex8 / Tet4 elements:
+      product (materials.cuh, compiled for the host): spectral tangent with divided differences;
+      C++ oracle: D2{9,45} dual arithmetic through Σλ^α = tr(U^α), U = (FᵀF)^(1/2) by a Newton iteration (no
+      eigen-decomposition, oracle/cxx/ad4sm_oracle.cpp: phi_ogden3).
+    ϕ_e, r_e and K_e must agree to 1e-12 -- including the undeformed element, where all stretches coincide."""
+    from oracle import elements as E
+    rng = np.random.default_rng(11)
+    mat = M.Ogden(alpha, 1000.0, K)
+    desc, params = X.mat_desc(mat)
+    for ctor, N in ((E.Hex08, 8), (E.Tet04, 4)):
+        if N == 8:
+            X0 = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float).T
+        else:
+            X0 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float).T
+        p0 = X0.T + 0.1 * rng.uniform(-1, 1, (N, 3))
+        el = ctor(list(range(1, N + 1)), [q for q in p0], mat)
+        for amp in (0.05, 0.0):
+            u = amp * rng.uniform(-1, 1, (3, N))
+            phi, re, Ke = H.element_u(3, N, desc, params, el.gradN, el.wgt, u.T)
+            v, g, Hs = X.elem_duals("CE", 3, el.P, N, mat, np.arange(1, N + 1)[None, :], el.gradN[None], el.wgt[None], None,
+                                    X.M_ELASTIC, np.asfortranarray(u))
+            sK = np.abs(Hs[0]).max()
+            assert abs(phi - v[0]) <= 1e-12 * max(1e-3, abs(v[0])), (N, amp)
+            assert np.abs(re - g[0]).max() <= 1e-12 * max(np.abs(g[0]).max(), 1e-3 * sK), (N, amp)
+            assert np.abs(Ke - Hs[0]).max() <= 1e-12 * sK, (N, amp, np.abs(Ke - Hs[0]).max() / sK)
