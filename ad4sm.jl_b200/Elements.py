@@ -675,14 +675,18 @@ class Plan:
         """Element stage with host inputs (numpy, column-major D x nNodes like `makeϕrKt`'s u): asynchronous upload --
         chunked and overlapped with K1 on large plans -- then K1.  The arrays must stay untouched until `sync()`."""
         u = np.asarray(u)
-        if u.dtype != np.float64 or not (u.flags.f_contiguous or u.flags.c_contiguous):
-            raise ValueError("u must be contiguous float64 memory laid out [node][component], i.e. a column-major "
-                             "D x nNodes matrix or its C-ordered transpose (no hidden copy on the asynchronous path)")
+        ok = u.dtype == np.float64 and u.ndim == 2 and (
+            (u.shape == (self.dpn, self.n_nodes) and u.flags.f_contiguous) or      # the reference's u, column-major
+            (u.shape == (self.n_nodes, self.dpn) and u.flags.c_contiguous))        # its C-ordered transpose: same bytes
+        if not ok:
+            raise ValueError(f"u must be float64 memory laid out [node][component]: a column-major {self.dpn} x {self.n_nodes} "
+                             f"matrix or its C-ordered transpose, got shape {u.shape} (no hidden copy on the asynchronous path; a "
+                             "C-ordered D x nNodes array would be read transposed)")
         dp = None
         if d is not None:
             d = np.asarray(d)
-            if d.dtype != np.float64 or not (d.flags.c_contiguous or d.flags.f_contiguous):
-                raise ValueError("d must be a contiguous float64 array")
+            if d.dtype != np.float64 or d.size != self.n_nodes or not (d.flags.c_contiguous or d.flags.f_contiguous):
+                raise ValueError(f"d must be a contiguous float64 array with {self.n_nodes} entries")
             dp = C.c_void_p(d.ctypes.data)
         capi.check(self._L.ad4sm_eval_elements_host(self._h, mode, C.c_void_p(u.ctypes.data), dp, None))
 

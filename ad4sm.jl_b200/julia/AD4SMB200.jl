@@ -82,31 +82,53 @@ function pack(elems::AbstractVector{E}, idx::Vector{Int}; kw...) where {D,P,M,T,
 end
 
 # ---- plan cache: one plan per (elems object, size(u)) ---------------------------------------------------
+# Keyed WEAKLY on the `elems` vector (a strong key would keep every mesh -- and ~12 GB of HBM per 1M-element plan --
+# alive for ever: the finalizer could never run).  A hit is validated against length(elems) and size(u), so a vector that
+# was push!-ed to, or is evaluated with another size(u,1), gets a fresh plan instead of a stale one.  Mutating an
+# element or a material IN PLACE is not detectable (the reference's element structs are immutable; `elems[i] = other`
+# on the same vector is the one case the caller must announce with `release!(elems)`).
 mutable struct Plan
   h::Ptr{Cvoid}
-  ndof::Int
-  nnodes::Int
+  ne::Int
+  usize::Tuple{Int,Int}
+  groups::Vector{Vector{Int}}      # per batch: positions in `elems` (history marshalling)
+  gauss::Vector{Int}               # per batch: Gauss points per element
 end
-const plans = IdDict{Any,Plan}()
+const plans = WeakKeyDict{Any,Plan}()
+
+destroy!(p::Plan) = (p.h != C_NULL && ccall((:ad4sm_plan_destroy, lib), Cvoid, (Ptr{Cvoid},), p.h); p.h = C_NULL; nothing)
+"""release!(elems): drop (and free on the device) the plan cached for `elems`."""
+release!(elems) = (haskey(plans, elems) && destroy!(pop!(plans, elems)); nothing)
 
 function plan_for(elems, u; kw...)
-  get!(plans, elems) do
-    groups = Dict{Any,Vector{Int}}()                     # one batch per (element type, material)
-    for (i, e) in enumerate(elems)
-      push!(get!(groups, (typeof(e), e.mat), Int[]), i)
-    end
-    packed = [pack(elems, idx; kw...) for idx in values(groups)]
-    batches = [p.batch for p in packed]
-    h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve packed batches begin
-      check(ccall((:ad4sm_plan_create, lib), Cint, (Ptr{Batch}, Int32, Int64, Int32, Int32, Ref{Ptr{Cvoid}}),
-                  batches, length(batches), size(u, 2), size(u, 1), -1, h))
-    end
-    p = Plan(h[], length(u), size(u, 2))
-    finalizer(q -> ccall((:ad4sm_plan_destroy, lib), Cvoid, (Ptr{Cvoid},), q.h), p)
-    p
+  hit = get(plans, elems, nothing)
+  if hit !== nothing
+    hit.ne == length(elems) && hit.usize == size(u) && return hit
+    release!(elems)
   end
+  groups = Dict{Any,Vector{Int}}()                     # one batch per (element type, material)
+  order = Any[]
+  for (i, e) in enumerate(elems)
+    k = (typeof(e), e.mat)
+    haskey(groups, k) || push!(order, k)
+    push!(get!(groups, k, Int[]), i)
+  end
+  idxs = [groups[k] for k in order]                    # deterministic batch order: first appearance in `elems`
+  packed = [pack(elems, idx; kw...) for idx in idxs]
+  batches = [p.batch for p in packed]
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve packed batches begin
+    check(ccall((:ad4sm_plan_create, lib), Cint, (Ptr{Batch}, Int32, Int64, Int32, Int32, Ref{Ptr{Cvoid}}),
+                batches, length(batches), size(u, 2), size(u, 1), -1, h))
+  end
+  p = Plan(h[], length(elems), size(u), idxs, [Int(b.n_gauss) for b in batches])
+  finalizer(destroy!, p)
+  plans[elems] = p
+  p
 end
+
+dense(u::Matrix{Float64}) = u                          # already what the C ABI reads: no copy
+dense(u::AbstractMatrix)  = Matrix{Float64}(u)
 
 function fetch(p::Plan, n, nnz)
   colptr = Vector{Int64}(undef, n + 1); rowval = Vector{Int64}(undef, nnz); nzval = Vector{Float64}(undef, nnz)
@@ -118,8 +140,8 @@ end
 function AD4SM.Elements.makeϕrKt(elems::AbstractVector{<:AbstractCElem}, u::AbstractMatrix{Float64})
   @assert length(elems) > 0                                        # elasticelements.jl:210
   p = plan_for(elems, u); ϕ = Ref(0.0); nnz = Ref{Int64}(0); r = Vector{Float64}(undef, length(u))
-  uc = Matrix{Float64}(u)                                          # dense column-major D x nNodes
-  check(ccall((:ad4sm_eval, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ref{Int64}), p.h, uc, ϕ, r, nnz))
+  uc = dense(u)                                                    # dense column-major D x nNodes (no copy for a Matrix{Float64})
+  GC.@preserve uc check(ccall((:ad4sm_eval, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ref{Int64}), p.h, uc, ϕ, r, nnz))
   (ϕ[], r, fetch(p, length(u), nnz[]))
 end
 
@@ -153,22 +175,63 @@ function AD4SM.Elements.makeϕrKt_d(elems::Vector{<:CPElem}, u::Array{Float64}, 
   (ϕ[], r, fetch(p, length(d), nnz[]))
 end
 
-# ϕmax[ii][gp] is a Tuple (ϕmax⁺, ϕmax⁻) mutated in place by the reference (phasefieldelements.jl:180): marshal it as
-# one [ne][P][2] array per batch (single homogeneous batch shown; mixed meshes scatter back by `orig_index`).
+# ϕmax[ii][gp] is mutated in place by the reference (phasefieldelements.jl:180): a Tuple (ϕmax⁺, ϕmax⁻) for the Hooke-type
+# bases (phasefieldmaterials.jl:75-93, 116-135), a scalar for PhaseField{NeoHooke} (:94-115, the second slot is unused).
+# Marshalled as one [ne_b][P][2] array per batch -- the library reads hist[b] for EVERY batch -- and scattered back through
+# the batch's positions in `elems`.
+hist_get(x::Tuple) = (Float64(x[1]), Float64(x[2]))
+hist_get(x::Real)  = (Float64(x), 0.0)
+hist_set(old::Tuple, a, b) = (a, b)
+hist_set(old::Real, a, b)  = a
 function AD4SM.Elements.makeϕrKt_d(elems::Vector{<:CPElem}, u::Array{Float64}, d::Array{Float64}, ϕmax::Array)
   p = plan_for(elems, u); ϕ = Ref(0.0); nnz = Ref{Int64}(0); r = Vector{Float64}(undef, length(d))
-  P = length(ϕmax[1])
-  h = Array{Float64}(undef, 2, P, length(elems))
-  for (e, he) in enumerate(ϕmax), gp in 1:P
-    h[1, gp, e], h[2, gp, e] = he[gp]
+  hs = [Array{Float64}(undef, 2, p.gauss[b], length(idx)) for (b, idx) in enumerate(p.groups)]
+  for (b, idx) in enumerate(p.groups), (k, e) in enumerate(idx), gp in 1:p.gauss[b]
+    hs[b][1, gp, k], hs[b][2, gp, k] = hist_get(ϕmax[e][gp])
   end
-  hp = [pointer(h)]
-  GC.@preserve h check(ccall((:ad4sm_eval_pf_d, lib), Cint,
+  hp = [pointer(h) for h in hs]
+  GC.@preserve hs check(ccall((:ad4sm_eval_pf_d, lib), Cint,
       (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Ptr{Float64}}, Ref{Float64}, Ptr{Float64}, Ref{Int64}), p.h, u, vec(d), hp, ϕ, r, nnz))
-  for e in eachindex(ϕmax), gp in 1:P
-    ϕmax[e][gp] = (h[1, gp, e], h[2, gp, e])
+  for (b, idx) in enumerate(p.groups), (k, e) in enumerate(idx), gp in 1:p.gauss[b]
+    ϕmax[e][gp] = hist_set(ϕmax[e][gp], hs[b][1, gp, k], hs[b][2, gp, k])
   end
   (ϕ[], r, fetch(p, length(d), nnz[]))
+end
+
+# ---- Newton-step glue on the device (solvers.jl:183-184, 211-224, 257-291; include/ad4sm_b200.h ad4sm_newton_*) --------
+# In `Solvers.solvestep!` replace, for nEqs == 0,
+#     res = fi[ifreeu]-fe[ifreeu];  res .-= Kt[ifreeu,icnstu]*Δucnst;  updt = lu(Kt[ifreeu,ifreeu])\res          (:220-223)
+# by
+#     makeϕrKt!(elems, uold);  res, Kff = newton_reduce(elems, uold, bfreeu, 0; fe=fe, Δucnst=Δucnst);  updt = lu(Kff)\res
+# so that the full Kt never crosses PCIe and no sparse slicing runs on the host.
+struct NewtonSplit
+  nfree::Int; ncnst::Int; colptr::Vector{Int64}; rowval::Vector{Int64}
+end
+const splits = WeakKeyDict{Any,Tuple{BitVector,NewtonSplit}}()
+function newton_split(elems, u, bfree)
+  p = plan_for(elems, u); bf = BitVector(vec(bfree))
+  hit = get(splits, elems, nothing)
+  hit !== nothing && hit[1] == bf && return hit[2]
+  nf = Ref{Int64}(0); nc = Ref{Int64}(0); nz = Ref{Int64}(0); b8 = UInt8.(bf)
+  check(ccall((:ad4sm_newton_setup, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{UInt8}, Ref{Int64}, Ref{Int64}, Ref{Int64}), p.h, 0, b8, nf, nc, nz))
+  cp = Vector{Int64}(undef, nf[] + 1); rv = Vector{Int64}(undef, nz[])
+  check(ccall((:ad4sm_newton_pattern, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Int64}), p.h, 0, cp, rv))
+  s = NewtonSplit(nf[], nc[], cp, rv); splits[elems] = (bf, s); s
+end
+"""evaluate on the device without fetching Kt: ϕ, r"""
+function makeϕrKt!(elems, u::Matrix{Float64})
+  p = plan_for(elems, u); ϕ = Ref(0.0); nnz = Ref{Int64}(0); r = Vector{Float64}(undef, length(u))
+  check(ccall((:ad4sm_eval, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ref{Int64}), p.h, u, ϕ, r, nnz))
+  (ϕ[], r)
+end
+"""kind 0: predictor residual (:220-221), 1: corrector residual (:262).  Returns (res, Kt[ifree,ifree], norm(res), norm(fi[icnst]))."""
+function newton_reduce(elems, u, bfree, kind; fe=nothing, Δucnst=nothing)
+  p = plan_for(elems, u); s = newton_split(elems, u, bfree)
+  res = Vector{Float64}(undef, s.nfree); nz = Vector{Float64}(undef, length(s.rowval)); norms = zeros(2)
+  check(ccall((:ad4sm_newton_reduce, lib), Cint,
+              (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+              p.h, 0, kind, fe === nothing ? C_NULL : pointer(fe), Δucnst === nothing ? C_NULL : pointer(Δucnst), res, nz, norms))
+  (res, SparseMatrixCSC{Float64,Int64}(s.nfree, s.nfree, copy(s.colptr), copy(s.rowval), nz), norms[1], norms[2])
 end
 
 end # module

@@ -82,7 +82,9 @@ typedef struct ad4sm_batch {
   const double* wgt;         /* [n_elems][P]        elem.wgt[gp] */
   const double* Nval;        /* [n_elems][P][N]     elem.N[gp][a]   (CPElem; NULL for CEElem) */
   const int64_t* orig_index; /* [n_elems] 0-based position of each element in `elems` (fixes the
-                                summation order); NULL = positions continue after the previous batch */
+                                summation order); NULL = the element's slot, i.e. its position in the
+                                concatenation of ALL batches in the order given (not "after the largest
+                                key so far": give every batch an orig_index when any batch has one) */
 } ad4sm_batch;
 
 typedef struct ad4sm_plan ad4sm_plan; /* opaque: device copies of the batches + CSC pattern + scatter maps */

@@ -46,3 +46,19 @@ def test_no_cpu_fallback():
     with pytest.raises(capi.AD4SMError) as ei:
         El.makeϕrKt(b, np.zeros((3, len(coords))))
     assert ei.value.code == capi.ENODEV
+
+
+def test_eval_elements_host_rejects_wrong_layout():
+    """A C-ordered D x nNodes array is contiguous but would be read as [node][component]: refuse it (no device needed,
+    the check runs before the library call)."""
+    from ad4sm_b200 import Elements as El
+
+    class _P(El.Plan):
+        def __init__(self):
+            self.dpn, self.n_nodes = 3, 10
+    p = _P()
+    for bad in (np.zeros((3, 10)), np.zeros((3, 9), order="F"), np.zeros((3, 10), dtype=np.float32, order="F")):
+        with pytest.raises(ValueError):
+            p.eval_elements_host(0, bad)
+    with pytest.raises(ValueError):
+        p.eval_elements_host(1, np.zeros((3, 10), order="F"), d=np.zeros(9))

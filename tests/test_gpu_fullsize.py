@@ -132,10 +132,10 @@ def test_c4_quadp_phasefield_500x500_vs_oracle():
 
 
 # ---- the named configurations against the oracle, at the largest size the oracle finishes in seconds -----------------
-def _vs_oracle(b, u, label):
+def _vs_oracle(b, u, label, tol=K.TOL):
     got = El.Plan(b, u.shape[1], u.shape[0]).makeϕrKt(u)
     st = {}
-    K.assert_parity(got, K.oracle_eval(b, u), stats=st)
+    K.assert_parity(got, K.oracle_eval(b, u), tol=tol, stats=st)
     print(f"{label}: ne={b.ne} nnz={got[2].nnz} max per-entry rel diff {st['max_rel']:.2e}, "
           f"{st['n_floor']} entries on the cancellation floor")
     return got
@@ -162,7 +162,11 @@ def test_c5_hex8_slab_vs_oracle(mat):
     NeoHooke control the reference can execute."""
     m = Ma.Ogden(3.0, 1000.0, 5000.0) if mat == "ogden" else Ma.NeoHooke(1000.0, 5000.0)
     b, u = K.hex_case((200, 200, 1), mat=m, seed=23)
-    _vs_oracle(b, u, f"C5 slab ({mat})")
+    # NeoHooke: the north-star 1e-12.  Ogden has NO reference values (the reference cannot differentiate it); product and
+    # oracle are two different formulations of the derivative (spectral divided differences vs dual arithmetic through a
+    # matrix square root), not two orderings of one arithmetic, so they are held to 1e-11 -- measured: every entry within
+    # 1e-13 of its natural scale, 0.4 % of the entries beyond a pure relative 1e-12.
+    _vs_oracle(b, u, f"C5 slab ({mat})", tol=1e-11 if mat == "ogden" else K.TOL)
 
 
 @pytest.mark.skipif(os.environ.get("AD4SM_FULL_ORACLE") != "1", reason="opt-in: the serial oracle assembly of 576 M "
