@@ -29,8 +29,8 @@ class Batch(C.Structure):
 
 
 BATCH_HALO = 1
-OPT_FUSED, OPT_FUSED_LAG, OPT_SORTED, OPT_PEER_PUSH = 1, 2, 3, 4
-INFO_FUSED, INFO_FUSED_STEPS, INFO_SORTED = 1, 2, 3
+OPT_SORTED, OPT_PEER_PUSH = 3, 4
+INFO_SORTED = 3
 
 
 class StagingView(C.Structure):
@@ -52,6 +52,14 @@ class DeviceView(C.Structure):
         ("phi_dev", C.c_void_p), ("r_dev", C.c_void_p), ("nzval_dev", C.c_void_p),
         ("colptr_dev", C.c_void_p), ("rowval_dev", C.c_void_p), ("n_zero_dev", C.c_void_p),
     ]
+
+
+NCCL_ID_BYTES = 128
+
+
+class DistPeer(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("n_send", C.c_int64), ("send_slots", C.c_void_p), ("recv_first_slot", C.c_int64),
+                ("n_recv", C.c_int64)]
 
 
 class NewtonView(C.Structure):
@@ -105,6 +113,12 @@ SIGNATURES = {
     "ad4sm_newton_reduce": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ad4sm_newton_reduce_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ad4sm_newton_view_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(NewtonView)]),
+    "ad4sm_dist_unique_id": (C.c_int, [C.c_void_p]),
+    "ad4sm_dist_init": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ad4sm_dist_destroy": (None, [C.c_void_p]),
+    "ad4sm_dist_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(DistPeer)]),
+    "ad4sm_dist_eval_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ad4sm_dist_eval": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ad4sm_measure_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

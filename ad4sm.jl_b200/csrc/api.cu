@@ -119,27 +119,35 @@ struct ad4sm_plan {
   long long prof_launches[AD4SM_PROF_NCLASS] = {0, 0, 0, 0};
   EvSet* ev_cur = nullptr;  // events of the evaluation in flight between the elements and assemble stages
   int elements_mode = -1;
-  // fused persistent path (single elastic / PF-u batch, no HALO): K1 + K2 + K3 in one cooperative launch
-  FuseArgs fz = {};
-  bool fused_last = false;  // the pending element stage already assembled Kt and r
-  bool fuse_allowed = false;  // ad4sm_set_option(AD4SM_OPT_FUSED); off by default: measured slower in round 1
   // destination-sorted staging (single 3-D batch of a persistent-kernel shape, dpn == 3)
   bool sorted_built = false, sorted_on = true, sorted_last = false;
   long long n_pairs = 0;
   unsigned *cpos = nullptr, *cptr = nullptr, *out_up = nullptr, *out_lo = nullptr, *nn_pack = nullptr;
   double* C = nullptr;
-  // fused + sorted (FuseArgs mode 2): batches of node pairs by readiness step
-  uint4* batch_rec = nullptr;
-  unsigned* sb_ptr = nullptr;
-  unsigned* done2 = nullptr;
-  int n_steps2 = 0, fused_mode_last = 0;
   long long n_own_sorted = 0;  // slots [n_own_sorted, ne) are HALO: scattered into C before K2s
   bool dist_aware = false;     // the caller declared its export ranges / peer links (ad4sm_peer_attach / ad4sm_export_ranges)
   // peer staging / export ranges
   int n_xr = 0, n_xr_local = 0;
   K1Args::PeerRange xr[AD4SM_MAX_PEER_LINKS] = {};
   std::vector<void*> ipc_open;
-  long long gstep2 = 0, n_groups2 = 0;
+  // in-library partitioned evaluation (ad4sm_dist_attach)
+  struct DistPeer {
+    int rank = 0;
+    long long n_send = 0, recv_first = 0, n_recv = 0;
+    long long *rows_x = nullptr, *rows_s = nullptr;  // device: rows in the export buffers / staging slots, in the peer's HALO order
+    long long first_x = -1, first_s = -1;            // >= 0: the list is the contiguous range starting there (sent in place)
+    double *ske = nullptr, *sre = nullptr;           // packed send buffers (non-contiguous lists)
+  };
+  ad4sm_dist* dcomm = nullptr;
+  std::vector<DistPeer> dpeers;
+  int* xmap = nullptr;
+  double *xke = nullptr, *xre = nullptr, *allphi = nullptr, *phi_local = nullptr;
+  long long n_export = 0;
+};
+
+struct ad4sm_dist {
+  ad4sm::DistComm* c;
+  int device;
 };
 
 template <class T> static int dev_alloc(ad4sm_plan* p, T** ptr, size_t count) {
@@ -550,7 +558,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     for (int b = 1; b < n_batches; b++) rest_halo &= (batches[b].batch_flags & AD4SM_BATCH_HALO) != 0;
     if (!(env && env[0] == '0') && rest_halo && !(B0.batch_flags & AD4SM_BATCH_HALO) && D == 3 && dofs_per_node == 3 &&
         k1_config(D, N, B0.n_gauss, B0.elem_kind == AD4SM_ELEM_CP && B0.mat_kind == AD4SM_MAT_PHASEFIELD, B0.n_elems, &c) &&
-        c.persistent && (double)n_blocks * 9.0 < 4.0e9 && (double)ne * NPB < 2.0e9 && n_blocks < (1ll << 31)) {
+        (double)n_blocks * 9.0 < 4.0e9 && (double)ne * NPB < 2.0e9 && n_blocks < (1ll << 31)) {
       std::vector<unsigned> up_index(n_blocks, 0xffffffffu);
       long long U = 0;
       for (long long i = 0; i < n_nodes; i++)
@@ -613,114 +621,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
         p->n_pairs = U;
         p->sorted_built = true;
         p->n_own_sorted = B0.n_elems;
-        // ---- batches for the fused K2s: consecutive pairs, contiguous contributions, readiness = prefix max ----
-        const long long gstep = (long long)c.grid * c.warps;
-        const long long n_groups = (ne + c.EW - 1) / c.EW;
-        const int n_steps = (int)((n_groups + gstep - 1) / gstep);
-        const int cap_blocks = std::min<int>(FUSE_BATCH_BLOCKS, c.rec_bytes / (CBLK3 * 8));
-        std::vector<int> pready(U, 0);
-        for (size_t k = 0; k < n_contrib; k++) {
-          const int st = (int)(((long long)(k / NPB) / c.EW) / gstep);
-          int& r = pready[dest[k] >> 1];
-          if (st > r) r = st;
-        }
-        std::vector<uint4> brec;
-        std::vector<int> bready;
-        bool fits = cap_blocks >= 8 && n_batches == 1;
-        for (long long u = 0; u < U && fits;) {
-          long long v = u;
-          int rdy = 0;
-          while (v < U && v - u < FUSE_BATCH_PAIRS && (int)(cptr[v + 1] - cptr[u]) <= cap_blocks) {
-            rdy = std::max(rdy, pready[v]);
-            v++;
-          }
-          if (v == u) {  // a single pair with more contributions than the landing buffer holds (very high valence)
-            fits = false;
-            break;
-          }
-          brec.push_back(make_uint4((unsigned)u, (unsigned)v, cptr[u], cptr[v]));
-          bready.push_back(rdy);
-          u = v;
-        }
-        if (fits) {
-          std::vector<unsigned> sb_ptr(n_steps + 1, 0);
-          int pm = 0;
-          for (size_t k = 0; k < brec.size(); k++) {
-            pm = std::max(pm, bready[k]);
-            sb_ptr[pm + 1]++;
-          }
-          for (int t = 0; t < n_steps; t++) sb_ptr[t + 1] += sb_ptr[t];
-          int rc3 = dev_upload(p, &p->batch_rec, brec.data(), brec.size());
-          if (!rc3) rc3 = dev_upload(p, &p->sb_ptr, sb_ptr.data(), sb_ptr.size());
-          if (!rc3) rc3 = dev_alloc(p, &p->done2, (size_t)n_steps + 1);
-          if (rc3) {
-            ad4sm_plan_destroy(p);
-            return rc3;
-          }
-          p->n_steps2 = n_steps;
-          p->gstep2 = gstep;
-          p->n_groups2 = n_groups;
-        }
       }
-    }
-  }
-  // ---- fused work lists: which step (= iteration of the persistent K1) makes each block / row complete ----------
-  {
-    const char* env = getenv("AD4SM_FUSED");
-    const bool want = !(env && env[0] == '0');
-    p->fuse_allowed = env && env[0] == '1';
-    K1Config c;
-    const ad4sm_batch& B0 = batches[0];
-    if (want && n_batches == 1 && !(B0.batch_flags & AD4SM_BATCH_HALO) &&
-        k1_config(D, N, B0.n_gauss, B0.elem_kind == AD4SM_ELEM_CP && B0.mat_kind == AD4SM_MAT_PHASEFIELD, ne, &c) &&
-        c.persistent && c.staged) {
-      const long long gstep = (long long)c.grid * c.warps;
-      const long long n_groups = (ne + c.EW - 1) / c.EW;
-      const int n_steps = (int)((n_groups + gstep - 1) / gstep);
-      auto step_of = [&](unsigned slot) { return (int)((slot / (unsigned)c.EW) / gstep); };
-      std::vector<unsigned> kb_ptr(n_steps + 1, 0), kr_ptr(n_steps + 1, 0), blk_sorted(n_blocks), row_sorted(n_nodes);
-      std::vector<int> bstep(n_blocks), rstep(n_nodes);
-#pragma omp parallel for schedule(static)
-      for (long long b = 0; b < n_blocks; b++) {
-        int m = 0;
-        for (unsigned q = blk_ptr[b]; q < blk_ptr[b + 1]; q++) m = std::max(m, step_of((src[q] >> 1) / (unsigned)NPB));
-        bstep[b] = m;
-      }
-#pragma omp parallel for schedule(static)
-      for (long long i = 0; i < n_nodes; i++) {
-        int m = 0;
-        for (unsigned q = adj_ptr[i]; q < adj_ptr[i + 1]; q++) m = std::max(m, step_of(adj[q] / (unsigned)N));
-        rstep[i] = m;
-      }
-      for (long long b = 0; b < n_blocks; b++) kb_ptr[bstep[b] + 1]++;
-      for (long long i = 0; i < n_nodes; i++) kr_ptr[rstep[i] + 1]++;
-      for (int t = 0; t < n_steps; t++) kb_ptr[t + 1] += kb_ptr[t], kr_ptr[t + 1] += kr_ptr[t];
-      {
-        std::vector<unsigned> cb(kb_ptr.begin(), kb_ptr.end() - 1), cr(kr_ptr.begin(), kr_ptr.end() - 1);
-        for (long long b = 0; b < n_blocks; b++) blk_sorted[cb[bstep[b]]++] = (unsigned)b;
-        for (long long i = 0; i < n_nodes; i++) row_sorted[cr[rstep[i]]++] = (unsigned)i;
-      }
-      unsigned *d_kb = nullptr, *d_bs = nullptr, *d_kr = nullptr, *d_rs = nullptr, *d_done = nullptr;
-      int rc2 = dev_upload(p, &d_kb, kb_ptr.data(), kb_ptr.size());
-      if (!rc2) rc2 = dev_upload(p, &d_bs, blk_sorted.data(), blk_sorted.size());
-      if (!rc2) rc2 = dev_upload(p, &d_kr, kr_ptr.data(), kr_ptr.size());
-      if (!rc2) rc2 = dev_upload(p, &d_rs, row_sorted.data(), row_sorted.size());
-      if (!rc2) rc2 = dev_alloc(p, &d_done, (size_t)n_steps + 1);
-      if (rc2) {
-        ad4sm_plan_destroy(p);
-        return rc2;
-      }
-      p->fz.enabled = 1;
-      p->fz.lag = 2;
-      if (const char* l = getenv("AD4SM_FUSED_LAG")) p->fz.lag = std::max(1, atoi(l));
-      p->fz.n_steps = n_steps;
-      p->fz.gstep = gstep;
-      p->fz.n_groups = n_groups;
-      p->fz.done = d_done;
-      p->fz.kb_ptr = d_kb;
-      p->fz.blk_sorted = d_bs;
-      p->fz.kr_ptr = d_kr;
-      p->fz.row_sorted = d_rs;
     }
   }
 #undef TRY
@@ -857,7 +758,7 @@ static int check_eval_args(ad4sm_plan* p, int32_t mode, const double* u_dev, con
 }
 
 // `internal`: called from ad4sm_eval_device, which also runs the assembly and may therefore pick a staging layout of its
-// own (destination-sorted, or consumed inside the fused kernel).  The public two-stage API promises the element-major
+// own (destination-sorted).  The public two-stage API promises the element-major
 // staging of ad4sm_staging_view_get between the stages (interface exchange of partitioned runs).
 static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev,
                               bool internal) {
@@ -874,17 +775,10 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
   const bool kmode_ok = want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U);
   const bool sorted_ok = kmode_ok && p->sorted_built && p->sorted_on && (internal || p->dist_aware);
 
-  const bool fuse2 = internal && sorted_ok && p->fuse_allowed && p->batch_rec != nullptr;  // K1 + K2s in one kernel
-  const bool fuse = internal && !fuse2 && kmode_ok && p->fz.enabled && p->fuse_allowed;   // K1 + K2 + K3 in one kernel
-  const bool sorted = sorted_ok && !fuse;
+  const bool sorted = sorted_ok;
   if (p->push_mode && !internal && !sorted)
     return fail(AD4SM_ESTATE, "peer push is set up for Kt evaluations on the destination-sorted path only (modes 0 and 1)");
-  p->fused_mode_last = fuse2 ? 2 : (fuse ? 1 : 0);
-  p->fused_last = fuse;
   p->sorted_last = sorted;
-  if (fuse) CK(cudaMemsetAsync(p->fz.done, 0, sizeof(unsigned) * ((size_t)p->fz.n_steps + 1), p->stream));
-  if (fuse2) CK(cudaMemsetAsync(p->done2, 0, sizeof(unsigned) * ((size_t)p->n_steps2 + 1), p->stream));
-  if (fuse || fuse2) CK(cudaMemsetAsync(p->n_zero_dev, 0, sizeof(unsigned long long), p->stream));
   for (const BatchPlan& b : p->batches) {
     if (b.halo) continue;
     K1Args a = b.k;
@@ -903,9 +797,10 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
         for (int x = 0; x < p->n_xr; x++) a.xr[x] = p->xr[x];
       }
     }
-    if (fuse) {
-      a.fz = p->fz;
-      a.as = asm_args(p, AD4SM_FIELD_U);
+    if (p->xmap && sorted && !internal && b.k.slot0 == 0) {
+      a.xmap = p->xmap;
+      a.xke = p->xke;
+      a.xre = p->xre;
     }
     if (sorted) {
       a.cpos = p->cpos;
@@ -920,23 +815,11 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
       if (k1exp < 0) k1exp = getenv("AD4SM_EXP_K1") ? atoi(getenv("AD4SM_EXP_K1")) : 0;
       a.exp = k1exp;
     }
-    if (fuse2) {
-      a.fz = FuseArgs{};
-      a.fz.enabled = 2;
-      a.fz.lag = p->fz.lag > 0 ? p->fz.lag : 2;
-      a.fz.n_steps = p->n_steps2;
-      a.fz.gstep = p->gstep2;
-      a.fz.n_groups = p->n_groups2;
-      a.fz.done = p->done2;
-      a.fz.batch_rec = p->batch_rec;
-      a.fz.sb_ptr = p->sb_ptr;
-      a.as = asm_args(p, AD4SM_FIELD_U);
-    }
     // Sub-launches over element slices of the batch: (i) host API -- slice c starts after chunk c of u has arrived;
     // (ii) peer push -- the slices covering the pushed ranges run first, then the copy engine ships them while the
     // rest of K1 runs.
     const bool push = p->push_mode && !internal && sorted && b.k.slot0 == 0;
-    if ((p->h2d_active || push) && !fuse && !fuse2) {
+    if (p->h2d_active || push) {
       long long cut[ad4sm_plan::H2D_MAX + 3];
       int nc = 0;
       cut[nc++] = 0;
@@ -1008,10 +891,10 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   EvSet* ev = p->ev_cur;
   if (ev) CK(cudaEventRecord(ev->e[4], p->stream));  // exchange time (if any) lies between e[1] and e[4]
   // r and ϕ first: the host API copies them back while the (much longer) Kt assembly is still running
-  if (!p->fused_last) CK(launch_k3(asm_args(p, field), p->stream));
+  CK(launch_k3(asm_args(p, field), p->stream));
   CK(launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, p->stream));
   CK(cudaEventRecord(p->ev_r_ready, p->stream));
-  if (!p->fused_last && p->fused_mode_last != 2 && want_K) {
+  if (want_K) {
     if (p->sorted_last) {
       if (p->n_own_sorted < p->ne) {
         const long long kw = (long long)n_pair_blocks(p->N) * p->D * p->D;
@@ -1025,7 +908,7 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   if (ev) CK(cudaEventRecord(ev->e[2], p->stream));
   if (ev) CK(cudaEventRecord(ev->e[3], p->stream));
   if (p->prof) {
-    if (!p->fused_last) p->prof_launches[AD4SM_PROF_ASSEMBLE] += want_K ? 2 : 1;
+    p->prof_launches[AD4SM_PROF_ASSEMBLE] += want_K ? 2 : 1;
     p->prof_launches[AD4SM_PROF_REDUCE] += 2;
   }
   p->ev_cur = nullptr;
@@ -1070,21 +953,14 @@ int ad4sm_staging_view_get(ad4sm_plan* p, int32_t field, ad4sm_staging_view* v) 
 int ad4sm_set_option(ad4sm_plan* p, int32_t option, int64_t value) {
   if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
   switch (option) {
-    case AD4SM_OPT_FUSED: p->fuse_allowed = value != 0; return AD4SM_OK;
     case AD4SM_OPT_SORTED: p->sorted_on = value != 0; return AD4SM_OK;
     case AD4SM_OPT_PEER_PUSH: p->push_opt = value != 0; return AD4SM_OK;
-    case AD4SM_OPT_FUSED_LAG:
-      if (value < 1 || value > 64) return fail(AD4SM_EINVAL, "lag must be in 1..64");
-      p->fz.lag = (int)value;
-      return AD4SM_OK;
   }
   return fail(AD4SM_EINVAL, "unknown option");
 }
 int ad4sm_get_info(ad4sm_plan* p, int32_t what, int64_t* value) {
   if (!p || !value) return fail(AD4SM_EINVAL, "plan or value is NULL");
   switch (what) {
-    case AD4SM_INFO_FUSED: *value = (p->fz.enabled || p->batch_rec) ? (p->fuse_allowed ? 2 : 1) : 0; return AD4SM_OK;
-    case AD4SM_INFO_FUSED_STEPS: *value = p->fz.n_steps; return AD4SM_OK;
     case AD4SM_INFO_SORTED: *value = p->sorted_built ? (p->sorted_on ? 2 : 1) : 0; return AD4SM_OK;
   }
   return fail(AD4SM_EINVAL, "unknown info id");
@@ -1360,8 +1236,6 @@ static int assemble_duals_impl(ad4sm_plan* p, const void* Phi, int64_t stride, b
   if (sorted && launch_halo_scatter(p->Ke, p->cpos, p->C, 0, p->n_own_sorted, n_pair_blocks(p->N), s) != cudaSuccess)
     return done(fail(AD4SM_ENODEV, "staging scatter launch failed"));
   p->ev_cur = nullptr;
-  p->fused_last = false;
-  p->fused_mode_last = 0;
   p->sorted_last = sorted;
   const int mode = want_K ? MODE_ELASTIC : MODE_PHI_R;
   p->elements_mode = mode;
@@ -1607,6 +1481,177 @@ int ad4sm_newton_view_get(ad4sm_plan* p, int32_t field, ad4sm_newton_view* v) {
   v->norms_dev = w.norms;
   v->colptr_ff_dev = (const int64_t*)w.colptr_ff;
   v->rowval_ff_dev = (const int64_t*)w.rowval_ff;
+  return AD4SM_OK;
+}
+
+// ---- the partitioned evaluation behind the C ABI (NCCL inside the library; plumbing in dist.cu) ------------------------
+int ad4sm_dist_unique_id(void* id_out) {
+  if (!id_out) return fail(AD4SM_EINVAL, "id_out is NULL");
+  std::string err;
+  if (dist_unique_id(id_out, &err)) return fail(AD4SM_ENCCL, err);
+  return AD4SM_OK;
+}
+
+int ad4sm_dist_init(int32_t nranks, int32_t rank, const void* nccl_id, int32_t device, ad4sm_dist** comm_out) {
+  if (!comm_out) return fail(AD4SM_EINVAL, "comm_out is NULL");
+  *comm_out = nullptr;
+  if (nranks < 1 || rank < 0 || rank >= nranks || !nccl_id) return fail(AD4SM_EINVAL, "bad rank / nranks / id");
+  int dev = device;
+  if (dev < 0) CK(cudaGetDevice(&dev));
+  CK(cudaSetDevice(dev));
+  std::string err;
+  DistComm* c = dist_comm_init(nranks, rank, nccl_id, dev, &err);
+  if (!c) return fail(AD4SM_ENCCL, err);
+  *comm_out = new ad4sm_dist{c, dev};
+  return AD4SM_OK;
+}
+
+void ad4sm_dist_destroy(ad4sm_dist* comm) {
+  if (!comm) return;
+  cudaSetDevice(comm->device);
+  dist_comm_destroy(comm->c);
+  delete comm;
+}
+
+int ad4sm_dist_attach(ad4sm_plan* p, ad4sm_dist* comm, int32_t n_peers, const ad4sm_dist_peer* peers) {
+  if (!p || !comm) return fail(AD4SM_EINVAL, "plan or comm is NULL");
+  if (n_peers < 0 || (n_peers && !peers)) return fail(AD4SM_EINVAL, "bad peer list");
+  if (comm->device != p->device) return fail(AD4SM_EINVAL, "communicator and plan live on different devices");
+  if (p->batches.empty() || p->batches[0].halo) return fail(AD4SM_EINVAL, "the first batch of a partitioned plan must be the rank's own elements");
+  for (size_t b = 1; b < p->batches.size(); b++)
+    if (!p->batches[b].halo) return fail(AD4SM_EINVAL, "ad4sm_dist_attach needs a plan of one own batch followed by HALO batches");
+  CK(cudaSetDevice(p->device));
+  const long long n_own = p->batches[0].k.ne;
+  const int nranks = dist_comm_size(comm->c), me = dist_comm_rank(comm->c);
+  // export rows: one per own element some neighbour needs, numbered in (peer, list) order so that a partition whose
+  // interface elements each go to one neighbour (slabs) sends every list in place
+  std::vector<int> xmap(n_own, -1);
+  long long n_export = 0;
+  std::vector<std::vector<long long>> rows_x(n_peers), rows_s(n_peers);
+  for (int i = 0; i < n_peers; i++) {
+    const ad4sm_dist_peer& P = peers[i];
+    if (P.rank < 0 || P.rank >= nranks || P.rank == me) return fail(AD4SM_EINVAL, "peer rank out of range");
+    if (P.n_send < 0 || P.n_recv < 0 || (P.n_send && !P.send_slots)) return fail(AD4SM_EINVAL, "bad peer send list");
+    if (P.n_recv && (P.recv_first_slot < n_own || P.recv_first_slot + P.n_recv > p->ne))
+      return fail(AD4SM_EINVAL, "peer receive range outside the plan's HALO slots");
+    for (long long k = 0; k < P.n_send; k++) {
+      const long long sl = P.send_slots[k];
+      if (sl < 0 || sl >= n_own) return fail(AD4SM_EINVAL, "send slot outside the plan's own elements");
+      if (xmap[sl] < 0) xmap[sl] = (int)n_export++;
+      rows_x[i].push_back(xmap[sl]);
+      rows_s[i].push_back(sl);
+    }
+  }
+  p->dpeers.clear();
+  p->dcomm = comm;
+  p->n_export = n_export;
+  const long long kw = (long long)n_pair_blocks(p->N) * p->D * p->D, rw = (long long)p->N * p->D;  // widest field (u)
+  int rc = 0;
+  if (!p->allphi) rc = dev_alloc(p, &p->allphi, (size_t)nranks);
+  if (!rc && !p->phi_local) rc = dev_alloc(p, &p->phi_local, 1);
+  if (!rc && p->sorted_built && n_export > 0) {
+    rc = dev_upload(p, &p->xmap, xmap.data(), xmap.size());
+    if (!rc) rc = dev_alloc(p, &p->xke, (size_t)(n_export * kw));
+    if (!rc) rc = dev_alloc(p, &p->xre, (size_t)(n_export * rw));
+  }
+  if (rc) return rc;
+  auto contiguous = [](const std::vector<long long>& v) -> long long {
+    for (size_t k = 1; k < v.size(); k++)
+      if (v[k] != v[0] + (long long)k) return -1;
+    return v.empty() ? 0 : v[0];
+  };
+  for (int i = 0; i < n_peers; i++) {
+    ad4sm_plan::DistPeer d;
+    d.rank = peers[i].rank;
+    d.n_send = peers[i].n_send;
+    d.recv_first = peers[i].recv_first_slot;
+    d.n_recv = peers[i].n_recv;
+    d.first_x = contiguous(rows_x[i]);
+    d.first_s = contiguous(rows_s[i]);
+    if (d.n_send && (d.first_x < 0 || d.first_s < 0)) {
+      rc = dev_upload(p, &d.rows_x, rows_x[i].data(), rows_x[i].size());
+      if (!rc) rc = dev_upload(p, &d.rows_s, rows_s[i].data(), rows_s[i].size());
+      if (!rc) rc = dev_alloc(p, &d.ske, (size_t)(d.n_send * kw));
+      if (!rc) rc = dev_alloc(p, &d.sre, (size_t)(d.n_send * rw));
+      if (rc) return rc;
+    }
+    p->dpeers.push_back(d);
+  }
+  p->dist_aware = true;   // the element stage may use the destination-sorted staging: the exported rows are materialised apart
+  p->n_xr = 0;
+  p->n_xr_local = 0;
+  p->push_mode = false;
+  return AD4SM_OK;
+}
+
+// element stage -> grouped neighbour exchange -> assembly -> ϕ all-gather + rank-ordered sum, all on the plan's stream
+static int dist_eval_stages(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (!p->dcomm) return fail(AD4SM_ESTATE, "ad4sm_dist_eval before ad4sm_dist_attach");
+  int rc = eval_elements_impl(p, mode, u_dev, d_dev, hist_dev, false);
+  if (rc) return rc;
+  const int DB = mode == MODE_PF_D ? 1 : p->D;
+  const long long kw = (long long)n_pair_blocks(p->N) * DB * DB, rw = (long long)p->N * DB;
+  const bool want_K = mode != MODE_PHI_R;
+  const bool from_x = p->sorted_last && p->xmap;   // K1 wrote the exported rows into xke / xre
+  cudaStream_t s = p->stream;
+  std::vector<DistXfer> xf;
+  for (ad4sm_plan::DistPeer& d : p->dpeers) {
+    if (d.n_send) {
+      const double* kbase = from_x ? p->xke : p->Ke;
+      const double* rbase = from_x ? p->xre : p->re;
+      const long long first = from_x ? d.first_x : d.first_s;
+      double *ksend, *rsend;
+      if (first >= 0) {
+        ksend = const_cast<double*>(kbase) + first * kw;
+        rsend = const_cast<double*>(rbase) + first * rw;
+      } else {
+        const long long* rows = from_x ? d.rows_x : d.rows_s;
+        if (want_K) CK(launch_gather_rows(kbase, rows, d.n_send, (int)kw, d.ske, s));
+        CK(launch_gather_rows(rbase, rows, d.n_send, (int)rw, d.sre, s));
+        ksend = d.ske;
+        rsend = d.sre;
+      }
+      if (want_K) xf.push_back({1, d.rank, ksend, (size_t)(d.n_send * kw)});
+      xf.push_back({1, d.rank, rsend, (size_t)(d.n_send * rw)});
+    }
+    if (d.n_recv) {
+      if (want_K) xf.push_back({0, d.rank, p->Ke + d.recv_first * kw, (size_t)(d.n_recv * kw)});
+      xf.push_back({0, d.rank, p->re + d.recv_first * rw, (size_t)(d.n_recv * rw)});
+    }
+  }
+  std::string err;
+  if (!xf.empty() && dist_exchange(p->dcomm->c, (int)xf.size(), xf.data(), s, &err)) return fail(AD4SM_ENCCL, err);
+  rc = ad4sm_eval_assemble_device(p, mode);
+  if (rc) return rc;
+  // ϕ: this rank's partial (phi_dev) -> all ranks -> summed in rank order, back into phi_dev (the global ϕ)
+  const int nranks = dist_comm_size(p->dcomm->c);
+  CK(cudaMemcpyAsync(p->phi_local, p->phi_dev, sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (dist_allgather(p->dcomm->c, p->phi_local, p->allphi, 1, s, &err)) return fail(AD4SM_ENCCL, err);
+  CK(launch_phi_rank_sum(p->allphi, nranks, p->phi_dev, s));
+  return AD4SM_OK;
+}
+
+int ad4sm_dist_eval_device(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
+  return dist_eval_stages(p, mode, u_dev, d_dev, hist_dev);
+}
+
+int ad4sm_dist_eval(ad4sm_plan* p, int32_t mode, const double* u, const double* d, double* phi_global, double* r_local) {
+  int rc = upload_inputs(p, mode, u, d, nullptr);
+  if (rc) return rc;
+  const bool needs_d = (mode == MODE_PF_U || mode == MODE_PF_D);
+  p->h2d_active = p->n_h2d > 0;
+  rc = dist_eval_stages(p, mode, p->u_dev, needs_d ? p->d_dev : nullptr, nullptr);
+  p->h2d_active = false;
+  if (rc) {
+    if (p->n_h2d > 0) cudaStreamSynchronize(p->copy_stream);
+    return rc;
+  }
+  const int field = mode == MODE_PF_D ? AD4SM_FIELD_D : AD4SM_FIELD_U;
+  rc = download_phi_r(p, field, nullptr, r_local);   // r leaves on the copy stream while Kt is still being assembled
+  if (rc) return rc;
+  if (phi_global) CK(cudaMemcpyAsync(phi_global, p->phi_dev, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
   return AD4SM_OK;
 }
 

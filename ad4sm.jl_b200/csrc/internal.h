@@ -39,26 +39,6 @@ struct AsmArgs {
 };
 constexpr int CBLK3 = 10;       // doubles per 3x3 contribution block: 9 + 1 pad = 80 B, 16-byte aligned
 
-// Work lists of the FUSED persistent kernel (K1 + K2 + K3 in one launch, DESIGN.md "Fused path").  The element groups a
-// warp processes in its iteration `it` form "step" it; a node-pair block / residual row becomes ready when the last
-// step that contributes to it has been published in `done`.  Blocks and rows are listed sorted by that step.
-struct FuseArgs {
-  int enabled, lag, n_steps, pad;
-  long long gstep;             // element groups per step = grid * warps per CTA of the launch the lists were built for
-  long long n_groups;          // element groups of the batch
-  unsigned* done;              // [n_steps] number of groups of each step whose staging is globally visible
-  const unsigned* kb_ptr;      // [n_steps+1] into blk_sorted
-  const unsigned* blk_sorted;  // [n_blocks] block ids by readiness step (stable: ascending block id inside a step)
-  const unsigned* kr_ptr;      // [n_steps+1] into row_sorted
-  const unsigned* row_sorted;  // [n_nodes] node ids by readiness step
-  // enabled == 2: destination-sorted staging.  Consecutive node pairs are grouped into batches whose contribution
-  // blocks are one contiguous range (<= FUSE_BATCH_BLOCKS); batches are listed in pair order, which is also their
-  // (prefix-max) readiness order.
-  const uint4* batch_rec;      // [n_batches] {first pair, end pair, first contribution, end contribution}
-  const unsigned* sb_ptr;      // [n_steps+1] batches that become ready with each step
-};
-constexpr int FUSE_BATCH_PAIRS = 64, FUSE_BATCH_BLOCKS = 160;
-
 // One K1 launch = one batch (SoA copy of a Vector{CEElem}/Vector{CPElem}, elements.jl:71-111).
 struct K1Args {
   MatDev mat;
@@ -91,19 +71,20 @@ struct K1Args {
     double* ke;  // peer Ke + remote_first_slot * width, i.e. indexed by (slot - first)
     double* re;
   } xr[4];
-  // fused assembly (fz.enabled): the persistent kernel also runs K2/K3 over `as`
-  FuseArgs fz;
-  AsmArgs as;
+  // general export map (in-library partitioned evaluation, ad4sm_dist_attach): own slot -> row of the element-major export
+  // buffers xke / xre, or -1; nullptr = nothing to export this way
+  const int* xmap;
+  double* xke;
+  double* xre;
 };
 
-// launch shape of the persistent K1 for a batch (shared by the launcher and the fused work-list builder)
+// launch shape of the persistent K1 for a batch
 struct K1Config {
   int persistent;  // 0: thread-per-element kernel (one Gauss point)
   int EW;          // elements per warp iteration
   int warps;       // warps per CTA
   int grid;        // CTAs
   int staged;      // blocks/residual leave through the shared-memory staging + bulk stores
-  int rec_bytes;   // bytes of the per-warp record area (landing buffer of the fused K2s batches)
 };
 bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c);
 
@@ -127,6 +108,26 @@ cudaError_t launch_dropzeros(long long n_dof, const long long* colptr, const lon
                              size_t cub_tmp_bytes, cudaStream_t s);
 size_t dropzeros_tmp_bytes(long long n_dof);
 cudaError_t launch_fp64_peak(double* tflops, double* mhz);
+
+// ---- NCCL plumbing of the partitioned evaluation (dist.cu) ---------------------------------------------------------
+struct DistComm;
+struct DistXfer {
+  int send, peer;   // send != 0: ncclSend, else ncclRecv
+  double* buf;
+  size_t count;     // doubles
+};
+}  // namespace ad4sm
+#include <string>
+namespace ad4sm {
+int dist_unique_id(void* out, std::string* err);
+DistComm* dist_comm_init(int nranks, int rank, const void* id_bytes, int device, std::string* err);
+void dist_comm_destroy(DistComm* c);
+int dist_comm_size(const DistComm* c);
+int dist_comm_rank(const DistComm* c);
+int dist_exchange(DistComm* c, int n, const DistXfer* x, cudaStream_t s, std::string* err);
+int dist_allgather(DistComm* c, const double* src, double* dst, size_t count, cudaStream_t s, std::string* err);
+cudaError_t launch_gather_rows(const double* src, const long long* rows, long long n_rows, int width, double* dst, cudaStream_t s);
+cudaError_t launch_phi_rank_sum(const double* allphi, int n, double* out, cudaStream_t s);
 
 // ---- Newton-step glue (newton.cu; solvers.jl:183-184, 211-224, 257-291) ----------------------------------------------
 struct NewtonArgs {

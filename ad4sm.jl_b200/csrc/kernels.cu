@@ -100,6 +100,7 @@ __device__ __forceinline__ void bulk_store(void* dst, unsigned src, unsigned byt
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -153,7 +154,7 @@ static WarpLayout k1p_layout(int D, int N, int P, int LP, bool pf) {
   L.psi_off = off;
   off += rup(EW * P * 8, 16);
   L.bar_off = off;
-  off += 48;  // 5 mbarriers (the fifth: fused K2s batches), padded to 16 bytes
+  off += 32;  // 4 mbarriers
   L.bytes = rup(off, 128);
   // epilogue: the element blocks and residual are staged in the (dead) record region when they fit, and leave
   // with one bulk copy each (16-byte granularity)
@@ -168,7 +169,7 @@ static WarpLayout k1p_layout(int D, int N, int P, int LP, bool pf) {
   return L;
 }
 
-// ---- assembly of one node-pair block / one residual entry (shared by K2/K3 and the fused persistent kernel) ----------
+// ---- assembly of one node-pair block / one residual entry (K2 / K3) ----------
 // Sums the DB x DB source blocks of node-pair block `blk` in `elems` order (left fold, like Julia's sparse(),
 // toolkit:202) and writes DB rows of dpn consecutive values into CSC columns / CSR rows (i, 0..dpn-1).
 // CG: read the staging with ld.global.cg (L2 only) -- required when it was written earlier in the same kernel.
@@ -237,17 +238,6 @@ template <bool CG> __device__ __forceinline__ void assemble_r_entry(const AsmArg
     }
   }
   a.r[i * a.dpn + j] = acc;
-}
-
-// ---- fused path: inter-warp publication of finished steps ---------------------------------------------------------
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ---- phase 1 of the persistent K1: one Gauss point per lane ----------------------------------------------
@@ -413,6 +403,14 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
             for (int j = 0; j < D; j++) (a.xr[x].re + k * (long long)(N * D))[q * D + j] = rq[j];
           }
         }
+        if (a.xmap) {  // general partition: this element's row of the export buffers, if a peer owns some of its nodes
+          const long long k = __ldg(a.xmap + slot);
+          if (k >= 0) {
+            column_u_store<D, N>(q, acc, a.xke + k * (long long)(n_pair_blocks(N) * DD));
+#pragma unroll
+            for (int j = 0; j < D; j++) (a.xre + k * (long long)(N * D))[q * D + j] = rq[j];
+          }
+        }
       }
       if (kout_s) bulk_commit();
     }
@@ -433,129 +431,8 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
   }
 }
 
-// ---- fused path: this warp's share of the K2/K3 work that became ready with step t -------------------------------
-// Waits (lane 0 polls, then the warp syncs) until every step <= t has been published by all warps that own element
-// groups in it; a warp only ever waits for steps that precede, in every warp's program order, the K1 work still
-// ahead of it, so with all CTAs co-resident (one per SM) there is no cycle.
-template <int D>
-__device__ __forceinline__ void fused_assemble_step(const K1Args& a, int t, int gwarp, int n_warps, int lane, int& verified,
-                                                    int& nzero) {
-  if (t >= a.fz.n_steps) return;
-  while (verified <= t) {
-    if (lane == 0) {
-      const long long first = (long long)verified * a.fz.gstep;
-      long long left = a.fz.n_groups - first;
-      const unsigned target = (unsigned)(left < a.fz.gstep ? left : a.fz.gstep);
-      const unsigned* flag = a.fz.done + verified;
-      while (ld_acquire(flag) < target) __nanosleep(64);
-    }
-    __syncwarp();
-    verified++;
-  }
-  // node-pair blocks
-  {
-    const unsigned b0 = __ldg(a.fz.kb_ptr + t), b1 = __ldg(a.fz.kb_ptr + t + 1);
-    const unsigned cnt = b1 - b0, chunk = (cnt + n_warps - 1) / n_warps;
-    unsigned j0 = b0 + (unsigned)gwarp * chunk, j1 = j0 + chunk;
-    if (j1 > b1) j1 = b1;
-    for (unsigned j = j0 + lane; j < j1; j += 32) nzero += assemble_block<D, true>(a.as, (long long)__ldg(a.fz.blk_sorted + j));
-  }
-  // residual rows
-  {
-    const unsigned r0 = __ldg(a.fz.kr_ptr + t), r1 = __ldg(a.fz.kr_ptr + t + 1);
-    const unsigned cnt = r1 - r0, chunk = (cnt + n_warps - 1) / n_warps;
-    unsigned j0 = r0 + (unsigned)gwarp * chunk, j1 = j0 + chunk;
-    if (j1 > r1) j1 = r1;
-    const int dpn = a.as.dpn;
-    for (unsigned j = j0 * dpn + lane; j < j1 * dpn; j += 32) {
-      const unsigned row = j / dpn;
-      assemble_r_entry<true>(a.as, (long long)__ldg(a.fz.row_sorted + row), (int)(j - row * dpn));
-    }
-  }
-}
-
-__device__ __forceinline__ void k2s_add(double* acc, const double2* B);
-// ---- fused path, destination-sorted staging: this warp's batches of node pairs that became ready with step t -------
-// A batch's contribution blocks are one contiguous range of C: they arrive with ONE bulk copy (TMA) in the warp's
-// record area (dead between phase 2 and the next phase 1) while the lanes fetch their pairs' metadata; then every
-// lane folds its (<= 2) pairs in `elems` order and writes block (i, p) and its mirror -- as K2s does.
-__device__ __forceinline__ void fused_wait_steps(const K1Args& a, int t, int lane, int& verified) {
-  while (verified <= t) {
-    if (lane == 0) {
-      const long long first = (long long)verified * a.fz.gstep;
-      long long left = a.fz.n_groups - first;
-      const unsigned target = (unsigned)(left < a.fz.gstep ? left : a.fz.gstep);
-      const unsigned* flag = a.fz.done + verified;
-      while (ld_acquire(flag) < target) __nanosleep(64);
-    }
-    __syncwarp();
-    verified++;
-  }
-}
-__device__ __forceinline__ void fused_sorted_step(const K1Args& a, int t, int gwarp, int n_warps, int lane, unsigned char* ws,
-                                                  unsigned kbar, unsigned& kphase, int& verified, int& nzero) {
-  if (t >= a.fz.n_steps) return;
-  fused_wait_steps(a, t, lane, verified);
-  const unsigned b0 = __ldg(a.fz.sb_ptr + t), b1 = __ldg(a.fz.sb_ptr + t + 1);
-  const unsigned cnt = b1 - b0, chunk = (cnt + n_warps - 1) / n_warps;
-  unsigned k0 = b0 + (unsigned)gwarp * chunk, k1 = k0 + chunk;
-  if (k1 > b1) k1 = b1;
-  const double2* smc = reinterpret_cast<const double2*>(ws);
-  for (unsigned k = k0; k < k1; k++) {
-    const uint4 rec = __ldg(a.fz.batch_rec + k);  // {p0, p1, c_lo, c_hi}
-    const unsigned bytes = (rec.w - rec.z) * (unsigned)(CBLK3 * 8);
-    if (lane == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(kbar, bytes);
-      tma_load_1d(smem_u32(ws), a.as.C + (long long)rec.z * CBLK3, bytes, kbar);
-    }
-    unsigned c0[2], c1[2], oup[2], olo[2], nn[2];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const unsigned u = rec.x + lane + 32 * h;
-      const bool on = u < rec.y;
-      c0[h] = on ? __ldg(a.as.cptr + u) : 0u;
-      c1[h] = on ? __ldg(a.as.cptr + u + 1) : 0u;
-      oup[h] = on ? __ldg(a.as.out_up + u) : 0u;
-      olo[h] = on ? __ldg(a.as.out_lo + u) : 0u;
-      nn[h] = on ? __ldg(a.as.nn_pack + u) : 0u;
-    }
-    mbar_wait(kbar, kphase);
-    kphase ^= 1u;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      if (rec.x + lane + 32 * h < rec.y) {
-        double acc[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) acc[i] = 0.0;
-        for (unsigned c = c0[h]; c < c1[h]; c++) k2s_add(acc, smc + (c - rec.z) * (CBLK3 / 2));
-        const long long su = 3ll * (nn[h] & 0xffffu), sl = 3ll * (nn[h] >> 16);
-        int nz = 0;
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-#pragma unroll
-          for (int l = 0; l < 3; l++) {
-            a.as.nzval[oup[h] + j * su + l] = acc[j * 3 + l];
-            nz += (acc[j * 3 + l] == 0.0);
-          }
-        if (olo[h] != oup[h]) {
-#pragma unroll
-          for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int l = 0; l < 3; l++) a.as.nzval[olo[h] + l * sl + j] = acc[j * 3 + l];
-          nz *= 2;
-        }
-        nzero += nz;
-      }
-    }
-    __syncwarp();  // the record area is reused by the next batch / the next phase 1
-  }
-}
-
 // ---- K1, u-dual, persistent, LP lanes per element, TMA-staged inputs ------------------------------
-// FUSE: compile the in-kernel assembly (fused modes) in.  Kept out of the default instantiation: the extra code (the
-// kernel grows from ~2 600 to ~8 500 SASS instructions) costs the plain path ~4 % even when it is never executed.
-template <int D, int N, int LP, int MF, bool PF, bool FUSE>
+template <int D, int N, int LP, int MF, bool PF>
 __global__ void __launch_bounds__(256, 1)
     k1_u_kernel(const __grid_constant__ K1Args a, const WarpLayout L, const int warps_per_cta) {
   using R = GpRec<D>;
@@ -571,7 +448,7 @@ __global__ void __launch_bounds__(256, 1)
   const long long gstep = (long long)gridDim.x * warps_per_cta;
   const unsigned bar0 = smem_u32(ws0 + L.bar_off);
   if (lane == 0) {
-    for (int i = 0; i < 5; i++) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < 4; i++) mbar_init(bar0 + 8 * i, 1);
     fence_mbar_init();
   }
   __syncwarp();
@@ -614,12 +491,7 @@ __global__ void __launch_bounds__(256, 1)
     tma_load_1d(smem_u32(ws + (L.n_off + (s) * L.n_stg)), a.nodes + e0 * N, nbytes, bar0 + 16 + 8 * s);
   };
 
-  const bool fused = FUSE && a.fz.enabled == 1;   // element-major staging, K2 + K3 inside the kernel
-  const bool fused2 = FUSE && a.fz.enabled == 2;  // destination-sorted staging, K2s inside the kernel
-  unsigned kphase = 0;
   const int gwarp = blockIdx.x * warps_per_cta + warp;  // global warp id = its first element group
-  int verified = 0;                                      // steps [0, verified) are known to be published (fused path)
-  int nzero = 0, n_it = 0;
   long long grp = gwarp;
   if (grp < n_groups) {
     issue(grp, 0);
@@ -646,23 +518,9 @@ __global__ void __launch_bounds__(256, 1)
     mbar_wait(bar0 + 8 * s, (unsigned)((it >> 1) & 1));                        // this group's ∇N, wgt, N
     if (has_next) mbar_wait(bar0 + 16 + 8 * (s ^ 1), (unsigned)(((it + 1) >> 1) & 1));  // next group's node ids
     cp_async_wait_all();                                                        // this group's u
-    if (a.cpos && a.sorted_tma) {  // sorted staging through per-lane bulk copies
-      if (fused2 && it > 0) bulk_wait_all();  // complete (visible) before the step is published
-      else bulk_wait_read_all();              // their shared-memory source may be overwritten
-    }
-    if (fused2 && it > 0) __threadfence();  // this lane's block stores of step it-1 are visible GPU-wide
-    if (lane == 0) {
-      if (fused && it > 0) {
-        // publish step it-1: its bulk stores are complete (they had a whole iteration), make them visible GPU-wide
-        bulk_wait_all();
-        __threadfence();
-        red_release_add(a.fz.done + (it - 1), 1u);
-      } else {
-        bulk_wait_read_all();  // the previous bulk stores have read the staging area (aliases the records)
-      }
-    }
+    if (a.cpos && a.sorted_tma) bulk_wait_read_all();  // sorted staging through per-lane bulk copies: their shared-memory source may be overwritten
+    if (lane == 0) bulk_wait_read_all();  // the previous bulk stores have read the staging area (aliases the records)
     __syncwarp();
-    if (fused2 && it > 0 && lane == 0) red_release_add(a.fz.done + (it - 1), 1u);  // after every lane's fence
 
     const long long e = grp * EW + el;
     const bool valid = e < a.ne;
@@ -728,54 +586,14 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
     __syncwarp();
-    if constexpr (FUSE) {
-    if (fused && it >= a.fz.lag) fused_assemble_step<D>(a, it - a.fz.lag, gwarp, (int)gstep, lane, verified, nzero);
-    if (fused2 && a.sorted_tma) {  // the record area is about to receive K2s batches: its bulk stores must have read it
-      bulk_wait_read_all();
-      __syncwarp();
-    }
-    if (fused2 && it >= a.fz.lag)
-      fused_sorted_step(a, it - a.fz.lag, gwarp, (int)gstep, lane, ws, bar0 + 32, kphase, verified, nzero);
-    }
-    n_it = it + 1;
   }
-  if (a.cpos && a.sorted_tma) {
-    if (fused2) bulk_wait_all();
-    else bulk_wait_read_all();
-  }
-  if (fused2 && n_it > 0) {
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) red_release_add(a.fz.done + (n_it - 1), 1u);
-  }
+  if (a.cpos && a.sorted_tma) bulk_wait_read_all();
   if (lane == 0) {
-    if (fused && n_it > 0) {
-      bulk_wait_all();
-      __threadfence();
-      red_release_add(a.fz.done + (n_it - 1), 1u);
-    } else if (a.n_xr) {
+    if (a.n_xr) {
       bulk_wait_all();  // peer stores must be complete, not only read, when the kernel ends
       __threadfence_system();
     } else {
       bulk_wait_read_all();  // shared memory must outlive the last bulk stores
-    }
-  }
-  if constexpr (FUSE) {
-    if (fused) {  // the steps this warp has not assembled yet (its last `lag` ones, and any it had no elements in)
-      __syncwarp();
-      int t = n_it - a.fz.lag;
-      if (t < 0) t = 0;
-      for (; t < a.fz.n_steps; t++) fused_assemble_step<D>(a, t, gwarp, (int)gstep, lane, verified, nzero);
-      for (int o = 16; o > 0; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
-      if (lane == 0 && nzero) atomicAdd(a.as.n_zero, (unsigned long long)nzero);
-    }
-    if (fused2) {
-      __syncwarp();
-      int t = n_it - a.fz.lag;
-      if (t < 0) t = 0;
-      for (; t < a.fz.n_steps; t++) fused_sorted_step(a, t, gwarp, (int)gstep, lane, ws, bar0 + 32, kphase, verified, nzero);
-      for (int o = 16; o > 0; o >>= 1) nzero += __shfl_xor_sync(0xffffffffu, nzero, o);
-      if (lane == 0 && nzero) atomicAdd(a.as.n_zero, (unsigned long long)nzero);
     }
   }
 }
@@ -806,6 +624,127 @@ template <int D, int N, int MF, bool PF> __global__ void __launch_bounds__(K1_TH
 #pragma unroll
   for (int q = 0; q < N; q++) column_u<D, N, 1, ScalarMem>(q, 1, rec, 0, G, 0, N, Ke, re);  // G is [k][a]
   a.phie[slot] = rec[R::OFF_PSI];
+}
+
+
+// ---- K1, u-dual, one thread per element (P == 1), warp-cooperative output ------------------------------------------
+// The thread-per-element kernel above leaves every store to the owning thread: 102 STG.64 per Tet4 element at a lane
+// stride of 720 B, i.e. 32 cache lines per instruction -- the LSU's one-line-per-cycle front end, not DRAM, bounds it
+// (C3: 1.40 ms for 2 M elements).  Here the threads of a warp put their element blocks / residuals into the warp's
+// shared-memory slice (row stride 2 x odd doubles) and the warp copies them out together:
+//   element-major staging: the 32 elements' rows are ONE contiguous range of Ke (and of re): 16-byte chunks, lane-contiguous;
+//   destination-sorted staging (D = 3): every 80-byte block goes to its sorted slot (cpos), 5 consecutive lanes per block.
+// Interface elements of a partitioned run are additionally copied element-major to their export rows (xr / xmap).
+template <int D, int N> struct W1Layout {
+  static constexpr int DD = D * D, NPB = N * (N + 1) / 2, KW = NPB * DD, RW = N * D;
+  static constexpr int OS0 = KW + RW;
+  static constexpr int OS = (OS0 % 2) ? OS0 + 1 : (((OS0 / 2) % 2) ? OS0 : OS0 + 2);  // even, OS/2 odd
+  static constexpr int WARPS = 4;
+  static constexpr size_t BYTES = (size_t)WARPS * 32 * OS * sizeof(double);
+};
+template <int D, int N, int MF, bool PF>
+__global__ void __launch_bounds__(128) k1_u_kernel_w1(const __grid_constant__ K1Args a) {
+  using R = GpRec<D>;
+  using L = W1Layout<D, N>;
+  constexpr int DD = L::DD, NPB = L::NPB, KW = L::KW, RW = L::RW, OS = L::OS;
+  extern __shared__ __align__(16) double smw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long e0 = ((long long)blockIdx.x * L::WARPS + warp) * 32;
+  if (e0 >= a.ne) return;  // whole warp; no CTA-wide barrier below
+  const int cnt = (int)((a.ne - e0) < 32 ? (a.ne - e0) : 32);
+  double* ws = smw + (size_t)warp * 32 * OS;
+  double* row = ws + (size_t)lane * OS;
+  const long long e = e0 + lane;
+  const bool valid = lane < cnt;
+  if (valid) {
+    int nd[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) nd[n] = __ldg(a.nodes + e * N + n);
+    double G[D * N], ue[N * D], de[N], Nv[N];
+    load_gp_inputs<D, N>(a, e, 0, G, ue, nd);
+    if (PF) {
+#pragma unroll
+      for (int n = 0; n < N; n++) {
+        de[n] = __ldg(a.dfield + nd[n]);
+        Nv[n] = __ldg(a.Nval + e * N + n);
+      }
+    }
+    __align__(16) double rec[R::SIZE + 1];
+    gauss_point_u<D, N, MF, PF>(a.mat, G, ue, de, Nv, __ldg(a.wgt + e), rec);
+#pragma unroll
+    for (int q = 0; q < N; q++) column_u<D, N, 1, ScalarMem>(q, 1, rec, 0, G, 0, N, a.want_K ? row : nullptr, row + KW);  // G is [k][a]
+    a.phie[a.slot0 + e] = rec[R::OFF_PSI];
+  }
+  __syncwarp();
+  const long long slot_w = a.slot0 + e0;
+  // residual rows: contiguous [cnt][RW]
+  {
+    double* dst = a.re + slot_w * (long long)RW;
+    if constexpr (RW % 2 == 0) {
+      for (int c = lane; c < cnt * (RW / 2); c += 32) {
+        const int el = c / (RW / 2), w = c - el * (RW / 2);
+        reinterpret_cast<double2*>(dst)[c] = *reinterpret_cast<const double2*>(ws + (size_t)el * OS + KW + 2 * w);
+      }
+    } else {
+      for (int c = lane; c < cnt * RW; c += 32) {
+        const int el = c / RW, w = c - el * RW;
+        dst[c] = ws[(size_t)el * OS + KW + w];
+      }
+    }
+  }
+  if (!a.want_K) return;
+  if (a.cpos) {  // destination-sorted staging (D == 3): block b of element el -> C[cpos >> 1], 5 x 16 bytes
+    if constexpr (D == 3) {
+      const unsigned* cp = a.cpos + slot_w * (long long)NPB;
+      for (int c = lane; c < cnt * NPB * 5; c += 32) {
+        const int eb = c / 5, t = c - eb * 5;  // eb = el * NPB + b
+        const int el = eb / NPB, b = eb - el * NPB;
+        const unsigned code = __ldg(cp + eb);
+        const double* src = ws + (size_t)el * OS + b * 9 + 2 * t;
+        const double v0 = src[0];
+        const double v1 = t < 4 ? src[1] : ((code & 1u) ? 1.0 : 0.0);  // 10th double: "stored transposed" (K2s flips it)
+        reinterpret_cast<double2*>(a.C + (long long)(code >> 1) * CBLK3)[t] = make_double2(v0, v1);
+      }
+    }
+  } else {  // element-major staging: contiguous [cnt][KW]
+    double* dst = a.Ke + slot_w * (long long)KW;
+    if constexpr (KW % 2 == 0) {
+      for (int c = lane; c < cnt * (KW / 2); c += 32) {
+        const int el = c / (KW / 2), w = c - el * (KW / 2);
+        reinterpret_cast<double2*>(dst)[c] = *reinterpret_cast<const double2*>(ws + (size_t)el * OS + 2 * w);
+      }
+    } else {
+      for (int c = lane; c < cnt * KW; c += 32) {
+        const int el = c / KW, w = c - el * KW;
+        dst[c] = ws[(size_t)el * OS + w];
+      }
+    }
+  }
+  // interface elements of a partitioned run on the sorted path: element-major copies for the owner ranks
+  if (a.cpos && (a.n_xr || a.xmap)) {
+    for (int el = 0; el < cnt; el++) {
+      const long long slot = slot_w + el;
+      double *ke = nullptr, *re = nullptr;
+      for (int x = 0; x < a.n_xr; x++) {
+        const long long k = slot - a.xr[x].first;
+        if (k >= 0 && k < a.xr[x].count) {
+          ke = a.xr[x].ke + k * (long long)KW;
+          re = a.xr[x].re + k * (long long)RW;
+        }
+      }
+      if (!ke && a.xmap) {
+        const long long k = __ldg(a.xmap + slot);
+        if (k >= 0) {
+          ke = a.xke + k * (long long)KW;
+          re = a.xre + k * (long long)RW;
+        }
+      }
+      if (ke) {
+        for (int w = lane; w < KW; w += 32) ke[w] = ws[(size_t)el * OS + w];
+        for (int w = lane; w < RW; w += 32) re[w] = ws[(size_t)el * OS + KW + w];
+      }
+    }
+  }
 }
 
 // ---- K1, d-dual (makeϕrKt_d) -----------------------------------------------------------------------
@@ -916,7 +855,7 @@ bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c) {
   if (!lanes_for(D, N, P, LP)) return false;
   c->persistent = LP > 1;
   c->EW = 32 / LP;
-  c->warps = c->grid = c->staged = c->rec_bytes = 0;
+  c->warps = c->grid = c->staged = 0;
   if (LP == 1) return true;
   const WarpLayout L = k1p_layout(D, N, P, LP, pf);
   int warps = (227 * 1024) / L.bytes;
@@ -934,14 +873,26 @@ bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c) {
   c->warps = warps;
   c->grid = (int)grid;
   c->staged = L.kout_el != 0;
-  c->rec_bytes = c->EW * L.rec_el;
   return true;
 }
 
 template <int D, int N, int LP, int MF, bool PF> static cudaError_t launch_u_t(const K1Args& a, cudaStream_t s) {
   if constexpr (LP == 1) {
-    const unsigned grid = (unsigned)((a.ne + K1_THREADS - 1) / K1_THREADS);
-    k1_u_kernel_t1<D, N, MF, PF><<<grid, K1_THREADS, 0, s>>>(a);
+    const char* t1e = getenv("AD4SM_K1_T1");  // 1: the round-1 kernel (per-thread stores; element-major staging only)
+    const int t1 = t1e ? atoi(t1e) : 0;
+    if (t1 && !a.cpos) {
+      const unsigned grid = (unsigned)((a.ne + K1_THREADS - 1) / K1_THREADS);
+      k1_u_kernel_t1<D, N, MF, PF><<<grid, K1_THREADS, 0, s>>>(a);
+      return cudaGetLastError();
+    }
+    using WL = W1Layout<D, N>;
+    auto kern = k1_u_kernel_w1<D, N, MF, PF>;
+    if (WL::BYTES > 48 * 1024) {
+      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WL::BYTES);
+      if (err != cudaSuccess) return err;
+    }
+    const long long per_cta = 32ll * WL::WARPS;
+    kern<<<(unsigned)((a.ne + per_cta - 1) / per_cta), 32 * WL::WARPS, WL::BYTES, s>>>(a);
     return cudaGetLastError();
   } else {
     K1Config c;
@@ -949,22 +900,9 @@ template <int D, int N, int LP, int MF, bool PF> static cudaError_t launch_u_t(c
     const WarpLayout L = k1p_layout(D, N, a.P, LP, PF);
     const int smem_max = 227 * 1024;
     const size_t smem = (size_t)c.warps * L.bytes;
-    constexpr bool CAN_FUSE = (D == 3 && N == 8 && !PF);  // the in-kernel assembly is compiled for Hex8 elastic only
-    if (a.fz.enabled) {
-      if constexpr (!CAN_FUSE) return cudaErrorInvalidValue;
-    }
-    auto kern = (a.fz.enabled && CAN_FUSE) ? k1_u_kernel<D, N, LP, MF, PF, CAN_FUSE> : k1_u_kernel<D, N, LP, MF, PF, false>;
+    auto kern = k1_u_kernel<D, N, LP, MF, PF>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err != cudaSuccess) return err;
-    if (a.fz.enabled) {
-      // the fused kernel's warps wait on one another: all CTAs must be co-resident -> cooperative launch
-      if (a.fz.gstep != (long long)c.grid * c.warps || !a.want_K) return cudaErrorInvalidValue;
-      if (a.fz.enabled == 1 && !c.staged) return cudaErrorInvalidValue;
-      if (a.fz.enabled == 2 && (!a.cpos || D != 3)) return cudaErrorInvalidValue;
-      int warps = c.warps;
-      void* args[] = {(void*)&a, (void*)&L, (void*)&warps};
-      return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)c.grid), dim3((unsigned)(c.warps * 32)), args, smem, s);
-    }
     kern<<<(unsigned)c.grid, c.warps * 32, smem, s>>>(a, L, c.warps);
     return cudaGetLastError();
   }

@@ -237,6 +237,77 @@ class GpuBackend:
         return _wrap(self.torch, v.r_dev, (v.n_dof,))
 
 
+class LibDistPlan:
+    """Partitioned `makeϕrKt` with the whole exchange INSIDE the library (ad4sm_dist_*: NCCL bound by the library itself,
+    no torch.distributed on the data path).  This is the path a Julia / C host uses; Python only bootstraps it:
+    `share_id(bytes_or_None) -> bytes` must hand rank 0's 128-byte NCCL id to every rank (MPI bcast, a file, or -- here
+    -- torch.distributed.broadcast_object_list)."""
+
+    def __init__(self, own_batch, halo_nodes_local, part, dofs_per_node, share_id, device=-1, mode=None, **plan_opts):
+        import ctypes as C
+        from . import Elements as El, _capi as capi
+        self.capi, self.part = capi, part
+        self.mode = capi.MODE_ELASTIC if mode is None else mode
+        L = capi.lib()
+        batches = [own_batch]
+        own_batch.orig_index = np.ascontiguousarray(part.own_elems, dtype=np.int64)
+        if len(part.halo_elems):
+            batches.append(El.ElemBatch(own_batch.kind, own_batch.D, halo_nodes_local, None, None, own_batch.mat, None,
+                                        orig_index=np.ascontiguousarray(part.halo_elems, dtype=np.int64), halo=True,
+                                        halo_P=own_batch.P))
+        self.plan = El.Plan(batches, part.n_local_nodes, dofs_per_node, device=device, **plan_opts)
+        self.n_own = own_batch.ne
+        idb = None
+        if part.rank == 0:
+            buf = (C.c_ubyte * capi.NCCL_ID_BYTES)()
+            capi.check(L.ad4sm_dist_unique_id(buf))
+            idb = bytes(buf)
+        idb = share_id(idb)
+        h = C.c_void_p()
+        capi.check(L.ad4sm_dist_init(part.world, part.rank, C.create_string_buffer(idb, capi.NCCL_ID_BYTES), device, C.byref(h)))
+        self._comm = h
+        peers = sorted(set(part.send) | set(part.recv))
+        arr = (capi.DistPeer * max(1, len(peers)))()
+        self._keep = []
+        for i, peer in enumerate(peers):
+            ix = np.ascontiguousarray(part.send.get(peer, np.zeros(0, dtype=np.int64)), dtype=np.int64)
+            self._keep.append(ix)
+            s, c = part.recv.get(peer, (0, 0))
+            arr[i].rank, arr[i].n_send, arr[i].send_slots = peer, len(ix), ix.ctypes.data
+            arr[i].recv_first_slot, arr[i].n_recv = self.n_own + s, c
+        capi.check(L.ad4sm_dist_attach(self.plan._h, h, len(peers), arr))
+
+    def close(self):
+        if self._comm is not None:
+            self.plan.sync()
+            self.capi.lib().ad4sm_dist_destroy(self._comm)
+            self._comm = None
+
+    def step_device(self, u_ptr, d_ptr=None, hist_ptr=None):
+        """asynchronous on the plan's stream; the global ϕ, this rank's r and Kt rows are then in the plan's device view"""
+        import ctypes as C
+        self.capi.check(self.capi.lib().ad4sm_dist_eval_device(self.plan._h, self.mode, C.c_void_p(u_ptr),
+                                                               C.c_void_p(d_ptr) if d_ptr else None,
+                                                               C.c_void_p(hist_ptr) if hist_ptr else None))
+
+    def step_host(self, u_host, r_host, d_host=None):
+        """u (column-major D x nLocalNodes, pinned for overlap) in; returns the global ϕ, fills this rank's r"""
+        import ctypes as C
+        phi = C.c_double()
+        self.capi.check(self.capi.lib().ad4sm_dist_eval(self.plan._h, self.mode, C.c_void_p(u_host.ctypes.data),
+                                                        C.c_void_p(d_host.ctypes.data) if d_host is not None else None,
+                                                        C.byref(phi), C.c_void_p(r_host.ctypes.data)))
+        return phi.value
+
+
+def torch_share_id(idb):
+    """bootstrap helper: broadcast rank 0's NCCL id through an initialised torch.distributed group"""
+    import torch.distributed as D
+    box = [idb]
+    D.broadcast_object_list(box, src=0)
+    return box[0]
+
+
 class _DevArr:
     def __init__(self, ptr, shape):
         self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f8", "data": (int(ptr), False),
@@ -397,6 +468,12 @@ class SlabRunner:
         self.torch = torch
         mat = mat or Ma.NeoHooke(1000.0, 5000.0)
         self.batch, halo_conn, self.part, self.u_local = slab_hex_workload(n, nz_per_rank, rank, world, mat, nz_total=nz_total)
+        self.lib = None
+        if peer_staging == "lib":   # the exchange runs inside the library (ad4sm_dist_*), torch only ships the NCCL id
+            self.lib = LibDistPlan(self.batch, halo_conn, self.part, 3, torch_share_id, device=device)
+            self.plan, self.peer = self.lib.plan, False
+            self.backend = None
+            return
         self.backend = GpuBackend(self.batch, halo_conn, self.part, 3, device=device)
         self.plan = self.backend.plan
         self.dplan = DistPlan(self.backend, self.part)
@@ -406,10 +483,14 @@ class SlabRunner:
             self.peer = self.backend.enable_peer_staging(self.part, push=(peer_staging != "k1"))
 
     def step_device(self, u_dev):
+        if self.lib is not None:
+            return self.lib.step_device(u_dev.data_ptr())
         return self.dplan.step(u_dev)
 
     def step_host(self, u_host_np, r_host_np):
         """end to end: u from pinned host memory -> device, evaluation + exchange, ϕ and this rank's r back to the host"""
+        if self.lib is not None:
+            return self.lib.step_host(u_host_np, r_host_np)   # one C call; it returns when ϕ and r are on the host
         phi = self.dplan.step_host(u_host_np, r_host_np)
         val = float(phi.item())   # synchronises the main stream
         self.plan.sync()          # and the copy stream that carries r

@@ -287,18 +287,32 @@ def parity_check_partitioned(world, rank, local, interface, mat):
     plan1.close()
     p = AD.build_partition(conn, AD.contiguous_elem_ranks(len(conn), world), rank, world)
     own = El.ElemBatch("CE", 3, p.local_conn(conn[p.own_elems]), b.gradN[p.own_elems], b.wgt[p.own_elems], b.mat)
-    be = AD.GpuBackend(own, p.local_conn(conn[p.halo_elems]), p, 3, device=local)
-    if interface != "nccl":
-        be.enable_peer_staging(p, push=(interface == "push"))
-    dp = AD.DistPlan(be, p)
     ul = torch.from_numpy(np.ascontiguousarray(u[:, p.local_nodes - 1].T)).cuda()
+    if interface == "lib":
+        lp = AD.LibDistPlan(own, p.local_conn(conn[p.halo_elems]), p, 3, AD.torch_share_id, device=local)
+        plan = lp.plan
+        plan.set_stream(torch.cuda.current_stream().cuda_stream or 1)
+
+        def run(x):
+            lp.step_device(x.data_ptr())
+            v = plan.device_view()
+            return AD._wrap(torch, v.phi_dev, (1,))[0], AD._wrap(torch, v.r_dev, (v.n_dof,))
+    else:
+        be = AD.GpuBackend(own, p.local_conn(conn[p.halo_elems]), p, 3, device=local)
+        if interface != "nccl":
+            be.enable_peer_staging(p, push=(interface == "push"))
+        dp = AD.DistPlan(be, p)
+        plan = be.plan
+
+        def run(x):
+            return dp.step(x), be.r_tensor()
     ok = 1
     try:
         for f in (0.5, 1.0):   # two evaluations: the second runs on the other receive buffer of the push protocol
-            phi = dp.step(ul * f)
+            phi, r_t = run(ul * f)
         torch.cuda.synchronize()
-        Kt = be.plan.fetch_csc()
-        r = be.r_tensor().cpu().numpy()
+        Kt = plan.fetch_csc()
+        r = r_t.cpu().numpy()
         assert abs(float(phi.item()) - phi0) <= 1e-13 * abs(phi0)
         loc = np.where(p.owned)[0]
         g = p.local_nodes[loc] - 1
@@ -596,6 +610,8 @@ def run_ours(args):
         "config": {"workload": f"{cfg} {conf['name']} {'x'.join(map(str, gdims))} ({ne_total} elements), one makeϕrKt per step",
                    "elements_per_gpu": ne_local, "partition": part,
                    "interface": None if world == 1 else (
+                       "ad4sm_dist_eval: grouped ncclSend/ncclRecv of the staged interface rows + ncclAllGather(ϕ), issued inside the "
+                       "library on the plan's stream" if runner.lib is not None else
                        "copy-engine push of the interface rows into the owner's double-buffered HALO rows over NVLink, overlapped "
                        "with K1, + barrier" if runner.backend.push else
                        "K1 bulk stores into the owner's staging over NVLink peer memory + barrier" if runner.peer else
@@ -685,10 +701,11 @@ def main():
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-e2e-full", action="store_true")
     ap.add_argument("--no-newton", action="store_true")
-    ap.add_argument("--interface", default="push", choices=["nccl", "push", "k1"],
+    ap.add_argument("--interface", default="push", choices=["nccl", "push", "k1", "lib"],
                     help="multi-GPU interface transport: nccl = send/recv of the staged rows after K1; push = the copy engine "
                          "pushes them into the owner's HALO rows over NVLink (CUDA IPC) while K1 still runs; k1 = K1's own "
-                         "bulk stores into the owner's memory (element-major path)")
+                         "bulk stores into the owner's memory (element-major path); lib = the whole exchange inside the library "
+                         "(ad4sm_dist_eval: ncclSend/Recv + ϕ all-gather issued by the C ABI, what a Julia host calls)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

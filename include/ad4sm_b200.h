@@ -227,6 +227,34 @@ int ad4sm_peer_attach(ad4sm_plan* plan, int32_t n_links, const ad4sm_peer_link* 
  * stage use the destination-sorted staging for everything else; undeclared, the whole staging is element-major. */
 int ad4sm_export_ranges(ad4sm_plan* plan, int32_t n_ranges, const int64_t* first_slot, const int64_t* count);
 
+/* ---- the partitioned evaluation as ONE call, NCCL inside the library (ad4sm_dist_init(nranks, rank, id)) ----
+ * For hosts without torch.distributed (Julia with MPI.jl / Distributed, C): one process per GPU; rank 0 calls
+ * ad4sm_dist_unique_id and ships the 128 bytes to the others by whatever means the host has; every rank calls
+ * ad4sm_dist_init (ncclCommInitRank) and builds its plan as (own elements, HALO batch of the foreign elements touching its
+ * owned nodes, sorted by (owner rank, position in `elems`)).  ad4sm_dist_attach names, per neighbour, the OWN slots whose
+ * staged rows that neighbour needs (any subset in any order -- a general partition, not only slabs; non-contiguous lists
+ * are packed by a gather kernel) and the range of this rank's HALO slots that neighbour fills.  ad4sm_dist_eval* then runs
+ * element stage -> grouped ncclSend/ncclRecv of the staged rows on the plan's stream -> assembly -> ncclAllGather of the
+ * per-rank ϕ, summed in rank order (run-to-run reproducible).  Owned rows of Kt and r are bitwise those of a single-GPU
+ * evaluation of the whole mesh.  libnccl.so.2 is bound at run time (dlopen; AD4SM_NCCL_LIB overrides the name). */
+#define AD4SM_NCCL_ID_BYTES 128
+typedef struct ad4sm_dist ad4sm_dist;
+typedef struct ad4sm_dist_peer {
+  int32_t rank;               /* the neighbour */
+  int64_t n_send;             /* own elements that are HALO on that neighbour ... */
+  const int64_t* send_slots;  /* ... their slots in this plan (0-based), in the neighbour's HALO order */
+  int64_t recv_first_slot;    /* first staging slot (>= number of own elements) of the HALO elements it evaluates for us */
+  int64_t n_recv;
+} ad4sm_dist_peer;
+int ad4sm_dist_unique_id(void* id_out /* AD4SM_NCCL_ID_BYTES */);
+int ad4sm_dist_init(int32_t nranks, int32_t rank, const void* nccl_id, int32_t device, ad4sm_dist** comm_out);
+void ad4sm_dist_destroy(ad4sm_dist* comm);
+int ad4sm_dist_attach(ad4sm_plan* plan, ad4sm_dist* comm, int32_t n_peers, const ad4sm_dist_peer* peers);
+/* device-resident (asynchronous on the plan's stream; the global ϕ is phi_dev of ad4sm_device_view_get, r and Kt the
+ * plan's outputs, complete on the rows this rank owns) and host variants (u in; global ϕ and this rank's r out) */
+int ad4sm_dist_eval_device(ad4sm_plan* plan, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev);
+int ad4sm_dist_eval(ad4sm_plan* plan, int32_t mode, const double* u, const double* d, double* phi_global, double* r_local);
+
 typedef struct ad4sm_staging_view {
   int64_t n_slots;       /* elements of all batches, in batch order (slot = position in that concatenation) */
   int64_t ke_width;      /* doubles per slot in Ke_dev: N(N+1)/2 node-pair blocks of DB*DB (DB = D for FIELD_U, 1 for FIELD_D) */
@@ -238,17 +266,10 @@ typedef struct ad4sm_staging_view {
 int ad4sm_staging_view_get(ad4sm_plan* plan, int32_t field, ad4sm_staging_view* view);
 int ad4sm_sync(ad4sm_plan* plan);
 
-/* Plan options / introspection.  FUSED: a plan with a single non-HALO batch of a multi-Gauss-point element runs the
- * element stage and the assembly as ONE persistent cooperative kernel (the staged blocks are consumed from L2 a few
- * steps after they are written); 0 (the default in round 1, where the fused kernel is correct but slower)
- * uses the separate K1 -> K2/K3 launches.  Results are bitwise the same either way.
- * AD4SM_INFO_FUSED: 0 = not available for this plan, 1 = available, 2 = switched on. */
-#define AD4SM_OPT_FUSED 1
-#define AD4SM_OPT_FUSED_LAG 2     /* steps between staging a group and assembling the rows it completes */
+/* Plan options / introspection.  (Options 1, 2 and infos 1, 2 belonged to the round-1 fused K1+assembly kernel, which
+ * was measured slower than the separate kernels in every configuration and has been removed; the ids stay reserved.) */
 #define AD4SM_OPT_SORTED 3        /* destination-sorted staging + streaming assembly (K2s); default on where available */
 #define AD4SM_OPT_PEER_PUSH 4    /* 1: ad4sm_peer_attach sets up copy-engine pushes instead of K1 peer stores (see there) */
-#define AD4SM_INFO_FUSED 1
-#define AD4SM_INFO_FUSED_STEPS 2
 #define AD4SM_INFO_SORTED 3       /* 0 = not available for this plan, 1 = available but off, 2 = on */
 int ad4sm_set_option(ad4sm_plan* plan, int32_t option, int64_t value);
 int ad4sm_get_info(ad4sm_plan* plan, int32_t what, int64_t* value);

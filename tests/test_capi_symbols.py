@@ -62,3 +62,19 @@ def test_eval_elements_host_rejects_wrong_layout():
             p.eval_elements_host(0, bad)
     with pytest.raises(ValueError):
         p.eval_elements_host(1, np.zeros((3, 10), order="F"), d=np.zeros(9))
+
+
+def test_nccl_is_bound_at_run_time():
+    """ad4sm_dist_unique_id dlopens libnccl.so.2 (no link-time dependency) and returns a 128-byte id; without a CUDA
+    device ad4sm_dist_init must fail with a status code, not crash."""
+    L = capi.lib()
+    buf = (C.c_ubyte * capi.NCCL_ID_BYTES)()
+    assert L.ad4sm_dist_unique_id(buf) == capi.OK, L.ad4sm_last_error()
+    assert any(bytes(buf))
+    if capi.device_count() == 0:
+        h = C.c_void_p()
+        rc = L.ad4sm_dist_init(1, 0, buf, -1, C.byref(h))
+        assert rc in (capi.ENODEV, capi.ENCCL) and not h.value
+    import subprocess
+    out = subprocess.run(["readelf", "-d", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libnccl" not in out, "libnccl must not be a NEEDED dependency of libad4sm_b200.so"

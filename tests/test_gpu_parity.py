@@ -182,8 +182,8 @@ def test_cuda_path_reproduces_golden_vectors(path):
 def test_two_rank_halo_exchange_single_gpu(shape):
     """Mesh-partitioned evaluation (dist.py) emulated on ONE GPU: two in-process plans with HALO batches, the
     interface staging copied between them where NCCL send/recv would carry it.  Owned rows must be BITWISE equal to
-    the single-plan result (same contributions, same `elems` order).  hex8 runs on the destination-sorted path with
-    export ranges + HALO scatter, tet4 (one Gauss point) on the element-major path."""
+    the single-plan result (same contributions, same `elems` order).  Both shapes run on the destination-sorted path with
+    export ranges + HALO scatter (hex8: persistent K1; tet4, one Gauss point: the warp-cooperative K1)."""
     import torch
     from ad4sm_b200 import dist as AD, mesh
     if shape == "hex8":
@@ -201,7 +201,7 @@ def test_two_rank_halo_exchange_single_gpu(shape):
     for p in parts:
         own = El.ElemBatch("CE", 3, p.local_conn(conn[p.own_elems]), b.gradN[p.own_elems], b.wgt[p.own_elems], b.mat)
         backs.append(AD.GpuBackend(own, p.local_conn(conn[p.halo_elems]), p, 3))
-    assert all(be.plan.info(capi.INFO_SORTED) == (2 if shape == "hex8" else 0) for be in backs)
+    assert all(be.plan.info(capi.INFO_SORTED) == 2 for be in backs)
     for p, be in zip(parts, backs):
         ul = torch.from_numpy(np.ascontiguousarray(u[:, p.local_nodes - 1].T)).cuda()
         be.eval_elements(ul)
@@ -235,36 +235,27 @@ def test_two_rank_halo_exchange_single_gpu(shape):
     assert abs(sum(phis) - phi0) <= 1e-13 * abs(phi0)
 
 
-@pytest.mark.parametrize("n", [(6, 5, 4), (30, 30, 30), (40, 37, 29)])
-def test_fused_persistent_kernel_matches_separate_kernels(n):
-    """The four execution modes of a single-batch Hex8 plan -- {element-major, destination-sorted staging} x {separate
-    K1 -> K2 launches, ONE fused cooperative persistent launch with steps published through global counters} -- sum the
-    same contributions in the same `elems` order: ϕ, r and Kt must agree bit for bit, and match the oracle."""
-    b, u = K.hex_case(n)
-    plan = El.Plan(b, u.shape[1], 3)
-    assert plan.info(capi.INFO_FUSED) >= 1 and plan.info(capi.INFO_SORTED) == 2
-    res = {}
-    for sorted_on in (1, 0):
-        for fused_on in (1, 0):
-            plan.set_option(capi.OPT_SORTED, sorted_on)
-            plan.set_option(capi.OPT_FUSED, fused_on)
-            res[(sorted_on, fused_on)] = plan.makeϕrKt(u)
-            again = plan.makeϕrKt(u)
-            assert np.array_equal(again[2].nzval, res[(sorted_on, fused_on)][2].nzval)
-    f = res[(1, 1)]
-    for key, x in res.items():
-        assert f[0] == x[0] and np.array_equal(f[1], x[1]), key
-        assert np.array_equal(f[2].colptr, x[2].colptr) and np.array_equal(f[2].rowval, x[2].rowval), key
-        assert np.array_equal(f[2].nzval, x[2].nzval), key
-    for sorted_on in (1, 0):
+@pytest.mark.parametrize("make", [lambda: K.tet_case((9, 8, 7)), lambda: K.tet_case((4, 3, 3), mat=K.nh()),
+                                  lambda: K.tet_case((5, 4, 4), mat=Ma.Ogden(3.0, 1000.0, 5000.0))], ids=["tet4-mr", "tet4-nh", "tet4-ogden"])
+def test_one_gauss_point_kernels_agree(make, monkeypatch):
+    """P = 1 shapes: the warp-cooperative K1 (k1_u_kernel_w1) on the destination-sorted staging, the same kernel on the
+    element-major staging, and the round-1 thread-per-element kernel (AD4SM_K1_T1=1) sum the same contributions in the same
+    `elems` order: every bit of ϕ, r and Kt must agree."""
+    b, u = make()
+    res = []
+    for t1, sorted_on in ((0, 1), (0, 0), (1, 0)):
+        monkeypatch.setenv("AD4SM_K1_T1", str(t1))
+        plan = El.Plan(b, u.shape[1], 3)
+        assert plan.info(capi.INFO_SORTED) == 2
         plan.set_option(capi.OPT_SORTED, sorted_on)
-        plan.set_option(capi.OPT_FUSED, 1)
-        for lag in (1, 3, 7):
-            plan.set_option(capi.OPT_FUSED_LAG, lag)
-            g = plan.makeϕrKt(u)
-            assert np.array_equal(f[2].nzval, g[2].nzval) and np.array_equal(f[1], g[1])
-    if b.ne <= 30000:
-        K.assert_parity(f, K.oracle_eval(b, u))
+        res.append(plan.makeϕrKt(u))
+        phi2, r2 = plan.makeϕr(u)
+        assert phi2 == res[-1][0] and np.array_equal(r2, res[-1][1])
+    f = res[0]
+    for x in res[1:]:
+        assert f[0] == x[0] and np.array_equal(f[1], x[1])
+        assert np.array_equal(f[2].colptr, x[2].colptr) and np.array_equal(f[2].rowval, x[2].rowval)
+        assert np.array_equal(f[2].nzval, x[2].nzval)
 
 
 # ---- Ogden: no reference derivative exists (SURVEY §9-1/2; tests/test_ogden.py pins the tangent against mpmath) ----

@@ -85,3 +85,83 @@ def test_two_gpu_partition_nccl_and_peer_staging(tmp_path):
                     assert r[lc] == r0[gc], (mode, g, gn)
                     ls, gs = slice(cp[lc] - 1, cp[lc + 1] - 1), slice(Kt0.colptr[gc] - 1, Kt0.colptr[gc + 1] - 1)
                     assert np.array_equal(nz[ls], Kt0.nzval[gs]), (mode, g, gn)
+
+
+# ---- the exchange inside the library (ad4sm_dist_*): what a host without torch.distributed calls ---------------------
+def _checkerboard(nx, ny, nz, world):
+    """2x2x2-element bricks dealt to the ranks like a checkerboard: every rank has several neighbours-in-pieces, send
+    lists are non-contiguous, and elements at brick corners are HALO on the other rank through different nodes."""
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    r = ((i // 2 + j // 2 + k // 2) % world).transpose(2, 1, 0).reshape(-1)   # element index = i + nx*(j + ny*k)
+    return r.astype(np.int64)
+
+
+def _lib_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from ad4sm_b200 import dist as AD, mesh, Elements as El, Materials as Ma, _capi as capi
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # bootstrap only: ships the NCCL id; no torch NCCL at all
+    try:
+        dims = (8, 6, 8)
+        coords, conn = mesh.hex_block(*dims, jitter=0.1, seed=51)
+        b = El.Hex08_batch(conn, coords, Ma.NeoHooke(1000.0, 5000.0))
+        u = mesh.random_u(len(coords), 3, 1 / 8, seed=52)
+        res = {}
+        for name, er in (("slab", AD.contiguous_elem_ranks(len(conn), world)), ("checker", _checkerboard(*dims, world))):
+            p = AD.build_partition(conn, er, rank, world)
+            own = El.ElemBatch("CE", 3, p.local_conn(conn[p.own_elems]), b.gradN[p.own_elems], b.wgt[p.own_elems], b.mat)
+            lp = AD.LibDistPlan(own, p.local_conn(conn[p.halo_elems]), p, 3, AD.torch_share_id, device=rank)
+            assert lp.plan.info(capi.INFO_SORTED) == 2
+            ul = np.asfortranarray(u[:, p.local_nodes - 1])
+            r_host = np.empty(ul.size)
+            for f in (0.5, 1.0):                       # host entry point: u in, global ϕ and local r out
+                phi = lp.step_host(np.asfortranarray(ul * f), r_host)
+            Kt = lp.plan.fetch_csc()
+            # device entry point must give the same bits
+            ud = torch.from_numpy(np.ascontiguousarray(ul.T)).cuda()
+            torch.cuda.synchronize()
+            lp.step_device(ud.data_ptr())
+            lp.plan.sync()
+            Kt2 = lp.plan.fetch_csc()
+            assert np.array_equal(Kt.nzval, Kt2.nzval)
+            res[name] = (phi, r_host.copy(), Kt, p)
+            lp.close()
+        np.savez(os.path.join(out, f"lib{rank}.npz"),
+                 **{f"{m}_{k}": v for m, (ph, r, Kt, p) in res.items()
+                    for k, v in dict(phi=ph, r=r, cp=Kt.colptr, rv=Kt.rowval, nz=Kt.nzval, ln=p.local_nodes, owned=p.owned).items()})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_partition_inside_the_library(tmp_path):
+    """ad4sm_dist_init / attach / eval on 2 GPUs: a slab partition and a checkerboard (general, non-contiguous) partition
+    must both reproduce the single-GPU Kt and r bit for bit on owned rows."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from ad4sm_b200 import mesh, Elements as El, Materials as Ma
+    world = 2
+    mp.spawn(_lib_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    coords, conn = mesh.hex_block(8, 6, 8, jitter=0.1, seed=51)
+    b = El.Hex08_batch(conn, coords, Ma.NeoHooke(1000.0, 5000.0))
+    u = mesh.random_u(len(coords), 3, 1 / 8, seed=52)
+    phi0, r0, Kt0 = El.Plan(b, u.shape[1], 3).makeϕrKt(u)
+    for name in ("slab", "checker"):
+        seen = np.zeros(u.shape[1], dtype=int)
+        for g in range(world):
+            z = np.load(tmp_path / f"lib{g}.npz")
+            ln = z[f"{name}_ln"]
+            assert abs(float(z[f"{name}_phi"]) - phi0) <= 1e-13 * abs(phi0)
+            cp, nz, r = z[f"{name}_cp"], z[f"{name}_nz"], z[f"{name}_r"]
+            for loc in np.where(z[f"{name}_owned"])[0]:
+                gn = ln[loc]
+                seen[gn - 1] += 1
+                for c in range(3):
+                    lc, gc = loc * 3 + c, (gn - 1) * 3 + c
+                    assert r[lc] == r0[gc], (name, g, gn)
+                    ls, gs = slice(cp[lc] - 1, cp[lc + 1] - 1), slice(Kt0.colptr[gc] - 1, Kt0.colptr[gc + 1] - 1)
+                    assert np.array_equal(nz[ls], Kt0.nzval[gs]), (name, g, gn)
+        assert np.all(seen == 1), "every node is owned by exactly one rank"
