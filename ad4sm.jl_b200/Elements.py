@@ -658,6 +658,26 @@ class Plan:
         capi.check(self._L.ad4sm_newton_view_get(self._h, field, C.byref(v)))
         return v
 
+    # -- batched post-processing (elements.toolkit.jl:8-132) -------------------------------------------------------
+    def post(self, u, F=False, detJ=False, V=False, sigma=False, P=False):
+        """Per-element post-processing in `elems` order; returns a dict of the requested arrays:
+        F [ne, D, D], detJ [ne], V [ne] (current volumes), sigma [ne, D, D], P [ne, D, D] (the average of P1K')."""
+        u = self._u(u)
+        D = self.batches[0].D
+        out, ptr = {}, []
+        for name, want, shape in (("F", F, (self.ne, D * D)), ("detJ", detJ, (self.ne,)), ("V", V, (self.ne,)),
+                                  ("sigma", sigma, (self.ne, D * D)), ("P", P, (self.ne, D * D))):
+            if want:
+                out[name] = np.empty(shape)
+                ptr.append(C.c_void_p(out[name].ctypes.data))
+            else:
+                ptr.append(None)
+        capi.check(self._L.ad4sm_post(self._h, C.c_void_p(u.ctypes.data), *ptr))
+        for k in ("F", "sigma", "P"):
+            if k in out:   # column-major D x D per element, like Julia's SMatrix
+                out[k] = out[k].reshape(self.ne, D, D).transpose(0, 2, 1)
+        return out
+
     # -- device-resident API (bench / GPU-side callers) ------------------------------------------
     def set_stream(self, cuda_stream):
         capi.check(self._L.ad4sm_set_stream(self._h, C.c_void_p(cuda_stream)))
@@ -802,6 +822,44 @@ def pack_duals(val, grad, hess):
     return np.ascontiguousarray(np.concatenate([val[:, None], grad, hess[:, rows, cols]], axis=1))
 
 
+# ---- post-processing over `elems` (elements.toolkit.jl:10, 28, 47, 59, 88-113): the reference's array methods ----------
+def getF(elems, u, **opts):
+    """`getF(elems, u)`: one D x D volume-averaged deformation gradient per element."""
+    return _plan_for(elems, u, **opts).post(u, F=True)["F"]
+
+
+def get_grad_u(elems, u, **opts):
+    """`get∇u(elems, u)` (∇ is not a legal Python identifier character)."""
+    F = getF(elems, u, **opts)
+    return F - np.eye(F.shape[1])[None]
+
+
+def detJ(elems, u, **opts):
+    return _plan_for(elems, u, **opts).post(u, detJ=True)["detJ"]
+
+
+def getV(elems, u, **opts):
+    """`getV(elems, u)` = sum(getV(elem, u[:,elem.nodes]) for elem in elems): left fold in `elems` order."""
+    total = 0.0
+    for v in _plan_for(elems, u, **opts).post(u, V=True)["V"]:
+        total += v
+    return total
+
+
+def getσ(elems, u, **opts):
+    """`getσ(elems::Vector{<:C3D}, u)` -> 6 x nElems (xx yy zz xy zx yz), `::Vector{<:C2D}` -> 3 x nElems (xx yy xy)."""
+    s = _plan_for(elems, u, **opts).post(u, sigma=True)["sigma"]
+    D = s.shape[1]
+    flat = s.transpose(0, 2, 1).reshape(len(s), D * D)        # column-major linear index, like σii[idx]
+    idx = [0, 4, 8, 1, 2, 5] if D == 3 else [0, 3, 1]           # [1,5,9,2,3,6] / [1,4,2], toolkit:92, 106
+    return np.ascontiguousarray(flat[:, idx].T)
+
+
+def getP(elems, u, **opts):
+    return _plan_for(elems, u, **opts).post(u, P=True)["P"]
+
+
+get_sigma = getσ
 make_phi_r_Kt = makeϕrKt
 make_phi_r_Kt_d = makeϕrKt_d
 make_phi_r = makeϕr

@@ -119,6 +119,8 @@ SIGNATURES = {
     "ad4sm_dist_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(DistPeer)]),
     "ad4sm_dist_eval_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ad4sm_dist_eval": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ad4sm_post": (C.c_int, [C.c_void_p] * 7),
+    "ad4sm_post_device": (C.c_int, [C.c_void_p] * 7),
     "ad4sm_measure_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

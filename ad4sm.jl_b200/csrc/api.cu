@@ -1655,6 +1655,70 @@ int ad4sm_dist_eval(ad4sm_plan* p, int32_t mode, const double* u, const double* 
   return AD4SM_OK;
 }
 
+// ---- batched D1 post-processing (elements.toolkit.jl:8-132; kernel in post.cu) ----------------------------------------
+int ad4sm_post_device(ad4sm_plan* p, const double* u_dev, double* F, double* detJ, double* vol, double* sigma, double* Pk) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (!u_dev) return fail(AD4SM_EINVAL, "u is NULL");
+  for (const BatchPlan& b : p->batches) {
+    if (b.halo) return fail(AD4SM_EINVAL, "post-processing on a plan with HALO batches: evaluate each rank's own elements with its own plan");
+    if ((sigma || Pk) && b.k.mat.kind == MAT_PHASEFIELD)
+      return fail(AD4SM_EINVAL, "getσ / getP need an elastic material: the reference has no getϕ(F, ::PhaseField) (phasefieldmaterials.jl:20)");
+  }
+  CK(cudaSetDevice(p->device));
+  for (const BatchPlan& b : p->batches) {
+    PostArgs a = {};
+    a.mat = b.k.mat;
+    a.ne = b.k.ne;
+    a.slot0 = b.k.slot0;
+    a.D = b.k.D;
+    a.N = b.k.N;
+    a.P = b.k.P;
+    a.mf = b.k.mf;
+    a.dpn = b.k.dpn;
+    a.want_stress = (sigma || Pk) ? 1 : 0;
+    a.nodes = b.k.nodes;
+    a.gradN = b.k.gradN;
+    a.wgt = b.k.wgt;
+    a.u = u_dev;
+    a.index = p->key_dev ? p->key_dev + b.k.slot0 : nullptr;
+    a.F = F;
+    a.detJ = detJ;
+    a.vol = vol;
+    a.sigma = sigma;
+    a.Pk = Pk;
+    cudaError_t e = launch_post(a, p->stream);
+    if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("post-processing launch: ") + cudaGetErrorString(e));
+  }
+  return AD4SM_OK;
+}
+
+int ad4sm_post(ad4sm_plan* p, const double* u, double* F, double* detJ, double* vol, double* sigma, double* Pk) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (!u) return fail(AD4SM_EINVAL, "u is NULL");
+  CK(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  const size_t ne = (size_t)p->ne, dd = (size_t)p->D * p->D;
+  double* outs[5] = {F, detJ, vol, sigma, Pk};
+  const size_t width[5] = {dd, 1, 1, dd, dd};
+  double* dev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  auto release = [&]() {
+    for (double* d : dev) cudaFree(d);
+  };
+  for (int i = 0; i < 5; i++)
+    if (outs[i] && cudaMalloc((void**)&dev[i], sizeof(double) * ne * width[i]) != cudaSuccess) {
+      release();
+      return fail(AD4SM_ENOMEM, "cudaMalloc of the post-processing outputs failed");
+    }
+  cudaError_t e = cudaMemcpyAsync(p->u_dev, u, sizeof(double) * p->n_nodes * p->dpn, cudaMemcpyHostToDevice, s);
+  int rc = e == cudaSuccess ? ad4sm_post_device(p, p->u_dev, dev[0], dev[1], dev[2], dev[3], dev[4]) : fail(AD4SM_ENODEV, "upload of u failed");
+  for (int i = 0; i < 5 && !rc; i++)
+    if (outs[i] && cudaMemcpyAsync(outs[i], dev[i], sizeof(double) * ne * width[i], cudaMemcpyDeviceToHost, s) != cudaSuccess)
+      rc = fail(AD4SM_ENODEV, "download of the post-processing outputs failed");
+  if (cudaStreamSynchronize(s) != cudaSuccess && !rc) rc = fail(AD4SM_ENODEV, "post-processing failed");
+  release();
+  return rc;
+}
+
 int ad4sm_profile_enable(ad4sm_plan* p, int32_t on) {
   if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
   CK(cudaSetDevice(p->device));

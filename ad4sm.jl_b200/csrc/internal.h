@@ -109,6 +109,20 @@ cudaError_t launch_dropzeros(long long n_dof, const long long* colptr, const lon
 size_t dropzeros_tmp_bytes(long long n_dof);
 cudaError_t launch_fp64_peak(double* tflops, double* mhz);
 
+// ---- batched D1 post-processing (post.cu; elements.toolkit.jl:8-132) ---------------------------------------------------
+struct PostArgs {
+  MatDev mat;
+  long long ne, slot0;
+  int D, N, P, mf, dpn, want_stress;
+  const int* nodes;
+  const double* gradN;
+  const double* wgt;
+  const double* u;
+  const long long* index;  // position of each slot in `elems` (nullptr: slot0 + e)
+  double *F, *detJ, *vol, *sigma, *Pk;  // outputs in `elems` order; any may be nullptr
+};
+cudaError_t launch_post(const PostArgs& a, cudaStream_t s);
+
 // ---- NCCL plumbing of the partitioned evaluation (dist.cu) ---------------------------------------------------------
 struct DistComm;
 struct DistXfer {

@@ -1080,29 +1080,51 @@ template <int EXP> __global__ void __launch_bounds__(K2T_WARPS * 32) k2s_tma_ker
   if (u - lane >= a.n_pairs) return;  // whole warp; no CTA-wide barrier below
   const bool valid = u < a.n_pairs;
   const unsigned c0 = __ldg(a.cptr + (valid ? u : a.n_pairs)), c1 = valid ? __ldg(a.cptr + u + 1) : c0;
-  const unsigned w0 = __shfl_sync(0xffffffffu, c0, 0), w1 = __shfl_sync(0xffffffffu, c1, 31);  // the warp's range of C
-  const unsigned nb = w1 - w0;
-  const bool staged = nb <= (unsigned)K2T_BLOCKS && nb > 0;
   const unsigned bar = smem_u32(&bars[w]);
-  if (staged && lane == 0) {
+  if (lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
-    mbar_expect_tx(bar, nb * (unsigned)(CBLK3 * sizeof(double)));
-    tma_load_1d(smem_u32(buf[w]), a.C + (long long)w0 * CBLK3, nb * (unsigned)(CBLK3 * sizeof(double)), bar);
   }
-  const long long um = valid ? u : 0;  // destinations: fetched while the copy flies
+  const long long um = valid ? u : 0;  // destinations: fetched while the copies fly
   const unsigned oup = __ldg(a.out_up + um), olo = __ldg(a.out_lo + um), nn = __ldg(a.nn_pack + um);
   double acc[9];
 #pragma unroll
   for (int t = 0; t < 9; t++) acc[t] = 0.0;
   __syncwarp();
-  if (staged) {
-    mbar_wait(bar, 0);
-    const double2* B = buf[w] + (c0 - w0) * (CBLK3 / 2);
-    for (unsigned c = c0; c < c1; c++, B += CBLK3 / 2) k2s_add(acc, B);
-  } else {
-    const double2* C2 = reinterpret_cast<const double2*>(a.C);
-    for (unsigned c = c0; c < c1; c++) k2s_add(acc, C2 + (long long)c * (CBLK3 / 2));
+  // The warp's pairs own one contiguous range of C.  It is brought in by TMA bulk copies of at most K2T_BLOCKS blocks:
+  // one copy on a hex mesh (~82 blocks per 32 pairs), several on meshes of higher valence (Kuhn tets: ~240), each
+  // covering a run of consecutive lanes; a single pair with more contributions than a slice holds folds from global
+  // memory directly.
+  unsigned phase = 0;
+  for (int s = 0; s < 32;) {
+    const unsigned base = __shfl_sync(0xffffffffu, c0, s);
+    const unsigned fits = __ballot_sync(0xffffffffu, lane >= s && (c1 - base) <= (unsigned)K2T_BLOCKS);
+    const unsigned stop = ~(fits >> s);                      // first lane at or after s that does not fit
+    const int cnt = stop ? __ffs((int)stop) - 1 : 32 - s;
+    if (cnt == 0) {
+      if (lane == s) {
+        const double2* C2 = reinterpret_cast<const double2*>(a.C);
+        for (unsigned c = c0; c < c1; c++) k2s_add(acc, C2 + (long long)c * (CBLK3 / 2));
+      }
+      s += 1;
+      continue;
+    }
+    const unsigned nb = __shfl_sync(0xffffffffu, c1, s + cnt - 1) - base;
+    if (nb > 0) {
+      if (lane == 0) {
+        fence_proxy_async();  // the previous chunk's reads of the slice precede this copy's writes
+        mbar_expect_tx(bar, nb * (unsigned)(CBLK3 * sizeof(double)));
+        tma_load_1d(smem_u32(buf[w]), a.C + (long long)base * CBLK3, nb * (unsigned)(CBLK3 * sizeof(double)), bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      if (lane >= s && lane < s + cnt) {
+        const double2* B = buf[w] + (c0 - base) * (CBLK3 / 2);
+        for (unsigned c = c0; c < c1; c++, B += CBLK3 / 2) k2s_add(acc, B);
+      }
+      __syncwarp();
+    }
+    s += cnt;
   }
   if (valid) k2s_write<EXP>(a, acc, oup, olo, nn);
 }

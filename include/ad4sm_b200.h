@@ -178,6 +178,19 @@ typedef struct ad4sm_newton_view {
 int ad4sm_newton_reduce_device(ad4sm_plan* plan, int32_t field, int32_t kind, const double* fe_dev, const double* ducnst_dev);
 int ad4sm_newton_view_get(ad4sm_plan* plan, int32_t field, ad4sm_newton_view* view);
 
+/* ---- batched post-processing with first derivatives (elements.toolkit.jl:8-132), one value per element in `elems`
+ * order; any output may be NULL.  D = element dimension, matrices column-major like Julia's SMatrix{D,D}:
+ *   F     [ne][D*D]  getF(elem, u[:,elem.nodes]) = I + Σ_gp wgt ∇u_gp / V          (toolkit:8-27)
+ *   detJ  [ne]       detJ(elem, u) = Σ_gp wgt det F_gp / V                           (:33-47)
+ *   vol   [ne]       getV(elem, u) = Σ_gp wgt det F_gp; getV(elems,u) is their sum   (:52-59)
+ *   sigma [ne][D*D]  getσ(elem, u): volume-averaged Cauchy stress Σ_gp wgt (1/J P Fᵀ)_gp / V   (:63-87)
+ *   Pk    [ne][D*D]  getP(elem, u): volume average of P1K' (the transposed first Piola-Kirchhoff stress, :117-132)
+ * Elastic materials only (the reference has no getϕ(F, ::PhaseField) without d).  `u` as for ad4sm_eval. */
+int ad4sm_post(ad4sm_plan* plan, const double* u, double* F, double* detJ, double* vol, double* sigma, double* Pk);
+/* the same with u and the outputs in device memory (asynchronous on the plan's stream) */
+int ad4sm_post_device(ad4sm_plan* plan, const double* u_dev, double* F_dev, double* detJ_dev, double* vol_dev, double* sigma_dev,
+                      double* Pk_dev);
+
 /* ---- device-resident path (inputs/outputs stay in HBM; used by GPU-side callers and bench.py) ---- */
 int ad4sm_set_stream(ad4sm_plan* plan, void* cuda_stream); /* cudaStream_t; NULL = plan's own stream */
 /* mode: 0 = elastic (ad4sm_eval), 1 = PF u-phase, 2 = PF d-phase, 3 = elastic ϕ,r only.

