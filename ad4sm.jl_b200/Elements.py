@@ -780,7 +780,7 @@ def _plan_for(elems, u, **opts):
         return hit[1]
     plan = Plan(elems, u.shape[1], u.shape[0], **opts)
     try:
-        ref = weakref.ref(elems, lambda _r, k=key: _plans.pop(k, None))
+        ref = weakref.ref(elems, lambda _r, k=key, d=_plans: d.pop(k, None) if d is not None else None)
     except TypeError:  # plain lists cannot be weakly referenced: keep at most a few plans alive
         holder = elems
         ref = lambda h=holder: h  # noqa: E731

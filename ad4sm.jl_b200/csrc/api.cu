@@ -786,6 +786,10 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
     a.dfield = d_dev;
     a.hist = (mode == MODE_PF_D && hist_dev) ? hist_dev + b.hist_off * 2 : nullptr;
     a.want_K = want_K;
+    {
+      const char* e = getenv("AD4SM_K1_TURNS");
+      a.p2_turns = e ? atoi(e) : 1;
+    }
     a.Ke = p->Ke;
     a.re = p->re;
     a.phie = p->phie;

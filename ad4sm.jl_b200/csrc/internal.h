@@ -62,6 +62,7 @@ struct K1Args {
   // destination-sorted staging: cpos[slot*NPB + block] = position << 1 | transposed; nullptr = element-major staging
   const unsigned* cpos;
   double* C;
+  int p2_turns;         // persistent K1: the two warps of a sub-partition take turns in phase 2 (AD4SM_K1_TURNS, default 1)
   int exp;              // TIMING EXPERIMENT ONLY (AD4SM_EXP_K1, wrong results): 1 = the sorted epilogue stores nothing
   int sorted_tma;       // sorted blocks leave through shared memory + one 80-byte bulk copy each (else plain STG.128)
   // peer staging: slots [first, first+count) are also written to the owner rank's staging over NVLink

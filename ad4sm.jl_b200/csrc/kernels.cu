@@ -154,7 +154,7 @@ static WarpLayout k1p_layout(int D, int N, int P, int LP, bool pf) {
   L.psi_off = off;
   off += rup(EW * P * 8, 16);
   L.bar_off = off;
-  off += 32;  // 4 mbarriers
+  off += 48;  // 4 mbarriers + the phase-2 turn lock of the sub-partition's warp pair (in the lower warp's slice)
   L.bytes = rup(off, 128);
   // epilogue: the element blocks and residual are staged in the (dead) record region when they fit, and leave
   // with one bulk copy each (16-byte granularity)
@@ -342,7 +342,7 @@ __device__ __forceinline__ void k1_phase1(const MatDev* mat, int q, bool valid, 
 template <int D, int N, int PT>
 __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active, bool want_K, bool staged, const double* recs,
                                           const double* gS, double* kout_s, double* rout_s, double* kout_g, double* rout_g,
-                                          const unsigned* cpos_e, double* C, const K1Args& a, long long slot) {
+                                          const unsigned* cpos_e, double* C, const K1Args& a, long long slot, int* lock) {
   constexpr int NO = N / 2 + 1, DD = D * D;
   // destination-sorted staging: this lane's block positions, fetched now so that the loads fly during the contraction
   unsigned cp[NO];
@@ -351,7 +351,21 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
     for (int o = 0; o < NO; o++) cp[o] = (active && o < n_offsets(N, q)) ? __ldg(cpos_e + o * N + q) : 0xffffffffu;
   }
   double acc[NO][DD], rq[D];
+  // Phase 2 is the FP64-dense part: one warp alone keeps the sub-partition's FP64 pipe ~90 % busy (static schedule:
+  // 2.6 cycles per DFMA against the pipe's 2.2), so two warps of a sub-partition inside it at the same time gain nothing
+  // -- and left alone they drift INTO that state and stay there (both slowed equally), leaving the pipe idle while both
+  // run their latency-bound head / phase 1 / epilogue.  The two warps of a sub-partition therefore take turns: whoever
+  // holds the lock runs phase 2 at full rate while the other one's non-FP64 part hides underneath.
+  if (lock) {
+    if ((threadIdx.x & 31) == 0)
+      while (atomicCAS(lock, 0, 1) != 0) __nanosleep(32);
+    __syncwarp();
+  }
   column_u_acc<D, N, PT, VecMem>(q, P, recs, rstride, gS, N, (PT ? PT : P) * N, want_K, acc, rq);
+  if (lock) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) atomicExch(lock, 0);
+  }
   if (cpos_e) {  // (D == 3 only) every block goes to its own sorted slot
     if constexpr (D == 3) {
       __syncwarp();  // all lanes are done reading the records: their area becomes the staging
@@ -453,6 +467,13 @@ __global__ void __launch_bounds__(256, 1)
   }
   __syncwarp();
   unsigned char* const ws = ws0;
+  // phase-2 turn lock shared by the warps w and w + 4 (same sub-partition: warp id mod 4), see k1_phase2
+  int* lock = nullptr;
+  if (a.p2_turns && warps_per_cta > 4) {
+    lock = reinterpret_cast<int*>(smraw + (size_t)(warp & 3) * L.bytes + L.bar_off + 32);
+    if (warp < 4 && lane == 0) *lock = 0;
+    __syncthreads();  // once, before any warp can ask for the lock; every warp of the CTA gets here
+  }
 
   // TMA bulk copies of one element group into stage s (∇N per element, wgt, N).  Called by the whole warp: lane 0
   // announces the byte count, then lanes 0..cnt-1 issue one ∇N copy each and lanes EW, EW+1 the small arrays -- the
@@ -552,12 +573,12 @@ __global__ void __launch_bounds__(256, 1)
       k1_phase2<D, N, PTC>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS,
                            (sorted && !sorted_tma) ? nullptr : reinterpret_cast<double*>(stg),
                            reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
-                           a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot);
+                           a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot, lock);
     else
       k1_phase2<D, N, 0>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS,
                          (sorted && !sorted_tma) ? nullptr : reinterpret_cast<double*>(stg),
                          reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
-                         a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot);
+                         a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot, lock);
     if (valid && q == 0) {  // ϕ_e = Σ_gp w ψ, in Gauss-point order (elasticelements.jl:199-206)
       double ssum = 0.0;
       for (int gp = 0; gp < P; gp++) ssum += psiS[gp];
