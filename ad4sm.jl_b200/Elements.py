@@ -27,7 +27,7 @@ from . import Materials
 from . import _capi as capi
 
 __all__ = [
-    "CEElem", "CPElem", "ElemBatch", "SparseMatrixCSC", "Plan",
+    "CEElem", "CPElem", "ElemBatch", "MeshBatch", "SparseMatrixCSC", "Plan",
     "Tria", "Quad", "QuadR", "Tet04", "Hex08", "Hex08R",
     "TriaP", "QuadP", "QuadPR", "Hex08P", "Hex08PR", "Wdg06P", "Tet04P",
     "makeϕrKt", "makeϕrKt_d", "makeϕr", "make_phi_r_Kt", "make_phi_r_Kt_d", "make_phi_r",
@@ -90,6 +90,78 @@ class ElemBatch:
         if self.kind == "CP":
             kw["N"] = self.Nval[i]
         return cls(**kw)
+
+
+_SHAPES = {  # shape -> (capi code, D, N, tensor rule?)
+    "Tria": (capi.SHAPE_TRIA3, 2, 3, False), "Quad": (capi.SHAPE_QUAD4, 2, 4, True), "Tet04": (capi.SHAPE_TET4, 3, 4, False),
+    "Hex08": (capi.SHAPE_HEX8, 3, 8, True), "Wdg06": (capi.SHAPE_WDG6, 3, 6, False),
+}
+
+
+@dataclass
+class MeshBatch:
+    """A homogeneous group of elements given by connectivity + node coordinates: what the reference constructors
+    (`Hex08(nodes, p0; GP, mat)` ...) take, for all elements at once.  ∇N, wgt (and N) are constructed ON THE DEVICE
+    (csrc/construct.cu) -- when a Plan is built from it (no host ∇N, no upload), or explicitly into
+    host arrays by `materialize()`, which returns the `ElemBatch` the host constructors (`*_batch`) would."""
+    kind: str  # "CE" | "CP"
+    shape: str  # key of _SHAPES
+    nodes: np.ndarray  # [ne][N] int64, 1-based
+    coords: np.ndarray  # [n_nodes][>= D]
+    mat: object
+    GP: tuple = ()  # tensor shapes: ((xi, w), ...) -- the reference's GP keyword
+    orig_index: np.ndarray | None = None
+    halo = False
+    gradN = wgt = Nval = None
+
+    def __post_init__(self):
+        self.nodes = np.ascontiguousarray(self.nodes, dtype=np.int64)
+        self.coords = np.ascontiguousarray(self.coords, dtype=np.float64)
+        code, D, N, tensor = _SHAPES[self.shape]
+        if self.nodes.ndim != 2 or self.nodes.shape[1] != N:
+            raise ValueError(f"{self.shape}: connectivity must be [ne][{N}]")
+        if self.coords.ndim != 2 or self.coords.shape[1] < D:
+            raise ValueError(f"{self.shape}: coordinates must be [n_nodes][>= {D}]")
+        if tensor and not 1 <= len(self.GP) <= 3:
+            raise ValueError("GP must hold 1..3 (abscissa, weight) pairs")
+        self.D = D
+
+    @property
+    def ne(self):
+        return self.nodes.shape[0]
+
+    @property
+    def N(self):
+        return self.nodes.shape[1]
+
+    @property
+    def P(self):
+        code, D, N, tensor = _SHAPES[self.shape]
+        return len(self.GP) ** D if tensor else (6 if self.shape == "Wdg06" else 1)
+
+    def __len__(self):
+        return self.ne
+
+    def c_mesh(self):
+        m = capi.Mesh()
+        m.shape = _SHAPES[self.shape][0]
+        m.n_gp_1d = len(self.GP)
+        for i, (xi, w) in enumerate(self.GP):
+            m.gp_xi[i], m.gp_w[i] = xi, w
+        m.coord_dim = self.coords.shape[1]
+        m.n_nodes = self.coords.shape[0]
+        m.coords = self.coords.ctypes.data
+        return m
+
+    def materialize(self, device=-1):
+        """Run the batched constructor on the device and return the result as a host `ElemBatch`."""
+        ne, N, P, D = self.ne, self.N, self.P, self.D
+        gradN, wgt, V = np.empty((ne, D, P, N)), np.empty((ne, P)), np.empty(ne)
+        Nval = np.empty((ne, P, N)) if self.kind == "CP" else None
+        m = self.c_mesh()
+        capi.check(capi.lib().ad4sm_construct(C.byref(m), ne, self.nodes.ctypes.data, device, gradN.ctypes.data, wgt.ctypes.data,
+                                             Nval.ctypes.data if Nval is not None else None, V.ctypes.data))
+        return ElemBatch(self.kind, D, self.nodes, gradN, wgt, self.mat, Nval, V=V, orig_index=self.orig_index)
 
 
 @dataclass
@@ -264,40 +336,54 @@ _WDG_PTS = [((2 / 3, 1 / 6, 3 ** 0.5 / 3), 1 / 3), ((2 / 3, 1 / 6, -(3 ** 0.5) /
             ((1 / 6, 1 / 6, 3 ** 0.5 / 3), 1 / 3), ((1 / 6, 1 / 6, -(3 ** 0.5) / 3), 1 / 3)]
 
 
-def Tria_batch(conn, coords, mat):
-    return _tria_batch("CE", conn, coords, mat)
+# `device=True`: return a MeshBatch instead -- the same constructor runs on the GPU when the Plan is built (or on
+# `.materialize()`), and the host never holds ∇N.
+def Tria_batch(conn, coords, mat, device=False):
+    return MeshBatch("CE", "Tria", conn, coords, mat) if device else _tria_batch("CE", conn, coords, mat)
 
 
-def TriaP_batch(conn, coords, mat):
-    return _tria_batch("CP", conn, coords, mat)
+def TriaP_batch(conn, coords, mat, device=False):
+    return MeshBatch("CP", "Tria", conn, coords, mat) if device else _tria_batch("CP", conn, coords, mat)
 
 
-def Quad_batch(conn, coords, mat, GP=GP2):
+def Quad_batch(conn, coords, mat, GP=GP2, device=False):
+    if device:
+        return MeshBatch("CE", "Quad", conn, coords, mat, GP)
     return _iso_batch("CE", 2, _shape_quad, _tensor_points(2, GP), conn, coords, mat)
 
 
-def QuadP_batch(conn, coords, mat, GP=GP2):
+def QuadP_batch(conn, coords, mat, GP=GP2, device=False):
+    if device:
+        return MeshBatch("CP", "Quad", conn, coords, mat, GP)
     return _iso_batch("CP", 2, _shape_quad, _tensor_points(2, GP), conn, coords, mat)
 
 
-def Tet04_batch(conn, coords, mat):
-    return _tet_batch("CE", conn, coords, mat)
+def Tet04_batch(conn, coords, mat, device=False):
+    return MeshBatch("CE", "Tet04", conn, coords, mat) if device else _tet_batch("CE", conn, coords, mat)
 
 
-def Tet04P_batch(conn, coords, mat):
-    return _tet_batch("CP", conn, coords, mat)
+def Tet04P_batch(conn, coords, mat, device=False):
+    return MeshBatch("CP", "Tet04", conn, coords, mat) if device else _tet_batch("CP", conn, coords, mat)
 
 
-def Hex08_batch(conn, coords, mat, GP=GP2):
+def Hex08_batch(conn, coords, mat, GP=GP2, device=False):
+    if device:
+        return MeshBatch("CE", "Hex08", conn, coords, mat, GP)
     return _iso_batch("CE", 3, _shape_hex, _tensor_points(3, GP), conn, coords, mat)
 
 
-def Hex08P_batch(conn, coords, mat, GP=GP2):
+def Hex08P_batch(conn, coords, mat, GP=GP2, device=False):
+    if device:
+        return MeshBatch("CP", "Hex08", conn, coords, mat, GP)
     return _iso_batch("CP", 3, _shape_hex, _tensor_points(3, GP), conn, coords, mat)
 
 
-def Wdg06P_batch(conn, coords, mat):
-    return _iso_batch("CP", 3, _shape_wdg, _WDG_PTS, conn, coords, mat)
+def Wdg06_batch(conn, coords, mat, device=False):  # elasticelements.jl:163-197
+    return MeshBatch("CE", "Wdg06", conn, coords, mat) if device else _iso_batch("CE", 3, _shape_wdg, _WDG_PTS, conn, coords, mat)
+
+
+def Wdg06P_batch(conn, coords, mat, device=False):
+    return MeshBatch("CP", "Wdg06", conn, coords, mat) if device else _iso_batch("CP", 3, _shape_wdg, _WDG_PTS, conn, coords, mat)
 
 
 def _single(batch_ctor, nodes, p0, **kw):
@@ -413,11 +499,11 @@ def as_batches(elems):
     """`elems` (a list of CEElem/CPElem, an ElemBatch, or a list of ElemBatch) -> list[ElemBatch].
     Element objects are grouped by (kind, D, P, N, material); `orig_index` keeps the position in `elems`
     so the assembly sums duplicates in `elems` order like the reference."""
-    if isinstance(elems, ElemBatch):
+    if isinstance(elems, (ElemBatch, MeshBatch)):
         return [elems]
     if len(elems) == 0:
         raise AssertionError("makeϕrKt: `elems` is empty")  # elasticelements.jl:210
-    if all(isinstance(e, ElemBatch) for e in elems):
+    if all(isinstance(e, (ElemBatch, MeshBatch)) for e in elems):
         return list(elems)
     groups = {}
     for i, e in enumerate(elems):
@@ -461,6 +547,10 @@ class Plan:
             s.n_elems = b.ne
             s.batch_flags = capi.BATCH_HALO if b.halo else 0
             s.nodes = b.nodes.ctypes.data
+            if isinstance(b, MeshBatch):  # constructed on the device inside ad4sm_plan_create
+                m = b.c_mesh()
+                self._keep.append(m)
+                s.mesh = C.pointer(m)
             s.gradN = b.gradN.ctypes.data if b.gradN is not None else None
             s.wgt = b.wgt.ctypes.data if b.wgt is not None else None
             s.Nval = b.Nval.ctypes.data if b.Nval is not None else None

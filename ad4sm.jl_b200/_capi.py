@@ -17,6 +17,14 @@ MODE_ELASTIC, MODE_PF_U, MODE_PF_D, MODE_PHI_R = 0, 1, 2, 3
 PROF_ELEMENT, PROF_ASSEMBLE, PROF_REDUCE, PROF_GATHER, PROF_NCLASS = 0, 1, 2, 3, 4
 
 
+SHAPE_TRIA3, SHAPE_QUAD4, SHAPE_TET4, SHAPE_HEX8, SHAPE_WDG6 = 1, 2, 3, 4, 5
+
+
+class Mesh(C.Structure):
+    _fields_ = [("shape", C.c_int32), ("n_gp_1d", C.c_int32), ("gp_xi", C.c_double * 3), ("gp_w", C.c_double * 3),
+                ("coord_dim", C.c_int32), ("reserved", C.c_int32), ("n_nodes", C.c_int64), ("coords", C.c_void_p)]
+
+
 class Batch(C.Structure):
     _fields_ = [
         ("elem_kind", C.c_int32), ("dim", C.c_int32), ("n_gauss", C.c_int32), ("n_elem_nodes", C.c_int32),
@@ -24,7 +32,7 @@ class Batch(C.Structure):
         ("mat_params", C.c_double * 8),
         ("n_elems", C.c_int64),
         ("nodes", C.c_void_p), ("gradN", C.c_void_p), ("wgt", C.c_void_p), ("Nval", C.c_void_p),
-        ("orig_index", C.c_void_p),
+        ("orig_index", C.c_void_p), ("mesh", C.POINTER(Mesh)),
     ]
 
 
@@ -82,6 +90,9 @@ SIGNATURES = {
     "ad4sm_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "ad4sm_plan_create": (C.c_int, [C.POINTER(Batch), C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "ad4sm_plan_destroy": (None, [C.c_void_p]),
+    "ad4sm_construct": (C.c_int, [C.POINTER(Mesh), C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ad4sm_construct_device": (C.c_int, [C.POINTER(Mesh), C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     "ad4sm_plan_pattern_size": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ad4sm_plan_pattern": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ad4sm_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int64)]),

@@ -7,6 +7,7 @@
 //   makeϕrKt_d(elems, u, d[,ϕmax])/root/reference/src/phasefieldelements.jl:239-262
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -209,6 +210,91 @@ static int mat_family(const ad4sm_batch& b, int* mf, std::string* why) {
   return -1;
 }
 
+
+// ---- batched constructors: ad4sm_mesh -> kernel arguments (Gauss points in the reference's storage order) --------------
+static int shape_dims(int shape, int n1d, int* D, int* N, int* P) {
+  switch (shape) {
+    case AD4SM_SHAPE_TRIA3: *D = 2, *N = 3, *P = 1; return 0;
+    case AD4SM_SHAPE_TET4: *D = 3, *N = 4, *P = 1; return 0;
+    case AD4SM_SHAPE_WDG6: *D = 3, *N = 6, *P = 6; return 0;
+    case AD4SM_SHAPE_QUAD4:
+      if (n1d < 1 || n1d > 3) return -1;
+      *D = 2, *N = 4, *P = n1d * n1d;
+      return 0;
+    case AD4SM_SHAPE_HEX8:
+      if (n1d < 1 || n1d > 3) return -1;
+      *D = 3, *N = 8, *P = n1d * n1d * n1d;
+      return 0;
+  }
+  return -1;
+}
+static int construct_args(const ad4sm_mesh* m, ConstructArgs* a) {
+  if (!m) return fail(AD4SM_EINVAL, "mesh is NULL");
+  int D, N, P;
+  if (shape_dims(m->shape, m->n_gp_1d, &D, &N, &P))
+    return fail(AD4SM_EINVAL, "mesh: unknown shape, or a tensor rule with other than 1..3 points per direction");
+  if (m->coord_dim < D) return fail(AD4SM_EINVAL, "mesh: coord_dim < element dimension");
+  if (!m->coords || m->n_nodes <= 0) return fail(AD4SM_EINVAL, "mesh: coords missing");
+  memset(a, 0, sizeof(*a));
+  a->shape = m->shape;
+  a->P = P;
+  a->ldc = m->coord_dim;
+  if (m->shape == AD4SM_SHAPE_QUAD4 || m->shape == AD4SM_SHAPE_HEX8) {
+    const int n = m->n_gp_1d;
+    a->n1d = n;
+    a->n_wfac = D;
+    for (int g = 0; g < P; g++) {  // storage index g = ii + n (jj + n kk): Nx[ii,jj,kk] flattened column-major
+      const int idx[3] = {g % n, (g / n) % n, g / (n * n)};
+      for (int k = 0; k < D; k++) {
+        a->pt[g][k] = m->gp_xi[idx[k]];
+        a->wfac[g][k] = m->gp_w[idx[k]];
+      }
+    }
+  } else if (m->shape == AD4SM_SHAPE_WDG6) {  // elasticelements.jl:169-171
+    const double s3 = sqrt(3.0) / 3.0;
+    const double xy[3][2] = {{2.0 / 3.0, 1.0 / 6.0}, {1.0 / 6.0, 2.0 / 3.0}, {1.0 / 6.0, 1.0 / 6.0}};
+    a->n_wfac = 1;
+    for (int g = 0; g < 6; g++) {
+      a->pt[g][0] = xy[g / 2][0];
+      a->pt[g][1] = xy[g / 2][1];
+      a->pt[g][2] = (g % 2) ? -s3 : s3;
+      a->wfac[g][0] = 1.0 / 3.0;
+    }
+  }
+  return 0;
+}
+// nodes / coords: host; outputs: device.  Temporary device copies of the inputs live for the duration of the call.
+static int construct_run(const ad4sm_mesh* m, long long ne, const int64_t* nodes, double* gradN, double* wgt, double* Nval, double* V,
+                         cudaStream_t s) {
+  ConstructArgs a;
+  int rc = construct_args(m, &a);
+  if (rc) return rc;
+  int D, N, P;
+  shape_dims(m->shape, m->n_gp_1d, &D, &N, &P);
+  for (long long i = 0; i < ne * N; i++)
+    if (nodes[i] < 1 || nodes[i] > m->n_nodes) return fail(AD4SM_EINVAL, "node id out of range 1..n_nodes");
+  long long* nd = nullptr;
+  double* xc = nullptr;
+  cudaError_t e = cudaMalloc((void**)&nd, sizeof(long long) * (size_t)ne * N);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&xc, sizeof(double) * (size_t)m->n_nodes * m->coord_dim);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nd, nodes, sizeof(long long) * (size_t)ne * N, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(xc, m->coords, sizeof(double) * (size_t)m->n_nodes * m->coord_dim, cudaMemcpyHostToDevice, s);
+  a.ne = ne;
+  a.nodes = nd;
+  a.coords = xc;
+  a.gradN = gradN;
+  a.wgt = wgt;
+  a.Nval = Nval;
+  a.V = V;
+  if (e == cudaSuccess) e = launch_construct(a, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(nd);
+  cudaFree(xc);
+  if (e != cudaSuccess)
+    return fail(e == cudaErrorMemoryAllocation ? AD4SM_ENOMEM : AD4SM_ENODEV, std::string("construct: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 extern "C" {
 
 int ad4sm_abi_version(void) { return AD4SM_ABI_VERSION; }
@@ -223,6 +309,49 @@ int ad4sm_device_count(int* count) {
     return fail(AD4SM_ENODEV, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
   }
   *count = n;
+  return AD4SM_OK;
+}
+
+static int select_device(int32_t device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(AD4SM_ENODEV, "no CUDA device: libad4sm_b200 has no CPU fallback");
+  int dev = device;
+  if (dev < 0) CK(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(AD4SM_EINVAL, "device ordinal out of range");
+  CK(cudaSetDevice(dev));
+  return 0;
+}
+
+int ad4sm_construct_device(const ad4sm_mesh* mesh, int64_t n_elems, const int64_t* nodes, int32_t device, double* gradN_dev,
+                           double* wgt_dev, double* Nval_dev, double* V_dev) {
+  if (!mesh || n_elems < 0 || (n_elems > 0 && (!nodes || !gradN_dev || !wgt_dev))) return fail(AD4SM_EINVAL, "construct: arguments missing");
+  int rc = select_device(device);
+  if (rc) return rc;
+  return construct_run(mesh, n_elems, nodes, gradN_dev, wgt_dev, Nval_dev, V_dev, (cudaStream_t)0);
+}
+
+int ad4sm_construct(const ad4sm_mesh* mesh, int64_t n_elems, const int64_t* nodes, int32_t device, double* gradN, double* wgt,
+                    double* Nval, double* V) {
+  if (!mesh || n_elems < 0 || (n_elems > 0 && (!nodes || !gradN || !wgt))) return fail(AD4SM_EINVAL, "construct: arguments missing");
+  int D, N, P;
+  if (shape_dims(mesh->shape, mesh->n_gp_1d, &D, &N, &P))
+    return fail(AD4SM_EINVAL, "mesh: unknown shape, or a tensor rule with other than 1..3 points per direction");
+  int rc = select_device(device);
+  if (rc) return rc;
+  const size_t ng = (size_t)n_elems * D * P * N, nw = (size_t)n_elems * P, nv = (size_t)n_elems * P * N;
+  double* buf = nullptr;
+  CK(cudaMalloc((void**)&buf, sizeof(double) * (ng + nw + nv + (size_t)n_elems) + 64));
+  double *g = buf, *w = g + ng, *v = w + nw, *vol = v + nv;
+  rc = construct_run(mesh, n_elems, nodes, g, w, Nval ? v : nullptr, V ? vol : nullptr, (cudaStream_t)0);
+  cudaError_t e = cudaSuccess;
+  if (!rc) e = cudaMemcpy(gradN, g, sizeof(double) * ng, cudaMemcpyDeviceToHost);
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(wgt, w, sizeof(double) * nw, cudaMemcpyDeviceToHost);
+  if (!rc && e == cudaSuccess && Nval) e = cudaMemcpy(Nval, v, sizeof(double) * nv, cudaMemcpyDeviceToHost);
+  if (!rc && e == cudaSuccess && V) e = cudaMemcpy(V, vol, sizeof(double) * (size_t)n_elems, cudaMemcpyDeviceToHost);
+  cudaFree(buf);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("construct: ") + cudaGetErrorString(e));
   return AD4SM_OK;
 }
 
@@ -267,10 +396,16 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       return fail(AD4SM_EINVAL, "all elements must have the same number of dofs (elasticelements.jl:212-214)");
     if (B.dim != D) return fail(AD4SM_EINVAL, "all batches must have the same dimension D");
     const bool halo = (B.batch_flags & AD4SM_BATCH_HALO) != 0;
-    if (B.n_elems < 0 || (B.n_elems > 0 && (!B.nodes || (!halo && (!B.gradN || !B.wgt)))))
+    if (B.n_elems < 0 || (B.n_elems > 0 && (!B.nodes || (!halo && !B.mesh && (!B.gradN || !B.wgt)))))
       return fail(AD4SM_EINVAL, "batch arrays missing");
-    if (B.elem_kind == AD4SM_ELEM_CP && B.n_elems > 0 && !halo && !B.Nval)
+    if (B.elem_kind == AD4SM_ELEM_CP && B.n_elems > 0 && !halo && !B.mesh && !B.Nval)
       return fail(AD4SM_EINVAL, "CPElem batch needs Nval");
+    if (B.mesh && !halo) {  // constructed on the device from the coordinates: the declared shape must be the mesh's
+      int mD, mN, mP;
+      if (shape_dims(B.mesh->shape, B.mesh->n_gp_1d, &mD, &mN, &mP) || mD != B.dim || mN != B.n_elem_nodes || mP != B.n_gauss)
+        return fail(AD4SM_EINVAL, "batch.mesh: shape / rule do not match dim, n_elem_nodes, n_gauss of the batch");
+      if (B.mesh->n_nodes != n_nodes) return fail(AD4SM_EINVAL, "batch.mesh: n_nodes differs from the plan's");
+    }
     if (B.elem_kind != AD4SM_ELEM_CE && B.elem_kind != AD4SM_ELEM_CP) return fail(AD4SM_EINVAL, "unknown elem_kind");
     std::string why;
     if (mat_family(B, &mfs[b], &why)) return fail(AD4SM_EINVAL, why);
@@ -505,13 +640,24 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
         TRY(dev_upload(p, &nd, nodes0.data() + (size_t)s0 * N, (size_t)B.n_elems * N));
         bp.k.nodes = nd;
         double* x = nullptr;
-        TRY(dev_upload(p, &x, B.gradN, (size_t)B.n_elems * D * B.n_gauss * N));
-        bp.k.gradN = x;
-        TRY(dev_upload(p, &x, B.wgt, (size_t)B.n_elems * B.n_gauss));
-        bp.k.wgt = x;
-        if (B.elem_kind == AD4SM_ELEM_CP) {
-          TRY(dev_upload(p, &x, B.Nval, (size_t)B.n_elems * B.n_gauss * N));
-          bp.k.Nval = x;
+        if (B.mesh) {  // batched constructor on the device: no host ∇N, no upload
+          double *g = nullptr, *w = nullptr, *v = nullptr;
+          TRY(dev_alloc(p, &g, (size_t)B.n_elems * D * B.n_gauss * N));
+          TRY(dev_alloc(p, &w, (size_t)B.n_elems * B.n_gauss));
+          if (B.elem_kind == AD4SM_ELEM_CP) TRY(dev_alloc(p, &v, (size_t)B.n_elems * B.n_gauss * N));
+          TRY(construct_run(B.mesh, B.n_elems, B.nodes, g, w, v, nullptr, p->stream));
+          bp.k.gradN = g;
+          bp.k.wgt = w;
+          bp.k.Nval = v;
+        } else {
+          TRY(dev_upload(p, &x, B.gradN, (size_t)B.n_elems * D * B.n_gauss * N));
+          bp.k.gradN = x;
+          TRY(dev_upload(p, &x, B.wgt, (size_t)B.n_elems * B.n_gauss));
+          bp.k.wgt = x;
+          if (B.elem_kind == AD4SM_ELEM_CP) {
+            TRY(dev_upload(p, &x, B.Nval, (size_t)B.n_elems * B.n_gauss * N));
+            bp.k.Nval = x;
+          }
         }
       }
       p->batches.push_back(bp);
@@ -786,10 +932,6 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
     a.dfield = d_dev;
     a.hist = (mode == MODE_PF_D && hist_dev) ? hist_dev + b.hist_off * 2 : nullptr;
     a.want_K = want_K;
-    {
-      const char* e = getenv("AD4SM_K1_TURNS");
-      a.p2_turns = e ? atoi(e) : 1;
-    }
     a.Ke = p->Ke;
     a.re = p->re;
     a.phie = p->phie;

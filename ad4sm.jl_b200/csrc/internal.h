@@ -62,7 +62,6 @@ struct K1Args {
   // destination-sorted staging: cpos[slot*NPB + block] = position << 1 | transposed; nullptr = element-major staging
   const unsigned* cpos;
   double* C;
-  int p2_turns;         // persistent K1: the two warps of a sub-partition take turns in phase 2 (AD4SM_K1_TURNS, default 1)
   int exp;              // TIMING EXPERIMENT ONLY (AD4SM_EXP_K1, wrong results): 1 = the sorted epilogue stores nothing
   int sorted_tma;       // sorted blocks leave through shared memory + one 80-byte bulk copy each (else plain STG.128)
   // peer staging: slots [first, first+count) are also written to the owner rank's staging over NVLink
@@ -123,6 +122,21 @@ struct PostArgs {
   double *F, *detJ, *vol, *sigma, *Pk;  // outputs in `elems` order; any may be nullptr
 };
 cudaError_t launch_post(const PostArgs& a, cudaStream_t s);
+
+// ---- batched element constructors (construct.cu; elasticelements.jl:35-197, phasefieldelements.jl:9-145) ------------------
+enum ConstructShape { CS_TRIA3 = 1, CS_QUAD4 = 2, CS_TET4 = 3, CS_HEX8 = 4, CS_WDG6 = 5 };
+struct ConstructArgs {
+  int shape, P, ldc;
+  int n_wfac;               // weight factors per Gauss point (tensor rules: D, wedge: 1)
+  int n1d;                  // tensor rules: points per direction (fixes the order in which V is summed); 0 otherwise
+  long long ne;
+  const long long* nodes;   // device [ne][N], 1-based
+  const double* coords;     // device [n_nodes][ldc]
+  double pt[27][3];         // Gauss points, storage order (ξ index fastest)
+  double wfac[27][3];       // wgt = detJ * wfac[0] * wfac[1] * ..., left to right
+  double *gradN, *wgt, *Nval, *V;  // device outputs; Nval, V may be nullptr
+};
+cudaError_t launch_construct(const ConstructArgs& a, cudaStream_t s);
 
 // ---- NCCL plumbing of the partitioned evaluation (dist.cu) ---------------------------------------------------------
 struct DistComm;

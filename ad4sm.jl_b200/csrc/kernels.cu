@@ -154,7 +154,7 @@ static WarpLayout k1p_layout(int D, int N, int P, int LP, bool pf) {
   L.psi_off = off;
   off += rup(EW * P * 8, 16);
   L.bar_off = off;
-  off += 48;  // 4 mbarriers + the phase-2 turn lock of the sub-partition's warp pair (in the lower warp's slice)
+  off += 32;  // 4 mbarriers
   L.bytes = rup(off, 128);
   // epilogue: the element blocks and residual are staged in the (dead) record region when they fit, and leave
   // with one bulk copy each (16-byte granularity)
@@ -342,7 +342,8 @@ __device__ __forceinline__ void k1_phase1(const MatDev* mat, int q, bool valid, 
 template <int D, int N, int PT>
 __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active, bool want_K, bool staged, const double* recs,
                                           const double* gS, double* kout_s, double* rout_s, double* kout_g, double* rout_g,
-                                          const unsigned* cpos_e, double* C, const K1Args& a, long long slot, int* lock) {
+                                          const unsigned* cpos_e, double* C, const K1Args& a, long long slot,
+                                          long long* t_acc = nullptr) {
   constexpr int NO = N / 2 + 1, DD = D * D;
   // destination-sorted staging: this lane's block positions, fetched now so that the loads fly during the contraction
   unsigned cp[NO];
@@ -351,21 +352,8 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
     for (int o = 0; o < NO; o++) cp[o] = (active && o < n_offsets(N, q)) ? __ldg(cpos_e + o * N + q) : 0xffffffffu;
   }
   double acc[NO][DD], rq[D];
-  // Phase 2 is the FP64-dense part: one warp alone keeps the sub-partition's FP64 pipe ~90 % busy (static schedule:
-  // 2.6 cycles per DFMA against the pipe's 2.2), so two warps of a sub-partition inside it at the same time gain nothing
-  // -- and left alone they drift INTO that state and stay there (both slowed equally), leaving the pipe idle while both
-  // run their latency-bound head / phase 1 / epilogue.  The two warps of a sub-partition therefore take turns: whoever
-  // holds the lock runs phase 2 at full rate while the other one's non-FP64 part hides underneath.
-  if (lock) {
-    if ((threadIdx.x & 31) == 0)
-      while (atomicCAS(lock, 0, 1) != 0) __nanosleep(32);
-    __syncwarp();
-  }
   column_u_acc<D, N, PT, VecMem>(q, P, recs, rstride, gS, N, (PT ? PT : P) * N, want_K, acc, rq);
-  if (lock) {
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) atomicExch(lock, 0);
-  }
+  if (t_acc) *t_acc = clock64();  // PROF only (nullptr is a compile-time constant otherwise)
   if (cpos_e) {  // (D == 3 only) every block goes to its own sorted slot
     if constexpr (D == 3) {
       __syncwarp();  // all lanes are done reading the records: their area becomes the staging
@@ -446,7 +434,11 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
 }
 
 // ---- K1, u-dual, persistent, LP lanes per element, TMA-staged inputs ------------------------------
-template <int D, int N, int LP, int MF, bool PF>
+// PROF (developer tool, AD4SM_K1_PROF=1, Hex8 NeoHooke only): lane 0 of every warp accumulates the clock64() cycles of
+// the four parts of its iteration (0 head: TMA issue + waits, 1 phase 1, 2 phase 2 up to the end of the contraction incl.
+// the epilogue stores, 3 rest) in g_k1_prof[gwarp][4]; [4] = iterations.
+__device__ long long g_k1_prof[148 * 8 * 8];
+template <int D, int N, int LP, int MF, bool PF, bool PROF = false>
 __global__ void __launch_bounds__(256, 1)
     k1_u_kernel(const __grid_constant__ K1Args a, const WarpLayout L, const int warps_per_cta) {
   using R = GpRec<D>;
@@ -467,13 +459,6 @@ __global__ void __launch_bounds__(256, 1)
   }
   __syncwarp();
   unsigned char* const ws = ws0;
-  // phase-2 turn lock shared by the warps w and w + 4 (same sub-partition: warp id mod 4), see k1_phase2
-  int* lock = nullptr;
-  if (a.p2_turns && warps_per_cta > 4) {
-    lock = reinterpret_cast<int*>(smraw + (size_t)(warp & 3) * L.bytes + L.bar_off + 32);
-    if (warp < 4 && lane == 0) *lock = 0;
-    __syncthreads();  // once, before any warp can ask for the lock; every warp of the CTA gets here
-  }
 
   // TMA bulk copies of one element group into stage s (∇N per element, wgt, N).  Called by the whole warp: lane 0
   // announces the byte count, then lanes 0..cnt-1 issue one ∇N copy each and lanes EW, EW+1 the small arrays -- the
@@ -514,6 +499,15 @@ __global__ void __launch_bounds__(256, 1)
 
   const int gwarp = blockIdx.x * warps_per_cta + warp;  // global warp id = its first element group
   long long grp = gwarp;
+  long long pt[6] = {0, 0, 0, 0, 0, 0}, pt0 = 0;
+  auto tick = [&](int k) {
+    if constexpr (PROF) {
+      const long long t = clock64();
+      pt[k] += t - pt0;
+      pt0 = t;
+    }
+  };
+  if constexpr (PROF) pt0 = clock64();
   if (grp < n_groups) {
     issue(grp, 0);
     if (lane == 0) {
@@ -542,6 +536,7 @@ __global__ void __launch_bounds__(256, 1)
     if (a.cpos && a.sorted_tma) bulk_wait_read_all();  // sorted staging through per-lane bulk copies: their shared-memory source may be overwritten
     if (lane == 0) bulk_wait_read_all();  // the previous bulk stores have read the staging area (aliases the records)
     __syncwarp();
+    tick(0);
 
     const long long e = grp * EW + el;
     const bool valid = e < a.ne;
@@ -560,6 +555,7 @@ __global__ void __launch_bounds__(256, 1)
     k1_phase1<D, N, LP, MF, PF>(&a.mat, q, valid, P, L.rstride, uS, gS, vS, wS, recs, psiS, ng_ids,
                                 smem_u32(ws + L.u_off + el * L.u_el), a.u, a.dfield, a.dpn);
     __syncwarp();
+    tick(1);
 
     // phase 2: one column node per lane; the element blocks and residual go to the
     // staging area in the (then dead) record region, or straight to global memory when they do not fit
@@ -569,16 +565,24 @@ __global__ void __launch_bounds__(256, 1)
     const bool sorted_tma = sorted && (NPB * CBLK3 * 8 <= L.rec_el) && a.sorted_tma;
     unsigned char* stg = ws + (size_t)el * (sorted ? L.rec_el : L.kout_el);
     constexpr int PTC = (N == 8) ? 8 : ((N == 4) ? 4 : 0);  // the usual Gauss count of the shape, compiled in
+    long long t_acc = 0;
     if (PTC && P == PTC)
       k1_phase2<D, N, PTC>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS,
                            (sorted && !sorted_tma) ? nullptr : reinterpret_cast<double*>(stg),
                            reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
-                           a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot, lock);
+                           a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot, PROF ? &t_acc : nullptr);
     else
       k1_phase2<D, N, 0>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS,
                          (sorted && !sorted_tma) ? nullptr : reinterpret_cast<double*>(stg),
                          reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
-                         a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot, lock);
+                         a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot);
+    if constexpr (PROF) {  // split phase 2 at the end of the contraction: [2] contraction, [5] epilogue stores
+      if (t_acc) {
+        pt[5] += clock64() - t_acc;
+        pt[2] -= clock64() - t_acc;
+      }
+    }
+    tick(2);
     if (valid && q == 0) {  // ϕ_e = Σ_gp w ψ, in Gauss-point order (elasticelements.jl:199-206)
       double ssum = 0.0;
       for (int gp = 0; gp < P; gp++) ssum += psiS[gp];
@@ -607,6 +611,12 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
     __syncwarp();
+    tick(3);
+    pt[4]++;
+  }
+  if constexpr (PROF) {
+    if (lane == 0)
+      for (int k = 0; k < 6; k++) g_k1_prof[(size_t)gwarp * 8 + k] = pt[k];
   }
   if (a.cpos && a.sorted_tma) bulk_wait_read_all();
   if (lane == 0) {
@@ -924,6 +934,24 @@ template <int D, int N, int LP, int MF, bool PF> static cudaError_t launch_u_t(c
     auto kern = k1_u_kernel<D, N, LP, MF, PF>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err != cudaSuccess) return err;
+    if constexpr (D == 3 && N == 8 && MF == MF_NEO && !PF) {
+      static const bool prof = getenv("AD4SM_K1_PROF") != nullptr;
+      if (prof) {  // developer tool: synchronous, prints the per-part cycle split of this launch to stderr
+        auto pk = k1_u_kernel<D, N, LP, MF, PF, true>;
+        if ((err = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return err;
+        pk<<<(unsigned)c.grid, c.warps * 32, smem, s>>>(a, L, c.warps);
+        if ((err = cudaStreamSynchronize(s)) != cudaSuccess) return err;
+        static long long h[148 * 8 * 8];
+        cudaMemcpyFromSymbol(h, g_k1_prof, sizeof(h));
+        double sum[6] = {0, 0, 0, 0, 0, 0};
+        const int nw = c.grid * c.warps;
+        for (int w = 0; w < nw && w < 148 * 8; w++)
+          for (int k = 0; k < 6; k++) sum[k] += (double)h[w * 8 + k];
+        fprintf(stderr, "K1PROF warps/cta %d iters/warp %.1f cycles/iter: head %.0f phase1 %.0f contraction %.0f epilogue %.0f rest %.0f\n",
+                c.warps, sum[4] / nw, sum[0] / sum[4], sum[1] / sum[4], sum[2] / sum[4], sum[5] / sum[4], sum[3] / sum[4]);
+        return cudaSuccess;
+      }
+    }
     kern<<<(unsigned)c.grid, c.warps * 32, smem, s>>>(a, L, c.warps);
     return cudaGetLastError();
   }

@@ -36,7 +36,16 @@ struct Batch                      # struct ad4sm_batch
   mat_params::NTuple{8,Float64}
   n_elems::Int64
   nodes::Ptr{Int64}; gradN::Ptr{Float64}; wgt::Ptr{Float64}; Nval::Ptr{Float64}; orig_index::Ptr{Int64}
+  mesh::Ptr{Cvoid}               # NULL, or an ad4sm_mesh: ∇N / wgt / N constructed on the device (ABI version 2)
 end
+struct Mesh                       # struct ad4sm_mesh
+  shape::Int32; n_gp_1d::Int32
+  gp_xi::NTuple{3,Float64}; gp_w::NTuple{3,Float64}
+  coord_dim::Int32; reserved::Int32
+  n_nodes::Int64
+  coords::Ptr{Float64}
+end
+const SHAPE_TRIA3, SHAPE_QUAD4, SHAPE_TET4, SHAPE_HEX8, SHAPE_WDG6 = Int32.(1:5)
 
 check(rc) = rc == 0 || error("libad4sm_b200: " * unsafe_string(ccall((:ad4sm_last_error, lib), Cstring, ())))
 
@@ -77,8 +86,32 @@ function pack(elems::AbstractVector{E}, idx::Vector{Int}; kw...) where {D,P,M,T,
   kind, base, flags, params = elems[idx[1]].mat isa PhaseField ? matdesc(elems[idx[1]].mat; kw...) : matdesc(elems[idx[1]].mat)
   oi = Int64.(idx .- 1)
   b = Batch(iscp ? ELEM_CP : ELEM_CE, D, P, N, kind, base, flags, 0, pad8(params...), ne,
-            pointer(nodes), pointer(gradN), pointer(wgt), iscp ? pointer(Nval) : C_NULL, pointer(oi))
+            pointer(nodes), pointer(gradN), pointer(wgt), iscp ? pointer(Nval) : C_NULL, pointer(oi), C_NULL)
   Packed(b, Any[nodes, gradN, wgt, Nval, oi])
+end
+
+# ---- batched constructors on the device (ad4sm_construct; elasticelements.jl:35-197, phasefieldelements.jl:9-145) ---------
+# `construct(shape, conn, p0; GP, phasefield)`: what `[Hex08(conn[:,e], p0[conn[:,e]]; GP) for e in ...]` computes, for all
+# elements in two kernels.  conn: N x ne node ids (1-based), p0: dim x nNodes coordinates.  Returns (∇N[N,P,D,ne], wgt[P,ne],
+# N[N,P,ne] or nothing, V[ne]); `elements(...)` wraps them into the reference's element structs.
+const GP2 = ((-0.577350269189626, 1.0), (0.577350269189626, 1.0))
+shape_dims(shape, n) = shape == SHAPE_TRIA3 ? (2, 3, 1) : shape == SHAPE_QUAD4 ? (2, 4, n^2) : shape == SHAPE_TET4 ? (3, 4, 1) :
+                       shape == SHAPE_HEX8 ? (3, 8, n^3) : (3, 6, 6)
+function construct(shape::Int32, conn::Matrix{Int64}, p0::Matrix{Float64}; GP=GP2, phasefield=false)
+  n = shape in (SHAPE_QUAD4, SHAPE_HEX8) ? length(GP) : 0
+  D, N, P = shape_dims(shape, n)
+  size(conn, 1) == N || error("connectivity must be $N x ne")
+  ne = size(conn, 2)
+  xi = ntuple(i -> i <= n ? Float64(GP[i][1]) : 0.0, 3); w = ntuple(i -> i <= n ? Float64(GP[i][2]) : 0.0, 3)
+  gradN = Array{Float64}(undef, N, P, D, ne); wgt = Matrix{Float64}(undef, P, ne); V = Vector{Float64}(undef, ne)
+  Nval = phasefield ? Array{Float64}(undef, N, P, ne) : nothing
+  GC.@preserve p0 begin
+    m = Ref(Mesh(shape, n, xi, w, size(p0, 1), 0, size(p0, 2), pointer(p0)))
+    check(ccall((:ad4sm_construct, lib), Cint,
+                (Ref{Mesh}, Int64, Ptr{Int64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                m, ne, conn, -1, gradN, wgt, Nval === nothing ? C_NULL : Nval, V))
+  end
+  (gradN, wgt, Nval, V)
 end
 
 # ---- plan cache: one plan per (elems object, size(u)) ---------------------------------------------------

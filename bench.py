@@ -154,7 +154,9 @@ def material(cfg, override=None):
 class Workload:
     """One configuration at one size: the SoA batch, u (D x nNodes, column-major), and for C4 d and the history."""
 
-    def __init__(self, cfg, dims=None, jitter=0.0, seed=20261021, mat=None):
+    def __init__(self, cfg, dims=None, jitter=0.0, seed=20261021, mat=None, device_ctor=False):
+        """device_ctor: the product builds its plan from connectivity + coordinates (batched constructors on the GPU,
+        `*_batch(..., device=True)`); the host constructors' arrays are then only made when the oracle asks for them."""
         from ad4sm_b200 import Elements as El, mesh
         c = CONFIGS[cfg]
         dims = tuple(dims or c["n"])
@@ -164,34 +166,46 @@ class Workload:
         self.d = self.hist = None
         if self.shape == "hex8":
             coords, conn = mesh.hex_block(*dims, jitter=jitter, seed=seed)
-            self.batch, self.D = El.Hex08_batch(conn, coords, m), 3
+            ctor, self.D = El.Hex08_batch, 3
         elif self.shape == "tet4":
             coords, conn = mesh.tet_kuhn(*dims, jitter=jitter, seed=seed)
-            self.batch, self.D = El.Tet04_batch(conn, coords, m), 3
+            ctor, self.D = El.Tet04_batch, 3
         elif self.shape == "quad4":
             coords, conn = mesh.quad_grid(*dims, jitter=jitter, seed=seed)
-            self.batch, self.D = El.Quad_batch(conn, coords, m), 2
+            ctor, self.D = El.Quad_batch, 2
         else:
             coords, conn = mesh.quad_grid(*dims, jitter=jitter, seed=seed)
-            self.batch, self.D = El.QuadP_batch(conn, coords, m), 2
+            ctor, self.D = El.QuadP_batch, 2
             self.plan_opts = {"nh2d_extension": True}   # C4 as named needs the plane-strain embedding
             self.d = np.random.default_rng(seed + 3).uniform(0.0, 0.5, len(coords))
+        self._host_ctor = lambda: ctor(conn, coords, m)
+        self._host_batch = None
+        self.batch = ctor(conn, coords, m, device=True) if device_ctor else self.host_batch
+        if self.shape == "quadp":
             self.hist = np.zeros((self.batch.ne, self.batch.P, 2))
         # amplitude relative to the element size of the FULL configuration's generator (h = 1 / max(dims))
         self.u = mesh.random_u(len(coords), self.D, 1.0 / max(dims), a=0.02, seed=seed + 2)
         self.n_nodes = len(coords)
         self.ne = self.batch.ne
 
+    @property
+    def host_batch(self):
+        """the element arrays as the host (numpy) constructors build them -- what the oracle evaluates"""
+        if self._host_batch is None:
+            self._host_batch = self._host_ctor()
+        return self._host_batch
+
     def oracle(self, nthreads=0):
         """the reference-algorithm restatement on this workload: list of (ϕ, r, (colptr, rowval, nzval)) and seconds"""
         from oracle import cxx_binding as X
+        hb = self.host_batch
         t0 = time.perf_counter()
         if self.shape == "quadp":
             kw = dict(nh2d_extension=True)
-            res = [X.make_phi_r_Kt([self.batch], self.u, mode=X.M_PF_U, d=self.d, nthreads=nthreads, **kw),
-                   X.make_phi_r_Kt([self.batch], self.u, mode=X.M_PF_D, d=self.d, hist=[self.hist.copy()], nthreads=nthreads, **kw)]
+            res = [X.make_phi_r_Kt([hb], self.u, mode=X.M_PF_U, d=self.d, nthreads=nthreads, **kw),
+                   X.make_phi_r_Kt([hb], self.u, mode=X.M_PF_D, d=self.d, hist=[self.hist.copy()], nthreads=nthreads, **kw)]
         else:
-            res = [X.make_phi_r_Kt([self.batch], self.u, nthreads=nthreads)]
+            res = [X.make_phi_r_Kt([hb], self.u, nthreads=nthreads)]
         return res, time.perf_counter() - t0
 
     def product(self):
@@ -258,7 +272,7 @@ def parity_check_single(cfg, dims, mat, oracle_res=None, workload=None):
     """The CUDA path against the oracle on a block of the benchmarked configuration: pattern bit-exact, every stored
     value to relative 1e-12 (oracle/check.py).  Reuses the oracle result of the cpu_baseline leg when there is one."""
     from oracle.check import assert_result_parity
-    w = workload or Workload(cfg, dims, mat=mat, jitter=0.1)
+    w = workload or Workload(cfg, dims, mat=mat, jitter=0.1, device_ctor=True)
     ref = oracle_res if oracle_res is not None else w.oracle(nthreads=host_threads())[0]
     got = w.product()
     worst = 0.0
@@ -369,7 +383,7 @@ def run_ours(args):
     t_build0 = time.perf_counter()
     w = None
     if world == 1:
-        w = Workload(cfg, dims, mat=args.material)
+        w = Workload(cfg, dims, mat=args.material, device_ctor=not args.host_constructors)
         t_mesh = time.perf_counter() - t_build0
         t_plan0 = time.perf_counter()
         plan = El.Plan(w.batch, w.n_nodes, w.D, device=local, **w.plan_opts)
@@ -527,7 +541,7 @@ def run_ours(args):
     oracle_res = sample_w = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sdims = tuple(args.cpu_sample) if args.cpu_sample else conf["sample"]
-        sample_w = Workload(cfg, sdims, mat=args.material, jitter=0.1)
+        sample_w = Workload(cfg, sdims, mat=args.material, jitter=0.1, device_ctor=not args.host_constructors)
         nthreads = host_threads()
         oracle_res, dt = sample_w.oracle(nthreads=nthreads)
         cpu = {"value": sample_w.ne / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
@@ -619,6 +633,8 @@ def run_ours(args):
                    "l2": ("working set (∇N, staging, Kt values: GBs per GPU) >> 126 MB L2; no flush needed" if ne_local * b_alg > 5e8 else
                           f"working set {ne_local * b_alg / 1e6:.0f} MB: partly L2-resident between steps (not flushed; launch-latency-bound config)"),
                    "first_call": {"mesh_and_element_constructors_s": t_mesh, "plan_build_s": t_plan, "first_evaluation_s": t_first,
+                                  "constructors": ("host (numpy) + upload" if args.host_constructors or world > 1 else
+                                                   "batched on the device inside plan_build (ad4sm_batch.mesh)"),
                                   "note": "paid once per `elems`; every later makeϕrKt on the same elems costs ms_per_step"}},
         "clocks": dict(clk.summary(), note="sampled every 50 ms over the timed region and ~0.4 s more of the same load"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -697,6 +713,8 @@ def main():
     ap.add_argument("--mesh-nz", "--nz", dest="nz", type=int, default=0, help="override: element layers (per GPU for weak scaling)")
     ap.add_argument("--material", default=None, choices=["neohooke", "ogden"], help="override the Hex8 configurations' material")
     ap.add_argument("--cpu-sample", type=int, nargs="+", default=None, help="dims of the CPU sample block (default per config)")
+    ap.add_argument("--host-constructors", action="store_true",
+                    help="build ∇N / wgt with the host (numpy) constructors and upload them, instead of the batched device constructors")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-e2e-full", action="store_true")

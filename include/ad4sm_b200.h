@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AD4SM_ABI_VERSION 1
+#define AD4SM_ABI_VERSION 2
 
 /* status codes */
 #define AD4SM_OK 0
@@ -63,6 +63,26 @@ extern "C" {
 #define AD4SM_FIELD_U 0 /* displacement dofs: dofs_per_node per node */
 #define AD4SM_FIELD_D 1 /* phase-field dofs: 1 per node (makeϕrKt_d) */
 
+/* Element shapes of the batched constructors (ad4sm_construct, ad4sm_batch.mesh): the reference constructor each one
+ * replaces for a whole group of elements at once. */
+#define AD4SM_SHAPE_TRIA3 1 /* Tria, TriaP               elasticelements.jl:35-46,   phasefieldelements.jl:9-24    D=2 N=3 P=1 */
+#define AD4SM_SHAPE_QUAD4 2 /* Quad, QuadR, QuadP[R]     elasticelements.jl:50-80,   phasefieldelements.jl:25-55   D=2 N=4 P=n^2 */
+#define AD4SM_SHAPE_TET4 3  /* Tet04, Tet04P             elasticelements.jl:81-96,   phasefieldelements.jl:129-145 D=3 N=4 P=1 */
+#define AD4SM_SHAPE_HEX8 4  /* Hex08, Hex08R, Hex08P[R]  elasticelements.jl:129-162, phasefieldelements.jl:56-94   D=3 N=8 P=n^3 */
+#define AD4SM_SHAPE_WDG6 5  /* Wdg06, Wdg06P             elasticelements.jl:163-197, phasefieldelements.jl:95-128  D=3 N=6 P=6 */
+
+/* Node coordinates + integration rule: what the reference constructors take as `p0` and `GP=`. */
+typedef struct ad4sm_mesh {
+  int32_t shape;        /* AD4SM_SHAPE_* */
+  int32_t n_gp_1d;      /* QUAD4 / HEX8: points per direction of the tensor rule (1..3), the length of `GP=`; else ignored */
+  double gp_xi[3];      /* the rule's abscissae and weights, GP = ((xi_1, w_1), ...) */
+  double gp_w[3];
+  int32_t coord_dim;    /* doubles per node in `coords` (>= D; extra components are ignored) */
+  int32_t reserved;
+  int64_t n_nodes;
+  const double* coords; /* [n_nodes][coord_dim] host */
+} ad4sm_mesh;
+
 /* One homogeneous group of elements: same element type parameters (kind, D, P, N) and the same
  * material.  This is the SoA packing of a `Vector{CEElem}` / `Vector{CPElem}`
  * (elements.jl:71-77,104-111); array layouts follow the reference's nesting order. */
@@ -85,6 +105,8 @@ typedef struct ad4sm_batch {
                                 summation order); NULL = the element's slot, i.e. its position in the
                                 concatenation of ALL batches in the order given (not "after the largest
                                 key so far": give every batch an orig_index when any batch has one) */
+  const ad4sm_mesh* mesh;    /* NULL, or: construct gradN / wgt / Nval on the device from the node coordinates (the three
+                                pointers above are then ignored); dim, n_gauss, n_elem_nodes must match mesh->shape */
 } ad4sm_batch;
 
 typedef struct ad4sm_plan ad4sm_plan; /* opaque: device copies of the batches + CSC pattern + scatter maps */
@@ -114,6 +136,16 @@ int ad4sm_device_count(int* count);
 int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_nodes, int32_t dofs_per_node,
                       int32_t device, ad4sm_plan** plan_out);
 void ad4sm_plan_destroy(ad4sm_plan* plan);
+
+/* The reference's element constructors for a whole group at once, on the device: writes what
+ * `Hex08(nodes, p0; GP)` etc. store per element -- ∇N as [n_elems][D][P][N], wgt [n_elems][P], N values
+ * [n_elems][P][N] (phase-field constructors; NULL to skip) and elem.V [n_elems] (NULL to skip) -- into host arrays.
+ * `nodes` [n_elems][N] 1-based.  ad4sm_construct_device writes device arrays instead (same layouts) and returns after the
+ * kernels have finished. */
+int ad4sm_construct(const ad4sm_mesh* mesh, int64_t n_elems, const int64_t* nodes, int32_t device, double* gradN, double* wgt,
+                    double* Nval, double* V);
+int ad4sm_construct_device(const ad4sm_mesh* mesh, int64_t n_elems, const int64_t* nodes, int32_t device, double* gradN_dev,
+                           double* wgt_dev, double* Nval_dev, double* V_dev);
 
 /* Structural CSC pattern of Kt (before dropzeros) for a field: sizes, then the arrays. */
 int ad4sm_plan_pattern_size(ad4sm_plan* plan, int32_t field, int64_t* n_dof, int64_t* nnz);

@@ -34,8 +34,9 @@ def test_header_constants_match_python_mirror():
         py = {"ABI_VERSION": None, "OK": "OK"}.get(name, name)
         if py and hasattr(capi, py):
             assert getattr(capi, py) == int(val), name
-    assert capi.lib().ad4sm_abi_version() == 1
-    assert C.sizeof(capi.Batch) == 8 * 4 + 8 * 8 + 8 + 5 * 8
+    assert capi.lib().ad4sm_abi_version() == 2
+    assert C.sizeof(capi.Batch) == 8 * 4 + 8 * 8 + 8 + 6 * 8
+    assert C.sizeof(capi.Mesh) == 2 * 4 + 6 * 8 + 2 * 4 + 8 + 8
 
 
 @pytest.mark.skipif(capi.device_count() > 0, reason="needs a box WITHOUT a GPU")
