@@ -9,12 +9,125 @@ What runs where
     (north_star): it stays on a host sparse direct solver.  In Julia that is UMFPACK's `lu`; here, where the host
     language is Python, it is `scipy.sparse.linalg.splu` -- passed in as `solve`, so any other solver can be used.
 
-Same argument names, defaults and control flow as the reference; constraint equations (`eqns`, the nEqs != 0 branch)
-are closures evaluated by the reference itself and are not covered.
+Same argument names, defaults and control flow as the reference.
+
+Constraint equations (`ConstEq`, `makeϕrKt(eqns, u, λ)`, solvers.jl:17-73): the reference stores an arbitrary closure per
+equation, which cannot cross a C ABI.  Offered instead is a CATALOGUE -- every constraint that is a polynomial of degree
+<= 2 in its dofs, ϕ(v) = ½ vᵀQv + cᵀv - c0 with v = u[iDoFs] (`ConstEq.linear`, `.quadratic`, and the usual special cases
+`.periodic`, `.tie`, `.average`, `.distance`) -- evaluated on the GPU by `ad4sm_consteq_eval` and assembled into the same
+three results the reference returns: veqs, reqs (nDoFs x nEqs sparse), Keqs (nDoFs x nDoFs sparse).
 """
 from __future__ import annotations
 
+import ctypes as C
+from dataclasses import dataclass
+
 import numpy as np
+
+from . import _capi as capi
+
+
+@dataclass
+class ConstEq:
+    """`ConstEq(func, iDoFs)` (solvers.jl:17-22) restricted to the catalogue ϕ(v) = ½ vᵀQv + cᵀv - c0, v = u[iDoFs].
+    iDoFs: 1-based linear indices into u[:] (column-major, like the reference)."""
+    iDoFs: np.ndarray
+    c: np.ndarray
+    c0: float = 0.0
+    Q: np.ndarray | None = None
+
+    def __post_init__(self):
+        self.iDoFs = np.ascontiguousarray(self.iDoFs, dtype=np.int64).reshape(-1)
+        self.c = np.ascontiguousarray(self.c, dtype=np.float64).reshape(-1)
+        n = len(self.iDoFs)
+        if len(self.c) != n:
+            raise ValueError("ConstEq: c and iDoFs must have the same length")
+        if self.Q is not None:
+            self.Q = np.asfortranarray(self.Q, dtype=np.float64)
+            if self.Q.shape != (n, n) or not np.array_equal(self.Q, self.Q.T):
+                raise ValueError("ConstEq: Q must be a symmetric n x n matrix")
+
+    # ---- the catalogue --------------------------------------------------------------------------------------------
+    @classmethod
+    def linear(cls, iDoFs, c, c0=0.0):
+        """Σ c_k u_k = c0"""
+        return cls(iDoFs, c, c0)
+
+    @classmethod
+    def quadratic(cls, iDoFs, Q, c=None, c0=0.0):
+        """½ vᵀQv + cᵀv = c0"""
+        n = len(np.atleast_1d(iDoFs))
+        return cls(iDoFs, np.zeros(n) if c is None else c, c0, Q)
+
+    @classmethod
+    def periodic(cls, dof_a, dof_b, jump=0.0):
+        """u_a - u_b = jump  (periodic boundary condition with a prescribed macroscopic jump)"""
+        return cls([dof_a, dof_b], [1.0, -1.0], jump)
+
+    @classmethod
+    def tie(cls, dof_slave, dofs_master, weights):
+        """u_slave = Σ w_k u_master,k  (multi-point tie / hanging node)"""
+        return cls([dof_slave, *dofs_master], [1.0, *(-np.asarray(weights, dtype=float))], 0.0)
+
+    @classmethod
+    def average(cls, iDoFs, value=0.0, weights=None):
+        """Σ w_k u_k = value  (prescribed weighted average, default w = 1/n)"""
+        n = len(iDoFs)
+        return cls(iDoFs, np.full(n, 1.0 / n) if weights is None else weights, value)
+
+    @classmethod
+    def distance(cls, dofs_a, dofs_b, x_a, x_b, length):
+        """|x_a + u_a - x_b - u_b|² = length²  (rigid link between two nodes; dofs_a/dofs_b: the D dofs of each node)"""
+        D = len(dofs_a)
+        dx = np.asarray(x_a, dtype=float) - np.asarray(x_b, dtype=float)
+        S = np.hstack([np.eye(D), -np.eye(D)])     # u_a - u_b = S v
+        return cls([*dofs_a, *dofs_b], 2.0 * (S.T @ dx), float(length) ** 2 - float(dx @ dx), 2.0 * (S.T @ S))
+
+
+def makeϕrKt(eqns, u, λ, device=-1):
+    """`makeϕrKt(eqns::Array{ConstEq}, u, λ)` (solvers.jl:24-73) for catalogue constraints, evaluated on the GPU.
+    Returns (veqs [nEqs], reqs scipy CSC nDoFs x nEqs, Keqs scipy CSC nDoFs x nDoFs): veqs[ii] = ϕ_ii, reqs[iDoFs,ii] =
+    grad, Keqs[iDoFs,iDoFs] += λ[ii] hess, in equation order.  (The reference's `Distributed` chunking, :36-50, only changes
+    who evaluates which equation; the sums are the same.)"""
+    import scipy.sparse as sp
+    nE = len(eqns)
+    uf = np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(-1, order="F"))
+    nD = uf.size
+    lam = np.ascontiguousarray(λ, dtype=np.float64).reshape(-1)
+    if lam.size != nE:
+        raise ValueError("λ must have one entry per equation")
+    if nE == 0:
+        return np.zeros(0), sp.csc_matrix((nD, 0)), sp.csc_matrix((nD, nD))
+    sizes = np.array([len(e.iDoFs) for e in eqns], dtype=np.int64)
+    dof_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    dofs = np.concatenate([e.iDoFs for e in eqns]).astype(np.int64)
+    c = np.concatenate([e.c for e in eqns])
+    c0 = np.array([e.c0 for e in eqns], dtype=np.float64)
+    qs = np.array([0 if e.Q is None else e.Q.size for e in eqns], dtype=np.int64)
+    q_ptr = np.concatenate([[0], np.cumsum(qs)]).astype(np.int64)
+    Q = np.concatenate([np.zeros(0)] + [e.Q.reshape(-1, order="F") for e in eqns if e.Q is not None])
+    veqs, grad, hess = np.empty(nE), np.empty(len(dofs)), np.empty(len(Q))
+    s = capi.ConstEqSet(nE, dof_ptr.ctypes.data, dofs.ctypes.data, c.ctypes.data, c0.ctypes.data, q_ptr.ctypes.data,
+                        Q.ctypes.data if len(Q) else None)
+    capi.check(capi.lib().ad4sm_consteq_eval(C.byref(s), nD, uf.ctypes.data, lam.ctypes.data, device, veqs.ctypes.data,
+                                             grad.ctypes.data, hess.ctypes.data if len(Q) else None))
+    cols = np.repeat(np.arange(nE), sizes)
+    # reqs[iDoFs, ii] = grad: an assignment -- a dof listed twice in one equation keeps its LAST value
+    last = {}
+    for k, (i, j) in enumerate(zip(dofs - 1, cols)):
+        last[(i, j)] = k
+    keep = np.fromiter(last.values(), dtype=np.int64)
+    reqs = sp.csc_matrix((grad[keep], (dofs[keep] - 1, cols[keep])), shape=(nD, nE))
+    II, JJ, VV = [], [], []
+    for ii, e in enumerate(eqns):
+        if e.Q is not None:
+            n = len(e.iDoFs)
+            II.append(np.tile(e.iDoFs - 1, n))
+            JJ.append(np.repeat(e.iDoFs - 1, n))
+            VV.append(hess[q_ptr[ii]:q_ptr[ii + 1]])
+    Keqs = (sp.csc_matrix((np.concatenate(VV), (np.concatenate(II), np.concatenate(JJ))), shape=(nD, nD)) if II
+            else sp.csc_matrix((nD, nD)))
+    return veqs, reqs, Keqs
 
 
 def _splu_solve(K, rhs):

@@ -25,6 +25,11 @@ class Mesh(C.Structure):
                 ("coord_dim", C.c_int32), ("reserved", C.c_int32), ("n_nodes", C.c_int64), ("coords", C.c_void_p)]
 
 
+class ConstEqSet(C.Structure):
+    _fields_ = [("n_eqs", C.c_int64), ("dof_ptr", C.c_void_p), ("dofs", C.c_void_p), ("c", C.c_void_p), ("c0", C.c_void_p),
+                ("q_ptr", C.c_void_p), ("Q", C.c_void_p)]
+
+
 class Batch(C.Structure):
     _fields_ = [
         ("elem_kind", C.c_int32), ("dim", C.c_int32), ("n_gauss", C.c_int32), ("n_elem_nodes", C.c_int32),
@@ -90,6 +95,8 @@ SIGNATURES = {
     "ad4sm_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "ad4sm_plan_create": (C.c_int, [C.POINTER(Batch), C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "ad4sm_plan_destroy": (None, [C.c_void_p]),
+    "ad4sm_consteq_eval": (C.c_int, [C.POINTER(ConstEqSet), C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
     "ad4sm_construct": (C.c_int, [C.POINTER(Mesh), C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ad4sm_construct_device": (C.c_int, [C.POINTER(Mesh), C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),

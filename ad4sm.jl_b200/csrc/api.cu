@@ -355,6 +355,58 @@ int ad4sm_construct(const ad4sm_mesh* mesh, int64_t n_elems, const int64_t* node
   return AD4SM_OK;
 }
 
+int ad4sm_consteq_eval(const ad4sm_consteq* q, int64_t n_dof, const double* u, const double* lambda, int32_t device, double* veqs,
+                       double* grad, double* hess) {
+  if (!q || !u || !veqs || !grad || n_dof <= 0) return fail(AD4SM_EINVAL, "consteq: arguments missing");
+  if (q->n_eqs < 0 || (q->n_eqs > 0 && (!q->dof_ptr || !q->dofs || !q->c || !q->c0))) return fail(AD4SM_EINVAL, "consteq: arrays missing");
+  if (q->n_eqs == 0) return AD4SM_OK;
+  const long long nd = q->dof_ptr[q->n_eqs], nq = q->q_ptr ? q->q_ptr[q->n_eqs] : 0;
+  for (long long ii = 0; ii < q->n_eqs; ii++) {
+    const long long n = q->dof_ptr[ii + 1] - q->dof_ptr[ii];
+    if (n < 0) return fail(AD4SM_EINVAL, "consteq: dof_ptr must be non-decreasing");
+    if (q->q_ptr) {
+      const long long m = q->q_ptr[ii + 1] - q->q_ptr[ii];
+      if (m != 0 && m != n * n) return fail(AD4SM_EINVAL, "consteq: Q of an equation must be empty or n x n");
+    }
+  }
+  if (nq > 0 && !q->Q) return fail(AD4SM_EINVAL, "consteq: Q missing");
+  for (long long k = 0; k < nd; k++)
+    if (q->dofs[k] < 1 || q->dofs[k] > n_dof) return fail(AD4SM_EINVAL, "consteq: dof index out of range 1..length(u) (BoundsError)");
+  int rc = select_device(device);
+  if (rc) return rc;
+  // one device buffer: [dof_ptr | dofs | q_ptr] int64, then [c | c0 | Q | u | lambda | veqs | grad | hess] doubles
+  const size_t ni = (size_t)(q->n_eqs + 1) * 2 + (size_t)nd;
+  const size_t nf = (size_t)nd * 2 + (size_t)q->n_eqs * 3 + (size_t)nq * 2 + (size_t)n_dof;
+  char* buf = nullptr;
+  CK(cudaMalloc((void**)&buf, ni * 8 + nf * 8 + 64));
+  long long* ip = (long long*)buf;
+  double* fp = (double*)(buf + ni * 8);
+  ConstEqArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_eqs = q->n_eqs;
+  long long *d_ptr = ip, *d_dofs = d_ptr + q->n_eqs + 1, *d_qptr = d_dofs + nd;
+  double *d_c = fp, *d_c0 = d_c + nd, *d_Q = d_c0 + q->n_eqs, *d_u = d_Q + nq, *d_lam = d_u + n_dof, *d_v = d_lam + q->n_eqs,
+         *d_g = d_v + q->n_eqs, *d_h = d_g + nd;
+  cudaError_t e = cudaMemcpy(d_ptr, q->dof_ptr, 8 * (size_t)(q->n_eqs + 1), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_dofs, q->dofs, 8 * (size_t)nd, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && q->q_ptr) e = cudaMemcpy(d_qptr, q->q_ptr, 8 * (size_t)(q->n_eqs + 1), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_c, q->c, 8 * (size_t)nd, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_c0, q->c0, 8 * (size_t)q->n_eqs, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nq) e = cudaMemcpy(d_Q, q->Q, 8 * (size_t)nq, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_u, u, 8 * (size_t)n_dof, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && lambda) e = cudaMemcpy(d_lam, lambda, 8 * (size_t)q->n_eqs, cudaMemcpyHostToDevice);
+  a.dof_ptr = d_ptr, a.dofs = d_dofs, a.q_ptr = q->q_ptr ? d_qptr : nullptr;
+  a.c = d_c, a.c0 = d_c0, a.Q = d_Q, a.u = d_u, a.lambda = lambda ? d_lam : nullptr;
+  a.veqs = d_v, a.grad = d_g, a.hess = (hess && nq) ? d_h : nullptr;
+  if (e == cudaSuccess) e = launch_consteq(a, (cudaStream_t)0);
+  if (e == cudaSuccess) e = cudaMemcpy(veqs, d_v, 8 * (size_t)q->n_eqs, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(grad, d_g, 8 * (size_t)nd, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && a.hess) e = cudaMemcpy(hess, d_h, 8 * (size_t)nq, cudaMemcpyDeviceToHost);
+  cudaFree(buf);
+  if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("consteq: ") + cudaGetErrorString(e));
+  return AD4SM_OK;
+}
+
 void ad4sm_plan_destroy(ad4sm_plan* p) {
   if (!p) return;
   cudaSetDevice(p->device);

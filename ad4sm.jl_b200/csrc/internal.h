@@ -138,6 +138,21 @@ struct ConstructArgs {
 };
 cudaError_t launch_construct(const ConstructArgs& a, cudaStream_t s);
 
+// ---- constraint-equation catalogue (consteq.cu; solvers.jl:17-22, 54-73) ----------------------------------------------------
+struct ConstEqArgs {
+  long long n_eqs;
+  const long long* dof_ptr;  // [n_eqs+1]
+  const long long* dofs;     // 1-based linear indices into u[:]
+  const double* c;           // linear coefficients, aligned with dofs
+  const double* c0;          // [n_eqs]
+  const long long* q_ptr;    // [n_eqs+1] offsets into Q (an equation without Q has an empty range), or nullptr
+  const double* Q;           // per equation n x n, column-major, symmetric
+  const double* u;           // [n_dof]
+  const double* lambda;      // [n_eqs] or nullptr
+  double *veqs, *grad, *hess;
+};
+cudaError_t launch_consteq(const ConstEqArgs& a, cudaStream_t s);
+
 // ---- NCCL plumbing of the partitioned evaluation (dist.cu) ---------------------------------------------------------
 struct DistComm;
 struct DistXfer {

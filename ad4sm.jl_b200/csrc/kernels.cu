@@ -433,6 +433,7 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
   }
 }
 
+
 // ---- K1, u-dual, persistent, LP lanes per element, TMA-staged inputs ------------------------------
 // PROF (developer tool, AD4SM_K1_PROF=1, Hex8 NeoHooke only): lane 0 of every warp accumulates the clock64() cycles of
 // the four parts of its iteration (0 head: TMA issue + waits, 1 phase 1, 2 phase 2 up to the end of the contraction incl.
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(256, 1)
       k1_phase2<D, N, 0>(q, P, L.rstride, active, a.want_K != 0, staged, recs, gS,
                          (sorted && !sorted_tma) ? nullptr : reinterpret_cast<double*>(stg),
                          reinterpret_cast<double*>(stg + L.re_off), a.Ke + slot * (long long)(NPB * DD),
-                         a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot);
+                         a.re + slot * (long long)(N * D), cpos_e, a.C, a, slot, PROF ? &t_acc : nullptr);
     if constexpr (PROF) {  // split phase 2 at the end of the contraction: [2] contraction, [5] epilogue stores
       if (t_acc) {
         pt[5] += clock64() - t_acc;

@@ -210,6 +210,28 @@ typedef struct ad4sm_newton_view {
 int ad4sm_newton_reduce_device(ad4sm_plan* plan, int32_t field, int32_t kind, const double* fe_dev, const double* ducnst_dev);
 int ad4sm_newton_view_get(ad4sm_plan* plan, int32_t field, ad4sm_newton_view* view);
 
+/* ---- constraint equations from a fixed catalogue (Solvers.makeϕrKt(eqns, u, λ), solvers.jl:17-22, 24-73) ----
+ * The reference's ConstEq holds an arbitrary closure `func`, evaluated with D2 duals: veqs[ii] = val, reqs[iDoFs,ii] =
+ * grad, Keqs[iDoFs,iDoFs] += λ[ii] hess.  A closure cannot cross a C ABI; the catalogue offered instead is every
+ * constraint that is a polynomial of degree <= 2 in its dofs (periodic boundary conditions, ties, prescribed averages,
+ * rigid links / distances):   ϕ(v) = 1/2 v'Qv + c'v - c0,  v = u[iDoFs].
+ * Equation ii owns dofs[dof_ptr[ii] .. dof_ptr[ii+1]) (1-based linear indices into u[:], the reference's iDoFs), the
+ * coefficients c at the same positions, and optionally a symmetric n x n matrix Q (column-major) at Q[q_ptr[ii] ..
+ * q_ptr[ii+1]) -- an empty range, or q_ptr == NULL, makes the equation linear.  Outputs keep that layout:
+ *   veqs [n_eqs];  grad aligned with dofs (= what is assigned to reqs[iDoFs, ii]);  hess aligned with Q (= λ[ii] hess(ϕ),
+ *   the increment of Keqs[iDoFs, iDoFs]; NULL to skip).  All arrays host memory. */
+typedef struct ad4sm_consteq {
+  int64_t n_eqs;
+  const int64_t* dof_ptr; /* [n_eqs+1] */
+  const int64_t* dofs;
+  const double* c;
+  const double* c0;       /* [n_eqs] */
+  const int64_t* q_ptr;   /* [n_eqs+1] or NULL */
+  const double* Q;
+} ad4sm_consteq;
+int ad4sm_consteq_eval(const ad4sm_consteq* eqns, int64_t n_dof, const double* u, const double* lambda, int32_t device,
+                       double* veqs, double* grad, double* hess);
+
 /* ---- batched post-processing with first derivatives (elements.toolkit.jl:8-132), one value per element in `elems`
  * order; any output may be NULL.  D = element dimension, matrices column-major like Julia's SMatrix{D,D}:
  *   F     [ne][D*D]  getF(elem, u[:,elem.nodes]) = I + Σ_gp wgt ∇u_gp / V          (toolkit:8-27)
