@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -120,12 +121,13 @@ struct ad4sm_plan {
   long long prof_launches[AD4SM_PROF_NCLASS] = {0, 0, 0, 0};
   EvSet* ev_cur = nullptr;  // events of the evaluation in flight between the elements and assemble stages
   int elements_mode = -1;
-  // destination-sorted staging (single 3-D batch of a persistent-kernel shape, dpn == 3)
+  // destination-sorted staging (3-D elements, dpn == 3, evaluated batches before the HALO batches)
   bool sorted_built = false, sorted_on = true, sorted_last = false;
   long long n_pairs = 0;
   unsigned *cpos = nullptr, *cptr = nullptr, *out_up = nullptr, *out_lo = nullptr, *nn_pack = nullptr;
   double* C = nullptr;
   long long n_own_sorted = 0;  // slots [n_own_sorted, ne) are HALO: scattered into C before K2s
+  int n_own_batches = 0;       // evaluated (non-HALO) batches; the partitioned-run features (export ranges, peer links) know one
   bool dist_aware = false;     // the caller declared its export ranges / peer links (ad4sm_peer_attach / ad4sm_export_ranges)
   // peer staging / export ranges
   int n_xr = 0, n_xr_local = 0;
@@ -481,6 +483,15 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
   if (dev >= ndev) return fail(AD4SM_EINVAL, "device ordinal out of range");
   CK(cudaSetDevice(dev));
 
+  // AD4SM_PLAN_TIMING=1: wall time of every stage of the plan construction to stderr (developer tool)
+  static const bool plan_timing = getenv("AD4SM_PLAN_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto stage = [&](const char* what) {
+    if (!plan_timing) return;
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "PLAN %-28s %.3f s\n", what, std::chrono::duration<double>(t - t_last).count());
+    t_last = t;
+  };
   // ---- host-side maps ---------------------------------------------------------------------------
   // slots: position in the concatenation of the batches; `key`: position in `elems` (summation order)
   std::vector<int> nodes0((size_t)ne * N);
@@ -505,6 +516,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
   for (long long s = 0; s < ne; s++) order[s] = (unsigned)s;
   if (keyed) std::stable_sort(order.begin(), order.end(), [&](unsigned x, unsigned y) { return key[x] < key[y]; });
 
+  stage("nodes, keys, order");
   // node -> (slot, local node) adjacency, lists in summation order
   std::vector<unsigned> adj_ptr(n_nodes + 1, 0), adj((size_t)ne * N);
   for (size_t i = 0; i < nodes0.size(); i++) adj_ptr[nodes0[i] + 1]++;
@@ -516,6 +528,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       for (int a = 0; a < N; a++) adj[cur[nodes0[(size_t)s * N + a]]++] = s * (unsigned)N + a;
     }
   }
+  stage("adjacency");
   // neighbour lists (sorted, unique) = block columns of each row node
   std::vector<unsigned> nbr_ptr(n_nodes + 1, 0);
 #pragma omp parallel
@@ -540,11 +553,18 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       nbr_ptr[i + 1] = (unsigned)tot;
     }
   }
+  stage("neighbour counts");
   const long long n_blocks = nbr_ptr[n_nodes];
   std::vector<unsigned> nbr(n_blocks), blk_row(n_blocks), blk_ptr(n_blocks + 1, 0);
+  // pidx[s * N + b]: position of node b of adjacency entry s's element in the neighbour list of the entry's node -- found
+  // once (binary search) and reused by the source map and by the destination-sorted tables
+  bool small_rows = true;
+  for (long long i = 0; i < n_nodes && small_rows; i++) small_rows = nbr_ptr[i + 1] - nbr_ptr[i] <= 0xffffu;
+  std::vector<unsigned short> pidx(small_rows ? (size_t)ne * N * N : 0);
 #pragma omp parallel
   {
     std::vector<int> tmp;
+    std::vector<unsigned> cnt;
 #pragma omp for schedule(static)
     for (long long i = 0; i < n_nodes; i++) {
       tmp.clear();
@@ -560,16 +580,26 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
         blk_row[b0 + p] = (unsigned)i;
       }
       // source counts per block
+      cnt.assign(tmp.size(), 0);
       for (unsigned s = adj_ptr[i]; s < adj_ptr[i + 1]; s++) {
         const unsigned slot = adj[s] / N;
         for (int b = 0; b < N; b++) {
           const int nb = nodes0[(size_t)slot * N + b];
           const size_t p = std::lower_bound(tmp.begin(), tmp.end(), nb) - tmp.begin();
-          blk_ptr[b0 + p + 1]++;
+          if (small_rows) pidx[(size_t)s * N + b] = (unsigned short)p;
+          cnt[p]++;
         }
       }
+      for (size_t p = 0; p < tmp.size(); p++) blk_ptr[b0 + p + 1] = cnt[p];
     }
   }
+  auto pos_of = [&](long long i, unsigned s, int b) -> unsigned {  // position of that node in row i's neighbour list
+    if (small_rows) return pidx[(size_t)s * N + b];
+    const unsigned* lo = nbr.data() + nbr_ptr[i];
+    const unsigned nb = (unsigned)nodes0[(size_t)(adj[s] / N) * N + b];
+    return (unsigned)(std::lower_bound(lo, (const unsigned*)(nbr.data() + nbr_ptr[i + 1]), nb) - lo);
+  };
+  stage("neighbour lists, block counts");
   for (long long k = 0; k < n_blocks; k++) blk_ptr[k + 1] += blk_ptr[k];
   std::vector<unsigned> src((size_t)ne * N * N);
 #pragma omp parallel
@@ -579,12 +609,10 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     for (long long i = 0; i < n_nodes; i++) {
       const unsigned b0 = nbr_ptr[i], nn = nbr_ptr[i + 1] - b0;
       cur.assign(nn, 0);
-      const unsigned* nb_i = nbr.data() + b0;
       for (unsigned s = adj_ptr[i]; s < adj_ptr[i + 1]; s++) {
         const unsigned slot = adj[s] / N, a = adj[s] % N;
         for (int b = 0; b < N; b++) {
-          const unsigned nb = (unsigned)nodes0[(size_t)slot * N + b];
-          const size_t p = std::lower_bound(nb_i, nb_i + nn, nb) - nb_i;
+          const unsigned p = pos_of(i, s, b);
           int idx, tr;
           pair_slot(N, (int)a, b, idx, tr);
           src[blk_ptr[b0 + p] + cur[p]++] = ((slot * (unsigned)NPB + (unsigned)idx) << 1) | (unsigned)tr;
@@ -593,6 +621,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     }
   }
 
+  stage("source map");
   // ---- device side ------------------------------------------------------------------------------
   ad4sm_plan* p = new ad4sm_plan;
   p->device = dev;
@@ -660,6 +689,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       }
     }
   }
+  stage("streams, upload slices");
   if (keyed) TRY(dev_upload(p, &p->key_dev, key.data(), key.size()));
   TRY(dev_upload(p, &p->blk_row, blk_row.data(), blk_row.size()));
   TRY(dev_upload(p, &p->nbr_ptr, nbr_ptr.data(), nbr_ptr.size()));
@@ -717,6 +747,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       h0 += B.n_elems * B.n_gauss;
     }
   }
+  stage("map + element uploads / constructors");
   {  // HALO slots get a second set of rows behind the staging (receive buffer B of the peer-push protocol)
     long long nh = 0;
     for (int b = 0; b < n_batches; b++)
@@ -747,48 +778,96 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     TRY(dev_alloc(p, &p->d_dev, (size_t)n_nodes));
     TRY(dev_alloc(p, &p->hist_dev, (size_t)n_gp * 2));
   }
+  stage("output allocations");
   // ---- destination-sorted staging: contributions grouped by unordered node pair, in `elems` order inside a pair ----
   {
     const char* env = getenv("AD4SM_SORTED");
-    K1Config c;
-    const ad4sm_batch& B0 = batches[0];
-    bool rest_halo = true;
-    for (int b = 1; b < n_batches; b++) rest_halo &= (batches[b].batch_flags & AD4SM_BATCH_HALO) != 0;
-    if (!(env && env[0] == '0') && rest_halo && !(B0.batch_flags & AD4SM_BATCH_HALO) && D == 3 && dofs_per_node == 3 &&
-        k1_config(D, N, B0.n_gauss, B0.elem_kind == AD4SM_ELEM_CP && B0.mat_kind == AD4SM_MAT_PHASEFIELD, B0.n_elems, &c) &&
+    // every evaluated (non-HALO) batch must come before the HALO batches and have a K1 that writes sorted blocks
+    bool shape_ok = !(batches[0].batch_flags & AD4SM_BATCH_HALO);
+    bool seen_halo = false;
+    long long n_own = 0;
+    int n_own_batches = 0;
+    for (int b = 0; b < n_batches && shape_ok; b++) {
+      const ad4sm_batch& B = batches[b];
+      if (B.batch_flags & AD4SM_BATCH_HALO) {
+        seen_halo = true;
+        continue;
+      }
+      K1Config c;
+      shape_ok = !seen_halo && k1_config(D, N, B.n_gauss, B.elem_kind == AD4SM_ELEM_CP && B.mat_kind == AD4SM_MAT_PHASEFIELD, B.n_elems, &c);
+      n_own += B.n_elems;
+      n_own_batches++;
+    }
+    p->n_own_batches = n_own_batches;
+    if (!(env && env[0] == '0') && shape_ok && D == 3 && dofs_per_node == 3 &&
         (double)n_blocks * 9.0 < 4.0e9 && (double)ne * NPB < 2.0e9 && n_blocks < (1ll << 31)) {
-      std::vector<unsigned> up_index(n_blocks, 0xffffffffu);
-      long long U = 0;
-      for (long long i = 0; i < n_nodes; i++)
-        for (unsigned b = nbr_ptr[i]; b < nbr_ptr[i + 1]; b++)
-          if (nbr[b] >= (unsigned)i) up_index[b] = (unsigned)U++;
+      // pairs {i <= p} are numbered row by row; in a (sorted) neighbour list the upper ones are the tail
+      std::vector<unsigned> up0(n_nodes + 1, 0), first_up(n_nodes);
+#pragma omp parallel for schedule(static)
+      for (long long i = 0; i < n_nodes; i++) {
+        const unsigned* lo = nbr.data() + nbr_ptr[i];
+        const unsigned* hi = nbr.data() + nbr_ptr[i + 1];
+        first_up[i] = (unsigned)(std::lower_bound(lo, hi, (unsigned)i) - lo);
+        up0[i + 1] = (unsigned)(hi - lo) - first_up[i];
+      }
+      for (long long i = 0; i < n_nodes; i++) up0[i + 1] += up0[i];
+      const long long U = up0[n_nodes];
       auto find_blk = [&](unsigned row, unsigned col) -> unsigned {
         const unsigned* lo = nbr.data() + nbr_ptr[row];
         const unsigned* hi = nbr.data() + nbr_ptr[row + 1];
         return (unsigned)(std::lower_bound(lo, hi, col) - nbr.data());
       };
       const size_t n_contrib = (size_t)ne * NPB;
-      std::vector<unsigned> dest(n_contrib), cptr(U + 1, 0), cpos(n_contrib);
-#pragma omp parallel for schedule(static)
-      for (long long sl = 0; sl < ne; sl++)
-        for (int idx = 0; idx < NPB; idx++) {
-          const int o = idx / N, q = idx % N;
-          const unsigned na = (unsigned)nodes0[(size_t)sl * N + (q + o) % N], nb = (unsigned)nodes0[(size_t)sl * N + q];
-          const unsigned row = std::min(na, nb), col = std::max(na, nb);
-          dest[(size_t)sl * NPB + idx] = (up_index[find_blk(row, col)] << 1) | (na > nb ? 1u : 0u);
-        }
-      for (size_t k = 0; k < n_contrib; k++) cptr[(dest[k] >> 1) + 1]++;
-      for (long long u = 0; u < U; u++) cptr[u + 1] += cptr[u];
-      {
-        std::vector<unsigned> cur(cptr.begin(), cptr.end() - 1);
-        for (long long o = 0; o < ne; o++) {  // `elems` order inside every pair
-          const size_t sl = order[o];
-          for (int idx = 0; idx < NPB; idx++) {
-            const unsigned d = dest[sl * NPB + idx];
-            cpos[sl * NPB + idx] = (cur[d >> 1]++ << 1) | (d & 1u);
+      std::vector<unsigned> cptr(U + 1, 0), cpos(n_contrib);
+      // Every contribution (slot, stored block idx) belongs to exactly one pair {i <= p}; seen from the smaller node i it
+      // is found by scanning adj[i], which lists the elements in summation (`elems`) order.  Two passes over the row
+      // nodes, both parallel and free of atomics: (1) contributions per pair, (2) positions.  Inside one element (only
+      // an element that names a node twice can contribute to a pair more than once) the order is that of idx.
+      struct Item {
+        unsigned idx, p, flag;
+      };
+      auto scan_row = [&](long long i, std::vector<Item>& items, auto&& emit) {
+        for (unsigned s = adj_ptr[i]; s < adj_ptr[i + 1];) {
+          const unsigned slot = adj[s] / N;
+          items.clear();
+          unsigned s1 = s;
+          for (; s1 < adj_ptr[i + 1] && adj[s1] / N == slot; s1++) {
+            const int a = (int)(adj[s1] % N);
+            for (int b = 0; b < N; b++) {
+              const unsigned nb = (unsigned)nodes0[(size_t)slot * N + b];
+              if (nb < (unsigned)i || (nb == (unsigned)i && b < a)) continue;  // the smaller node's row / once per local pair
+              int idx, tr;
+              pair_slot(N, a, b, idx, tr);
+              // the stored block holds K(a', b'), (a', b') = (a, b) or, transposed, (b, a); flag = node(a') > node(b')
+              items.push_back({(unsigned)idx, pos_of(i, s1, b) - first_up[i], (tr && nb > (unsigned)i) ? 1u : 0u});
+            }
           }
+          if (s1 - s > 1) std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.idx < y.idx; });
+          for (const Item& it : items) emit(slot, it);
+          s = s1;
+        }
+      };
+#pragma omp parallel
+      {
+        std::vector<Item> items;
+#pragma omp for schedule(static)
+        for (long long i = 0; i < n_nodes; i++)
+          scan_row(i, items, [&](unsigned, const Item& it) { cptr[up0[i] + it.p + 1]++; });
+      }
+      for (long long u = 0; u < U; u++) cptr[u + 1] += cptr[u];
+#pragma omp parallel
+      {
+        std::vector<Item> items;
+        std::vector<unsigned> cur;
+#pragma omp for schedule(static)
+        for (long long i = 0; i < n_nodes; i++) {
+          cur.assign(up0[i + 1] - up0[i], 0);
+          scan_row(i, items, [&](unsigned slot, const Item& it) {
+            cpos[(size_t)slot * NPB + it.idx] = ((cptr[up0[i] + it.p] + cur[it.p]++) << 1) | it.flag;
+          });
         }
       }
+      stage("sorted: dest, cptr, cpos");
       std::vector<unsigned> out_up(U), out_lo(U), nn_pack(U);
       const unsigned dd = (unsigned)(dofs_per_node * dofs_per_node);
       bool ok = true;
@@ -797,7 +876,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
         for (unsigned b = nbr_ptr[i]; b < nbr_ptr[i + 1]; b++) {
           const unsigned pn = nbr[b];
           if (pn < (unsigned)i) continue;
-          const unsigned u = up_index[b];
+          const unsigned u = up0[i] + (b - nbr_ptr[i]) - first_up[i];
           const unsigned nni = nbr_ptr[i + 1] - nbr_ptr[i], nnp = nbr_ptr[pn + 1] - nbr_ptr[pn];
           if (nni > 0xffffu || nnp > 0xffffu) ok = false;
           out_up[u] = nbr_ptr[i] * dd + (b - nbr_ptr[i]) * (unsigned)dofs_per_node;
@@ -805,6 +884,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
           out_lo[u] = nbr_ptr[pn] * dd + (b2 - nbr_ptr[pn]) * (unsigned)dofs_per_node;
           nn_pack[u] = nni | (nnp << 16);
         }
+      stage("sorted: pair tables");
       if (ok) {
         int rc2 = dev_upload(p, &p->cpos, cpos.data(), cpos.size());
         if (!rc2) rc2 = dev_upload(p, &p->cptr, cptr.data(), cptr.size());
@@ -818,11 +898,12 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
         }
         p->n_pairs = U;
         p->sorted_built = true;
-        p->n_own_sorted = B0.n_elems;
+        p->n_own_sorted = n_own;
       }
     }
   }
 #undef TRY
+  stage("sorted: uploads");
   *plan_out = p;
   return AD4SM_OK;
 }
@@ -971,7 +1052,7 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
   // the two-stage API promises element-major staging between the stages; a caller that declared which slot ranges
   // it reads (export ranges / peer links) gets the sorted path, with K1 materialising exactly those ranges
   const bool kmode_ok = want_K && (mode == MODE_ELASTIC || mode == MODE_PF_U);
-  const bool sorted_ok = kmode_ok && p->sorted_built && p->sorted_on && (internal || p->dist_aware);
+  const bool sorted_ok = kmode_ok && p->sorted_built && p->sorted_on && (internal || (p->dist_aware && p->n_own_batches == 1));
 
   const bool sorted = sorted_ok;
   if (p->push_mode && !internal && !sorted)
@@ -1184,7 +1265,8 @@ int ad4sm_peer_attach(ad4sm_plan* p, int32_t n_links, const ad4sm_peer_link* lin
   p->n_push = 0;
   p->push_mode = false;
   if (p->push_opt) {  // copy-engine pushes of locally materialised ranges (header: AD4SM_OPT_PEER_PUSH)
-    if (!p->sorted_built) return fail(AD4SM_ESTATE, "AD4SM_OPT_PEER_PUSH needs a plan with destination-sorted staging");
+    if (!p->sorted_built || p->n_own_batches != 1)
+      return fail(AD4SM_ESTATE, "AD4SM_OPT_PEER_PUSH needs a plan with destination-sorted staging and a single evaluated batch");
     if (!p->ev_exports) {
       CK(cudaEventCreateWithFlags(&p->ev_exports, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&p->ev_pushed, cudaEventDisableTiming));
@@ -1747,7 +1829,7 @@ int ad4sm_dist_attach(ad4sm_plan* p, ad4sm_dist* comm, int32_t n_peers, const ad
   int rc = 0;
   if (!p->allphi) rc = dev_alloc(p, &p->allphi, (size_t)nranks);
   if (!rc && !p->phi_local) rc = dev_alloc(p, &p->phi_local, 1);
-  if (!rc && p->sorted_built && n_export > 0) {
+  if (!rc && p->sorted_built && p->n_own_batches == 1 && n_export > 0) {
     rc = dev_upload(p, &p->xmap, xmap.data(), xmap.size());
     if (!rc) rc = dev_alloc(p, &p->xke, (size_t)(n_export * kw));
     if (!rc) rc = dev_alloc(p, &p->xre, (size_t)(n_export * rw));

@@ -331,6 +331,31 @@ def test_sorted_staging_matches_element_major_staging(make):
     assert abs(Kd - Kd.T).max() == 0.0
 
 
+def test_sorted_staging_with_several_batches():
+    """Two materials and two integration rules interleaved in `elems` (three batches keyed by orig_index): the plan still
+    gets the destination-sorted staging, its result is bitwise that of the element-major path and matches the oracle
+    evaluated element by element in `elems` order."""
+    from ad4sm_b200 import mesh
+    coords, conn = mesh.hex_block(6, 5, 4, jitter=0.1, seed=41)
+    m1, m2 = K.nh(), Ma.MooneyRivlin(800.0, 200.0, 5000.0)
+
+    def make(e):
+        if e % 5 == 0:
+            return El.Hex08R(conn[e], coords[conn[e] - 1], mat=m1)   # one Gauss point: other P, other K1 kernel... same N
+        return El.Hex08(conn[e], coords[conn[e] - 1], mat=(m1 if e % 3 else m2))
+    elems = [make(e) for e in range(len(conn))]
+    u = mesh.random_u(len(coords), 3, 1 / 6, seed=42)
+    plan = El.Plan(elems, len(coords), 3)
+    assert len(plan.batches) == 3 and plan.info(capi.INFO_SORTED) == 2
+    s = plan.makeϕrKt(u)
+    plan.set_option(capi.OPT_SORTED, 0)
+    e = plan.makeϕrKt(u)
+    assert s[0] == e[0] and np.array_equal(s[1], e[1]) and np.array_equal(s[2].nzval, e[2].nzval)
+    assert np.array_equal(s[2].colptr, e[2].colptr) and np.array_equal(s[2].rowval, e[2].rowval)
+    ob = [El.ElemBatch("CE", 3, x.nodes[None], x.gradN[None], x.wgt[None], x.mat) for x in elems]
+    K.assert_parity(s, K.oracle_eval(ob, u))
+
+
 def test_pipelined_upload_matches_single_copy(monkeypatch):
     """Host API on a mesh large enough for the pipelined upload (u in node chunks, K1 in element slices): same bits as
     one copy + one launch, for the elastic path and for the phase-field d-phase with history."""
