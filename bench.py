@@ -46,7 +46,7 @@ CONFIGS = {
                k1="k1_u_kernel<3,8,8,NEO>", asm="k3_kernel + k2s_tma_kernel3"),
     "C3": dict(name="3-D Tet4 MooneyRivlin Kuhn lattice 70x70x68", shape="tet4", n=(70, 70, 68), flop=2032.0,
                b_elem=16 + 96 + 8 + 4.2, b_asm=183.7 + 4.2, sample=(33, 33, 32),
-               k1="k1_u_kernel_t1<3,4,MOONEY>", asm="k3_kernel + k2_kernel<3>"),
+               k1="k1_u_kernel_w1<3,4,MOONEY> (thread per element, warp-cooperative sorted stores)", asm="k3_kernel + k2s_tma_kernel3"),
     "C4": dict(name="2-D QuadP PhaseField(NeoHooke) 500x500, staggered u/d assembly with history", shape="quadp",
                n=(500, 500), flop=4 * (32 + 32 + 288 + 400 + 60) + 800.0,
                b_elem=2 * (16 + 256 + 32 + 128 + 16.2 + 8) + 256, b_asm=(288.4 + 16.1) + (72.1 + 8.0), sample=(200, 200),
