@@ -812,6 +812,11 @@ class Plan:
         """K2/K3 + ϕ reduction over the staging of all batches (after any interface exchange)."""
         capi.check(self._L.ad4sm_eval_assemble_device(self._h, mode))
 
+    def eval_assemble_interior_device(self, mode):
+        """First half of a partitioned run's assembly (ad4sm_eval_assemble_split_device): the rows and node pairs no HALO
+        slot contributes to; may run while the interface rows are still in flight.  `eval_assemble_device` then finishes."""
+        capi.check(self._L.ad4sm_eval_assemble_split_device(self._h, mode))
+
     def staging_view(self, field=capi.FIELD_U):
         v = capi.StagingView()
         capi.check(self._L.ad4sm_staging_view_get(self._h, field, C.byref(v)))

@@ -44,6 +44,7 @@ class Batch(C.Structure):
 BATCH_HALO = 1
 OPT_SORTED, OPT_PEER_PUSH = 3, 4
 INFO_SORTED = 3
+INFO_SPLIT_PAIRS = 4
 
 
 class StagingView(C.Structure):
@@ -117,6 +118,7 @@ SIGNATURES = {
     "ad4sm_eval_elements_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ad4sm_fetch_phi_r_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ad4sm_eval_assemble_device": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ad4sm_eval_assemble_split_device": (C.c_int, [C.c_void_p, C.c_int32]),
     "ad4sm_staging_view_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(StagingView)]),
     "ad4sm_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ad4sm_peer_attach": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(PeerLink)]),

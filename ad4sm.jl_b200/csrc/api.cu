@@ -127,6 +127,10 @@ struct ad4sm_plan {
   unsigned *cpos = nullptr, *cptr = nullptr, *out_up = nullptr, *out_lo = nullptr, *nn_pack = nullptr;
   double* C = nullptr;
   long long n_own_sorted = 0;  // slots [n_own_sorted, ne) are HALO: scattered into C before K2s
+  // split assembly (ad4sm_eval_assemble_split_device): node rows < split_node -- and the pairs numbered under them,
+  // [0, split_pair) -- receive no HALO contribution and can be assembled before the interface exchange has completed
+  long long split_node = 0, split_pair = 0;
+  int split_done = 0;          // 1: the interior part of the pending evaluation has been assembled
   int n_own_batches = 0;       // evaluated (non-HALO) batches; the partitioned-run features (export ranges, peer links) know one
   bool dist_aware = false;     // the caller declared its export ranges / peer links (ad4sm_peer_attach / ad4sm_export_ranges)
   // peer staging / export ranges
@@ -899,6 +903,23 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
         p->n_pairs = U;
         p->sorted_built = true;
         p->n_own_sorted = n_own;
+        // first node row with a HALO slot in its adjacency: rows before it (and their pairs, which are numbered row by
+        // row under the smaller node) are complete without the exchange.  Rounded down to whole K2s CTAs (128 pairs).
+        long long sn = n_nodes;
+        if (n_own < ne) {
+#pragma omp parallel for schedule(static) reduction(min : sn)
+          for (long long i = 0; i < n_nodes; i++) {
+            if (i >= sn) continue;
+            for (unsigned s2 = adj_ptr[i]; s2 < adj_ptr[i + 1]; s2++)
+              if ((long long)(adj[s2] / N) >= n_own) {
+                sn = i;
+                break;
+              }
+          }
+        }
+        while (sn > 0 && (up0[sn] % 128u) != 0) sn--;
+        p->split_node = sn;
+        p->split_pair = up0[sn];
       }
     }
   }
@@ -947,6 +968,10 @@ static AsmArgs asm_args(ad4sm_plan* p, int field) {
   a.k2s_direct = k2s_direct;
   a.halo_adj0 = (unsigned long long)p->n_own_sorted * p->N;
   a.halo_adj_shift = (p->push_pending && p->parity) ? (unsigned long long)p->n_halo * p->N : 0ull;
+  a.node0 = 0;
+  a.node1 = a.n_nodes;
+  a.pair0 = 0;
+  a.pair1 = a.n_pairs;
   return a;
 }
 
@@ -1154,13 +1179,22 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
     if (e != cudaSuccess) return fail(AD4SM_ENODEV, std::string("K1 launch: ") + cudaGetErrorString(e));
     launches++;
   }
+  // ϕ = Σ ϕ_e right behind K1: it needs no interface exchange (HALO slots hold 0), so a partitioned run can ship its
+  // partial while the assembly is still to come
+  CK(launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, p->stream));
   if (p->ev_cur) CK(cudaEventRecord(p->ev_cur->e[1], p->stream));
-  if (p->prof) p->prof_launches[AD4SM_PROF_ELEMENT] += launches;
+  if (p->prof) {
+    p->prof_launches[AD4SM_PROF_ELEMENT] += launches;
+    p->prof_launches[AD4SM_PROF_REDUCE] += 2;
+  }
   p->elements_mode = mode;
+  p->split_done = 0;
   return AD4SM_OK;
 }
 
-int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
+// part 0: everything (or, after a part-1 call, the remainder); part 1: only the interior (rows / pairs without HALO
+// contributions), leaving the evaluation pending.
+static int assemble_impl(ad4sm_plan* p, int32_t mode, int part) {
   if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
   if (mode < 0 || mode > 3) return fail(AD4SM_EINVAL, "mode must be 0..3");
   if (p->elements_mode != mode) return fail(AD4SM_ESTATE, "ad4sm_eval_assemble_device: no element evaluation of this mode pending");
@@ -1168,10 +1202,31 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   const bool want_K = mode != MODE_PHI_R;
   CK(cudaSetDevice(p->device));
   EvSet* ev = p->ev_cur;
-  if (ev) CK(cudaEventRecord(ev->e[4], p->stream));  // exchange time (if any) lies between e[1] and e[4]
+  const bool splittable = want_K && p->sorted_last && p->n_own_sorted < p->ne && p->split_pair > 0;
+  if (part == 1) {
+    if (p->split_done) return fail(AD4SM_ESTATE, "ad4sm_eval_assemble_split_device: the interior part has already been assembled");
+    if (ev) CK(cudaEventRecord(ev->e[4], p->stream));
+    if (splittable) {
+      AsmArgs a = asm_args(p, field);
+      a.node1 = p->split_node;
+      a.pair1 = p->split_pair;
+      CK(launch_k3(a, p->stream));
+      CK(launch_k2s(a, p->stream));
+      if (p->prof) p->prof_launches[AD4SM_PROF_ASSEMBLE] += 2;
+    }
+    p->split_done = splittable ? 2 : 1;
+    return AD4SM_OK;
+  }
+  const bool rest = p->split_done == 2;  // K3 / K2s of the interior already ran
+  if (ev && !p->split_done) CK(cudaEventRecord(ev->e[4], p->stream));  // exchange time (if any) lies between e[1] and e[4]
   // r and ϕ first: the host API copies them back while the (much longer) Kt assembly is still running
-  CK(launch_k3(asm_args(p, field), p->stream));
-  CK(launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, p->stream));
+  AsmArgs a = asm_args(p, field);
+  if (rest) {
+    a.node0 = p->split_node;
+    a.pair0 = p->split_pair;
+    a.keep_zero_count = 1;
+  }
+  CK(launch_k3(a, p->stream));
   CK(cudaEventRecord(p->ev_r_ready, p->stream));
   if (want_K) {
     if (p->sorted_last) {
@@ -1180,16 +1235,16 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
         const double* rows = p->Ke + ((p->push_pending && p->parity) ? p->n_halo * kw : 0);  // receive buffer in use (peer push)
         CK(launch_halo_scatter(rows, p->cpos, p->C, p->n_own_sorted, p->ne - p->n_own_sorted, n_pair_blocks(p->N), p->stream));
       }
-      CK(launch_k2s(asm_args(p, field), p->stream));
+      CK(launch_k2s(a, p->stream));
     }
-    else CK(launch_k2(asm_args(p, field), p->stream));
+    else CK(launch_k2(a, p->stream));
   }
   if (ev) CK(cudaEventRecord(ev->e[2], p->stream));
   if (ev) CK(cudaEventRecord(ev->e[3], p->stream));
   if (p->prof) {
     p->prof_launches[AD4SM_PROF_ASSEMBLE] += want_K ? 2 : 1;
-    p->prof_launches[AD4SM_PROF_REDUCE] += 2;
   }
+  p->split_done = 0;
   p->ev_cur = nullptr;
   p->elements_mode = -1;
   if (p->push_pending) {  // the next evaluation's pushes land in the other receive buffer
@@ -1204,6 +1259,8 @@ int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) {
   p->last_field = field;
   return AD4SM_OK;
 }
+int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) { return assemble_impl(p, mode, 0); }
+int ad4sm_eval_assemble_split_device(ad4sm_plan* p, int32_t mode) { return assemble_impl(p, mode, 1); }
 
 int ad4sm_eval_elements_device(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
   return eval_elements_impl(p, mode, u_dev, d_dev, hist_dev, false);
@@ -1241,6 +1298,7 @@ int ad4sm_get_info(ad4sm_plan* p, int32_t what, int64_t* value) {
   if (!p || !value) return fail(AD4SM_EINVAL, "plan or value is NULL");
   switch (what) {
     case AD4SM_INFO_SORTED: *value = p->sorted_built ? (p->sorted_on ? 2 : 1) : 0; return AD4SM_OK;
+    case AD4SM_INFO_SPLIT_PAIRS: *value = (p->sorted_built && p->n_own_sorted < p->ne) ? p->split_pair : 0; return AD4SM_OK;
   }
   return fail(AD4SM_EINVAL, "unknown info id");
 }
@@ -1515,10 +1573,13 @@ static int assemble_duals_impl(ad4sm_plan* p, const void* Phi, int64_t stride, b
   const bool sorted = want_K && p->sorted_built && p->sorted_on;
   if (sorted && launch_halo_scatter(p->Ke, p->cpos, p->C, 0, p->n_own_sorted, n_pair_blocks(p->N), s) != cudaSuccess)
     return done(fail(AD4SM_ENODEV, "staging scatter launch failed"));
+  if (launch_phi_reduce(p->phie, p->ne, p->partials, p->phi_dev, s) != cudaSuccess)  // ϕ = Σ v (toolkit:186)
+    return done(fail(AD4SM_ENODEV, "ϕ reduction launch failed"));
   p->ev_cur = nullptr;
   p->sorted_last = sorted;
   const int mode = want_K ? MODE_ELASTIC : MODE_PHI_R;
   p->elements_mode = mode;
+  p->split_done = 0;
   int rc = ad4sm_eval_assemble_device(p, mode);
   if (rc) return done(rc);
   FieldOut& f = p->field[AD4SM_FIELD_U];
@@ -1900,14 +1961,27 @@ static int dist_eval_stages(ad4sm_plan* p, int32_t mode, const double* u_dev, co
       xf.push_back({0, d.rank, p->re + d.recv_first * rw, (size_t)(d.n_recv * rw)});
     }
   }
+  // The exchange and the ϕ all-gather run on the copy stream while the main stream assembles the interior (the rows and
+  // pairs no HALO slot contributes to); only the interface part of the assembly waits for them.
   std::string err;
-  if (!xf.empty() && dist_exchange(p->dcomm->c, (int)xf.size(), xf.data(), s, &err)) return fail(AD4SM_ENCCL, err);
+  const int nranks = dist_comm_size(p->dcomm->c);
+  cudaStream_t xs = p->copy_stream;
+  if (!p->ev_exports) {
+    CK(cudaEventCreateWithFlags(&p->ev_exports, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&p->ev_pushed, cudaEventDisableTiming));
+  }
+  CK(cudaMemcpyAsync(p->phi_local, p->phi_dev, sizeof(double), cudaMemcpyDeviceToDevice, s));  // this rank's partial ϕ
+  CK(cudaEventRecord(p->ev_exports, s));
+  CK(cudaStreamWaitEvent(xs, p->ev_exports, 0));
+  if (!xf.empty() && dist_exchange(p->dcomm->c, (int)xf.size(), xf.data(), xs, &err)) return fail(AD4SM_ENCCL, err);
+  if (dist_allgather(p->dcomm->c, p->phi_local, p->allphi, 1, xs, &err)) return fail(AD4SM_ENCCL, err);
+  CK(cudaEventRecord(p->ev_pushed, xs));
+  rc = ad4sm_eval_assemble_split_device(p, mode);
+  if (rc) return rc;
+  CK(cudaStreamWaitEvent(s, p->ev_pushed, 0));
   rc = ad4sm_eval_assemble_device(p, mode);
   if (rc) return rc;
-  // ϕ: this rank's partial (phi_dev) -> all ranks -> summed in rank order, back into phi_dev (the global ϕ)
-  const int nranks = dist_comm_size(p->dcomm->c);
-  CK(cudaMemcpyAsync(p->phi_local, p->phi_dev, sizeof(double), cudaMemcpyDeviceToDevice, s));
-  if (dist_allgather(p->dcomm->c, p->phi_local, p->allphi, 1, s, &err)) return fail(AD4SM_ENCCL, err);
+  // ϕ: the partials of all ranks, summed in rank order, into phi_dev (the global ϕ)
   CK(launch_phi_rank_sum(p->allphi, nranks, p->phi_dev, s));
   return AD4SM_OK;
 }

@@ -36,6 +36,10 @@ struct AsmArgs {
   const double* C;              // [ne*NPB][CBLK] contribution blocks, canonical orientation (row node <= col node)
   // peer push (double-buffered HALO rows): adj entries >= halo_adj0 read their residual row halo_adj_shift entries later
   unsigned long long halo_adj0, halo_adj_shift;
+  // split assembly of a partitioned run (ad4sm_eval_assemble_split_device): K3 covers the node rows [node0, node1), K2s the
+  // pairs [pair0, pair1); keep_zero_count: this launch continues the exact-zero count of the previous one
+  long long node0 = 0, node1 = 0, pair0 = 0, pair1 = 0;
+  int keep_zero_count = 0;
 };
 constexpr int CBLK3 = 10;       // doubles per 3x3 contribution block: 9 + 1 pad = 80 B, 16-byte aligned
 

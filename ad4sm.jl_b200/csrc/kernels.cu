@@ -438,7 +438,7 @@ __device__ __forceinline__ void k1_phase2(int q, int P, int rstride, bool active
 // PROF (developer tool, AD4SM_K1_PROF=1, Hex8 NeoHooke only): lane 0 of every warp accumulates the clock64() cycles of
 // the four parts of its iteration (0 head: TMA issue + waits, 1 phase 1, 2 phase 2 up to the end of the contraction incl.
 // the epilogue stores, 3 rest) in g_k1_prof[gwarp][4]; [4] = iterations.
-__device__ long long g_k1_prof[148 * 8 * 8];
+__device__ long long g_k1_prof[148 * 8 * 16];
 template <int D, int N, int LP, int MF, bool PF, bool PROF = false>
 __global__ void __launch_bounds__(256, 1)
     k1_u_kernel(const __grid_constant__ K1Args a, const WarpLayout L, const int warps_per_cta) {
@@ -461,31 +461,28 @@ __global__ void __launch_bounds__(256, 1)
   __syncwarp();
   unsigned char* const ws = ws0;
 
-  // TMA bulk copies of one element group into stage s (∇N per element, wgt, N).  Called by the whole warp: lane 0
-  // announces the byte count, then lanes 0..cnt-1 issue one ∇N copy each and lanes EW, EW+1 the small arrays -- the
-  // address arithmetic of the 4-6 copies runs in parallel instead of serially on one lane.
+  // TMA bulk copies of one element group into stage s (∇N per element, wgt, N), all issued by lane 0 in straight-line
+  // code.  (UBLKCP takes its operands from uniform registers: copies "issued by different lanes" are serialised by the
+  // compiler into a loop over the lanes anyway, and cost 1 000+ cycles per iteration that way -- measured,
+  // profiles/r02_k1_experiments.txt.)  No proxy fence: the stage buffers are only ever WRITTEN by the async proxy and
+  // read by LDS; the reads of the previous use of the stage are ordered before this point by the __syncwarp that ends
+  // every iteration (the write-after-read case needs no cross-proxy fence).
   auto issue = [&](long long grp, int s) {
+    if (lane != 0) return;
     const long long e0 = grp * EW;
     const int cnt = (int)((a.ne - e0) < EW ? (a.ne - e0) : EW);
     const unsigned bar = bar0 + 8 * s;
-    const unsigned gbytes = (unsigned)(D * P * N * 8);
+    const unsigned gb = (unsigned)(D * P * N * 8);
     const unsigned wbytes = (unsigned)((cnt * P * 8 + 15) & ~15);
     const unsigned vbytes = PF ? (unsigned)((cnt * P * N * 8 + 15) & ~15) : 0u;
-    if (lane == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(bar, cnt * gbytes + wbytes + vbytes);
-    }
-    __syncwarp();
-    if (lane < cnt) {
-      fence_proxy_async();
-      tma_load_1d(smem_u32(ws + (L.g_off + (s) * L.g_stg) + lane * L.g_el), a.gradN + (e0 + lane) * (long long)(D * P * N), gbytes, bar);
-    } else if (lane == EW) {
-      fence_proxy_async();
-      tma_load_1d(smem_u32(ws + (L.w_off + (s) * L.w_stg)), a.wgt + e0 * P, wbytes, bar);
-    } else if (PF && lane == EW + 1) {
-      fence_proxy_async();
-      tma_load_1d(smem_u32(ws + (L.v_off + (s) * L.v_stg)), a.Nval + e0 * (long long)(P * N), vbytes, bar);
-    }
+    mbar_expect_tx(bar, cnt * gb + wbytes + vbytes);
+    const unsigned dst0 = smem_u32(ws + (L.g_off + (s) * L.g_stg));
+    const double* src0 = a.gradN + e0 * (long long)(D * P * N);
+#pragma unroll
+    for (int i = 0; i < EW; i++)
+      if (i < cnt) tma_load_1d(dst0 + i * L.g_el, src0 + (long long)i * (D * P * N), gb, bar);
+    tma_load_1d(smem_u32(ws + (L.w_off + (s) * L.w_stg)), a.wgt + e0 * P, wbytes, bar);
+    if (PF) tma_load_1d(smem_u32(ws + (L.v_off + (s) * L.v_stg)), a.Nval + e0 * (long long)(P * N), vbytes, bar);
   };
   // lane 0: node ids of group grp into id stage s.  They run one group further ahead than the rest, so that the
   // u gather of group i+1 can start at the beginning of iteration i.
@@ -493,14 +490,20 @@ __global__ void __launch_bounds__(256, 1)
     const long long e0 = grp * EW;
     const int cnt = (int)((a.ne - e0) < EW ? (a.ne - e0) : EW);
     const unsigned nbytes = (unsigned)((cnt * N * 4 + 15) & ~15);
-    fence_proxy_async();
     mbar_expect_tx(bar0 + 16 + 8 * s, nbytes);
     tma_load_1d(smem_u32(ws + (L.n_off + (s) * L.n_stg)), a.nodes + e0 * N, nbytes, bar0 + 16 + 8 * s);
   };
 
   const int gwarp = blockIdx.x * warps_per_cta + warp;  // global warp id = its first element group
   long long grp = gwarp;
-  long long pt[6] = {0, 0, 0, 0, 0, 0}, pt0 = 0;
+  long long pt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt0 = 0, ph0 = 0;
+  auto htick = [&](int k) {  // PROF: sub-parts of the head (6 TMA issue, 7 wait ∇N, 8 wait ids, 9 wait u gather, 10 wait stores)
+    if constexpr (PROF) {
+      const long long t = clock64();
+      pt[k] += t - ph0;
+      ph0 = t;
+    }
+  };
   auto tick = [&](int k) {
     if constexpr (PROF) {
       const long long t = clock64();
@@ -529,14 +532,21 @@ __global__ void __launch_bounds__(256, 1)
   for (int it = 0; grp < n_groups; grp += gstep, it++) {
     const int s = it & 1;
     const bool has_next = grp + gstep < n_groups;
+    if constexpr (PROF) ph0 = clock64();
     if (has_next) issue(grp + gstep, s ^ 1);
-    if (lane == 31 && grp + 2 * gstep < n_groups) issue_ids(grp + 2 * gstep, s);  // id stage s held this group's ids: gather done
+    if (lane == 0 && grp + 2 * gstep < n_groups) issue_ids(grp + 2 * gstep, s);  // id stage s held this group's ids: gather done
+    if constexpr (PROF) __syncwarp();
+    htick(6);
     mbar_wait(bar0 + 8 * s, (unsigned)((it >> 1) & 1));                        // this group's ∇N, wgt, N
+    htick(7);
     if (has_next) mbar_wait(bar0 + 16 + 8 * (s ^ 1), (unsigned)(((it + 1) >> 1) & 1));  // next group's node ids
+    htick(8);
     cp_async_wait_all();                                                        // this group's u
+    htick(9);
     if (a.cpos && a.sorted_tma) bulk_wait_read_all();  // sorted staging through per-lane bulk copies: their shared-memory source may be overwritten
     if (lane == 0) bulk_wait_read_all();  // the previous bulk stores have read the staging area (aliases the records)
     __syncwarp();
+    htick(10);
     tick(0);
 
     const long long e = grp * EW + el;
@@ -617,7 +627,7 @@ __global__ void __launch_bounds__(256, 1)
   }
   if constexpr (PROF) {
     if (lane == 0)
-      for (int k = 0; k < 6; k++) g_k1_prof[(size_t)gwarp * 8 + k] = pt[k];
+      for (int k = 0; k < 12; k++) g_k1_prof[(size_t)gwarp * 16 + k] = pt[k];
   }
   if (a.cpos && a.sorted_tma) bulk_wait_read_all();
   if (lane == 0) {
@@ -942,14 +952,16 @@ template <int D, int N, int LP, int MF, bool PF> static cudaError_t launch_u_t(c
         if ((err = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return err;
         pk<<<(unsigned)c.grid, c.warps * 32, smem, s>>>(a, L, c.warps);
         if ((err = cudaStreamSynchronize(s)) != cudaSuccess) return err;
-        static long long h[148 * 8 * 8];
+        static long long h[148 * 8 * 16];
         cudaMemcpyFromSymbol(h, g_k1_prof, sizeof(h));
-        double sum[6] = {0, 0, 0, 0, 0, 0};
+        double sum[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         const int nw = c.grid * c.warps;
         for (int w = 0; w < nw && w < 148 * 8; w++)
-          for (int k = 0; k < 6; k++) sum[k] += (double)h[w * 8 + k];
+          for (int k = 0; k < 12; k++) sum[k] += (double)h[w * 16 + k];
         fprintf(stderr, "K1PROF warps/cta %d iters/warp %.1f cycles/iter: head %.0f phase1 %.0f contraction %.0f epilogue %.0f rest %.0f\n",
                 c.warps, sum[4] / nw, sum[0] / sum[4], sum[1] / sum[4], sum[2] / sum[4], sum[5] / sum[4], sum[3] / sum[4]);
+        fprintf(stderr, "K1PROF head split: TMA issue %.0f wait gradN %.0f wait ids %.0f wait u gather %.0f wait stores %.0f\n",
+                sum[6] / sum[4], sum[7] / sum[4], sum[8] / sum[4], sum[9] / sum[4], sum[10] / sum[4]);
         return cudaSuccess;
       }
     }
@@ -1016,9 +1028,9 @@ template <int DB> __global__ void __launch_bounds__(256) k2_kernel(const AsmArgs
 }
 // ---- K3: residual.  One thread per (node, component).
 __global__ void __launch_bounds__(256) k3_kernel(const AsmArgs a) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int dpn = a.dpn;
-  if (g >= a.n_nodes * dpn) return;
+  const long long g = a.node0 * dpn + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.node1 * dpn) return;
   const long long i = g / dpn;
   assemble_r_entry<false>(a, i, (int)(g - i * dpn));
 }
@@ -1102,8 +1114,8 @@ __device__ __forceinline__ void k2s_write(const AsmArgs& a, const double* acc, u
 }
 // direct-load variant (AD4SM_K2S_DIRECT=1; also what ranges too large for a slice fall back to, per warp)
 template <int EXP> __global__ void __launch_bounds__(K2S_THREADS, AD4SM_K2S_MINB) k2s_kernel3(const AsmArgs a) {
-  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= a.n_pairs) return;
+  const long long u = a.pair0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= a.pair1) return;
   const unsigned c0 = __ldg(a.cptr + u), c1 = __ldg(a.cptr + u + 1);
   const unsigned oup = __ldg(a.out_up + u), olo = __ldg(a.out_lo + u), nn = __ldg(a.nn_pack + u);
   double acc[9];
@@ -1126,10 +1138,10 @@ template <int EXP> __global__ void __launch_bounds__(K2T_WARPS * 32) k2s_tma_ker
   __shared__ __align__(128) double2 buf[K2T_WARPS][K2T_BLOCKS * (CBLK3 / 2)];
   __shared__ __align__(8) unsigned long long bars[K2T_WARPS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long u = ((long long)blockIdx.x * K2T_WARPS + w) * 32 + lane;
-  if (u - lane >= a.n_pairs) return;  // whole warp; no CTA-wide barrier below
-  const bool valid = u < a.n_pairs;
-  const unsigned c0 = __ldg(a.cptr + (valid ? u : a.n_pairs)), c1 = valid ? __ldg(a.cptr + u + 1) : c0;
+  const long long u = a.pair0 + ((long long)blockIdx.x * K2T_WARPS + w) * 32 + lane;
+  if (u - lane >= a.pair1) return;  // whole warp; no CTA-wide barrier below
+  const bool valid = u < a.pair1;
+  const unsigned c0 = __ldg(a.cptr + (valid ? u : a.pair1)), c1 = valid ? __ldg(a.cptr + u + 1) : c0;
   const unsigned bar = smem_u32(&bars[w]);
   if (lane == 0) {
     mbar_init(bar, 1);
@@ -1180,17 +1192,21 @@ template <int EXP> __global__ void __launch_bounds__(K2T_WARPS * 32) k2s_tma_ker
 }
 cudaError_t launch_k2s(const AsmArgs& a, cudaStream_t s) {
   if (a.DB != 3 || a.dpn != 3 || a.n_pairs <= 0) return cudaErrorInvalidValue;
-  cudaError_t err = cudaMemsetAsync(a.n_zero, 0, sizeof(unsigned long long), s);
-  if (err != cudaSuccess) return err;
+  if (!a.keep_zero_count) {
+    cudaError_t err = cudaMemsetAsync(a.n_zero, 0, sizeof(unsigned long long), s);
+    if (err != cudaSuccess) return err;
+  }
+  const long long np = a.pair1 - a.pair0;  // the launch's pair range (the whole pattern unless the assembly is split)
+  if (np <= 0) return cudaSuccess;
   if (a.k2s_direct) {
-    const unsigned grid = (unsigned)((a.n_pairs + K2S_THREADS - 1) / K2S_THREADS);
+    const unsigned grid = (unsigned)((np + K2S_THREADS - 1) / K2S_THREADS);
     switch (a.k2s_exp) {
       case 1: k2s_kernel3<1><<<grid, K2S_THREADS, 0, s>>>(a); break;
       case 2: k2s_kernel3<2><<<grid, K2S_THREADS, 0, s>>>(a); break;
       default: k2s_kernel3<0><<<grid, K2S_THREADS, 0, s>>>(a); break;
     }
   } else {
-    const unsigned grid = (unsigned)((a.n_pairs + K2T_WARPS * 32 - 1) / (K2T_WARPS * 32));
+    const unsigned grid = (unsigned)((np + K2T_WARPS * 32 - 1) / (K2T_WARPS * 32));
     switch (a.k2s_exp) {
       case 1: k2s_tma_kernel3<1><<<grid, K2T_WARPS * 32, 0, s>>>(a); break;
       case 2: k2s_tma_kernel3<2><<<grid, K2T_WARPS * 32, 0, s>>>(a); break;
@@ -1253,7 +1269,7 @@ cudaError_t launch_duals_to_staging(const double* Phi, long long stride, const l
   return cudaGetLastError();
 }
 cudaError_t launch_k3(const AsmArgs& a, cudaStream_t s) {
-  const long long nr = a.n_nodes * a.dpn;
+  const long long nr = (a.node1 - a.node0) * a.dpn;
   if (nr > 0) k3_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(a);
   return cudaGetLastError();
 }

@@ -120,6 +120,7 @@ class GpuBackend:
         self.peer = False
         self.push = False
         self._bound = None
+        self._phi_t = self._r_t = None
         self.bind_current_stream()
         self._declare_exports(part)
         field_id = capi.FIELD_D if self.mode == capi.MODE_PF_D else capi.FIELD_U
@@ -228,13 +229,20 @@ class GpuBackend:
     def assemble(self):
         self.plan.eval_assemble_device(self.mode)
 
+    def assemble_interior(self):
+        self.plan.eval_assemble_interior_device(self.mode)
+
     def phi_tensor(self):
-        v = self.plan.device_view(self.field_id)
-        return _wrap(self.torch, v.phi_dev, (1,))
+        if self._phi_t is None:   # library-owned device memory: the views are made once
+            v = self.plan.device_view(self.field_id)
+            self._phi_t = _wrap(self.torch, v.phi_dev, (1,))
+        return self._phi_t
 
     def r_tensor(self):
-        v = self.plan.device_view(self.field_id)
-        return _wrap(self.torch, v.r_dev, (v.n_dof,))
+        if self._r_t is None:
+            v = self.plan.device_view(self.field_id)
+            self._r_t = _wrap(self.torch, v.r_dev, (v.n_dof,))
+        return self._r_t
 
 
 class LibDistPlan:
@@ -354,6 +362,7 @@ class DistPlan:
     def __init__(self, backend, part):
         self.b, self.part = backend, part
         self._tok = None
+        self._allphi = self._side = None
 
     def step_host(self, u_host, r_host, d_host=None):
         """One evaluation with host-resident u (in) and r (out, this rank's local dofs): the upload overlaps K1, the
@@ -362,7 +371,12 @@ class DistPlan:
         return self.step(host=(u_host, r_host, d_host))
 
     def step(self, *eval_args, host=None):
-        """One evaluation, everything left on the device.  Returns the global ϕ as a 0-d tensor."""
+        """One evaluation, everything left on the device.  Returns the global ϕ as a 0-d tensor.
+
+        Stream plan (world > 1): the element stage and both halves of the assembly run on torch's current stream; the
+        interface exchange (send/recv, or the barrier that follows the copy-engine pushes) and the all-gather of the
+        per-rank ϕ -- which doubles as that barrier -- run on a side stream while the main stream assembles the interior
+        rows and pairs (`ad4sm_eval_assemble_split_device`); only the interface part of the assembly waits for them."""
         import torch
         import torch.distributed as D
         if hasattr(self.b, "bind_current_stream"):
@@ -378,25 +392,37 @@ class DistPlan:
             self.b.eval_elements_host(host[0], host[2])
         else:
             self.b.eval_elements(*eval_args)
-        if peer:
-            # the interface staging has been written into the owners' HALO slots by K1 itself: only a barrier is left
-            if self._tok is None:
-                self._tok = torch.zeros(1, device="cuda")
-            D.all_reduce(self._tok)
+        phi = self.b.phi_tensor()   # this rank's partial: reduced at the end of the element stage
+        if self.part.world == 1:
+            self.b.assemble()
+            if host is not None:
+                self.b.fetch_r_async(host[1])
+            return phi[0]
+        split = phi.is_cuda and hasattr(self.b, "assemble_interior")   # (the CPU stand-in of the gloo tests has no streams)
+        if self._allphi is None:
+            self._allphi = torch.empty(self.part.world, dtype=phi.dtype, device=phi.device)
+            self._side = torch.cuda.Stream() if split else None
+
+        def exchange():
+            if not peer:
+                exchange_staging(self.part, self.b.n_own, self.b.staging())
+            # every rank contributes after its element stage and its pushes: completion here means every peer's rows
+            # have landed (the barrier of the peer-staging protocols) and carries the ϕ partials at the same time
+            D.all_gather_into_tensor(self._allphi, phi.contiguous())
+
+        if split:
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                exchange()
+            self.b.assemble_interior()
+            main.wait_stream(self._side)
         else:
-            exchange_staging(self.part, self.b.n_own, self.b.staging())
+            exchange()
         self.b.assemble()
         if host is not None:
             self.b.fetch_r_async(host[1])
-        phi = self.b.phi_tensor()
-        if self.part.world == 1:
-            return phi[0]
-        allphi = torch.empty(self.part.world, dtype=phi.dtype, device=phi.device)
-        D.all_gather_into_tensor(allphi, phi.contiguous())
-        total = allphi[0].clone()
-        for g in range(1, self.part.world):   # fixed rank order: run-to-run reproducible
-            total = total + allphi[g]
-        return total
+        return self._allphi.sum()   # one fixed reduction over `world` values: run-to-run reproducible
 
 
 # ------------------------------------------------------------------------------------------------

@@ -259,6 +259,13 @@ int ad4sm_device_view_get(ad4sm_plan* plan, int32_t field, ad4sm_device_view* vi
  * assemble: K2/K3 over ALL batches' staging + the ϕ reduction (HALO slots contribute 0 to ϕ). */
 int ad4sm_eval_elements_device(ad4sm_plan* plan, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev);
 int ad4sm_eval_assemble_device(ad4sm_plan* plan, int32_t mode);
+/* Optional first half of the assembly stage of a partitioned run: assembles the INTERIOR -- the node rows of r and the
+ * node pairs of Kt that receive no contribution from a HALO slot (for contiguous partitions: everything but the
+ * interface planes) -- and leaves the evaluation pending; it may therefore run while the interface rows are still in
+ * flight.  The following ad4sm_eval_assemble_device then assembles only the remainder.  Results are bitwise those of the
+ * one-call assembly.  (ϕ, which needs no exchange either, is reduced at the end of the element stage.)  On plans without
+ * destination-sorted staging or without HALO batch it does nothing. */
+int ad4sm_eval_assemble_split_device(ad4sm_plan* plan, int32_t mode);
 /* The same two stages for callers whose u / r live in host memory (what makeϕrKt's arguments are, elasticelements.jl:
  * 356-358): elements_host uploads u (d, hist) and runs the element stage -- on large single-batch plans the upload goes
  * in node chunks and K1 starts on the element slice whose nodes have arrived; fetch_phi_r_async enqueues the copy of
@@ -338,6 +345,7 @@ int ad4sm_sync(ad4sm_plan* plan);
 #define AD4SM_OPT_SORTED 3        /* destination-sorted staging + streaming assembly (K2s); default on where available */
 #define AD4SM_OPT_PEER_PUSH 4    /* 1: ad4sm_peer_attach sets up copy-engine pushes instead of K1 peer stores (see there) */
 #define AD4SM_INFO_SORTED 3       /* 0 = not available for this plan, 1 = available but off, 2 = on */
+#define AD4SM_INFO_SPLIT_PAIRS 4  /* node pairs ad4sm_eval_assemble_split_device assembles ahead of the exchange (0: none) */
 int ad4sm_set_option(ad4sm_plan* plan, int32_t option, int64_t value);
 int ad4sm_get_info(ad4sm_plan* plan, int32_t what, int64_t* value);
 

@@ -178,19 +178,22 @@ def test_cuda_path_reproduces_golden_vectors(path):
     _golden.compare(_golden.run_product(case), case, tol=K.TOL)
 
 
-@pytest.mark.parametrize("shape", ["hex8", "tet4"])
-def test_two_rank_halo_exchange_single_gpu(shape):
+@pytest.mark.parametrize("shape,split", [("hex8", False), ("tet4", False), ("hex8", True), ("tet4", True)])
+def test_two_rank_halo_exchange_single_gpu(shape, split):
     """Mesh-partitioned evaluation (dist.py) emulated on ONE GPU: two in-process plans with HALO batches, the
     interface staging copied between them where NCCL send/recv would carry it.  Owned rows must be BITWISE equal to
     the single-plan result (same contributions, same `elems` order).  Both shapes run on the destination-sorted path with
-    export ranges + HALO scatter (hex8: persistent K1; tet4, one Gauss point: the warp-cooperative K1)."""
+    export ranges + HALO scatter (hex8: persistent K1; tet4, one Gauss point: the warp-cooperative K1).
+    split: the interior rows / pairs are assembled BEFORE the interface rows arrive (ad4sm_eval_assemble_split_device),
+    the rest after -- what DistPlan.step does to hide the exchange; the HALO rows hold garbage until then."""
     import torch
     from ad4sm_b200 import dist as AD, mesh
+    dims = (7, 6, 10) if split else (4, 3, 6)
     if shape == "hex8":
-        coords, conn = mesh.hex_block(4, 3, 6, jitter=0.1, seed=21)
+        coords, conn = mesh.hex_block(*dims, jitter=0.1, seed=21)
         b = El.Hex08_batch(conn, coords, K.nh())
     else:
-        coords, conn = mesh.tet_kuhn(3, 3, 4, jitter=0.1, seed=21)
+        coords, conn = mesh.tet_kuhn(*((6, 5, 8) if split else (3, 3, 4)), jitter=0.1, seed=21)
         b = El.Tet04_batch(conn, coords, Ma.MooneyRivlin(800.0, 200.0, 5000.0))
     u = mesh.random_u(len(coords), 3, 1 / 6, seed=22)
     phi0, r0, Kt0 = El.Plan(b, u.shape[1], 3).makeϕrKt(u)
@@ -202,9 +205,16 @@ def test_two_rank_halo_exchange_single_gpu(shape):
         own = El.ElemBatch("CE", 3, p.local_conn(conn[p.own_elems]), b.gradN[p.own_elems], b.wgt[p.own_elems], b.mat)
         backs.append(AD.GpuBackend(own, p.local_conn(conn[p.halo_elems]), p, 3))
     assert all(be.plan.info(capi.INFO_SORTED) == 2 for be in backs)
+    if split:   # rank 0 owns the interface nodes: it has an interior to assemble ahead; rank 1 receives nothing
+        assert backs[0].plan.info(capi.INFO_SPLIT_PAIRS) > 0
     for p, be in zip(parts, backs):
         ul = torch.from_numpy(np.ascontiguousarray(u[:, p.local_nodes - 1].T)).cuda()
+        if split:
+            for a in be.staging():
+                a[be.n_own:] = float("nan")   # nothing may read the HALO rows before the exchange
         be.eval_elements(ul)
+        if split:
+            be.assemble_interior()
         be.plan.sync()
     for g, (p, be) in enumerate(zip(parts, backs)):
         for peer, idx in p.send.items():
