@@ -30,6 +30,7 @@ __all__ = [
     "CEElem", "CPElem", "ElemBatch", "MeshBatch", "SparseMatrixCSC", "Plan",
     "Tria", "Quad", "QuadR", "Tet04", "Hex08", "Hex08R",
     "TriaP", "QuadP", "QuadPR", "Hex08P", "Hex08PR", "Wdg06P", "Tet04P",
+    "CAS", "ASTria", "ASQuad",
     "makeϕrKt", "makeϕrKt_d", "makeϕr", "make_phi_r_Kt", "make_phi_r_Kt_d", "make_phi_r",
 ]
 
@@ -44,7 +45,7 @@ GP1 = ((0.0, 1.0),)
 class ElemBatch:
     """Structure-of-arrays packing of a homogeneous `Vector{CEElem}` / `Vector{CPElem}`: one element
     type (kind, D, P, N) and one material.  Layouts follow the reference's nesting order."""
-    kind: str  # "CE" | "CP"
+    kind: str  # "CE" | "CP" | "CAS" (axisymmetric: D = 2, Nval = N, X0 = radius at the Gauss points)
     D: int
     nodes: np.ndarray  # [ne][N] int64, 1-based
     gradN: np.ndarray  # [ne][D][P][N]
@@ -55,6 +56,7 @@ class ElemBatch:
     orig_index: np.ndarray | None = None  # [ne] position in `elems` (summation order); None = in order
     halo: bool = False  # mesh-partitioned runs: elements evaluated by another rank (dist.py); gradN/wgt may be None
     halo_P: int = 0  # number of Gauss points of a halo batch without wgt
+    X0: np.ndarray | None = None  # [ne][P]  (CAS)
 
     def __post_init__(self):
         self.nodes = np.ascontiguousarray(self.nodes, dtype=np.int64)
@@ -84,12 +86,18 @@ class ElemBatch:
         return self.ne
 
     def __getitem__(self, i):
-        cls = CEElem if self.kind == "CE" else CPElem
+        cls = {"CE": CEElem, "CP": CPElem, "CAS": CAS}[self.kind]
         kw = dict(nodes=self.nodes[i].copy(), gradN=self.gradN[i], wgt=self.wgt[i],
                   V=float(self.V[i]) if self.V is not None else float(self.wgt[i].sum()), mat=self.mat, D=self.D)
-        if self.kind == "CP":
+        if self.kind != "CE":
             kw["N"] = self.Nval[i]
+        if self.kind == "CAS":
+            kw["X0"] = self.X0[i]
         return cls(**kw)
+
+    def hoop_row(self):
+        """CAS: N[gp][a] / X0[gp] -- ∂F33/∂u_r, what the C ABI takes as `Nval` for AD4SM_ELEM_CAS."""
+        return np.ascontiguousarray(self.Nval / self.X0[:, :, None])
 
 
 _SHAPES = {  # shape -> (capi code, D, N, tensor rule?)
@@ -104,7 +112,7 @@ class MeshBatch:
     (`Hex08(nodes, p0; GP, mat)` ...) take, for all elements at once.  ∇N, wgt (and N) are constructed ON THE DEVICE
     (csrc/construct.cu) -- when a Plan is built from it (no host ∇N, no upload), or explicitly into
     host arrays by `materialize()`, which returns the `ElemBatch` the host constructors (`*_batch`) would."""
-    kind: str  # "CE" | "CP"
+    kind: str  # "CE" | "CP" | "CAS" (axisymmetric: D = 2, Nval = N, X0 = radius at the Gauss points)
     shape: str  # key of _SHAPES
     nodes: np.ndarray  # [ne][N] int64, 1-based
     coords: np.ndarray  # [n_nodes][>= D]
@@ -203,6 +211,20 @@ class CPElem(CEElem):
     def __post_init__(self):
         super().__post_init__()
         self.N = np.asarray(self.N, dtype=np.float64)
+
+
+@dataclass
+class CAS(CPElem):
+    """The axisymmetric continuum element `CAS(nodes, N, Nx, Ny, X0, wgt, V, mat)` that `ASTria` / `ASQuad` construct
+    (elasticelements.jl:235-284).  Upstream the struct itself and its `getϕ` are missing; here it is a 2-D
+    element with dofs (u_r, u_z), `gradN = (Nx, Ny)`, the shape-function values `N` and the radius `X0` per Gauss point,
+    evaluated with a 3x3 F (in-plane block + hoop stretch 1 + (N·u_r)/X0) and the 3-D materials -- an extension."""
+    X0: np.ndarray = None  # [P]
+    kind = "CAS"
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.X0 = np.asarray(self.X0, dtype=np.float64)
 
 
 @dataclass
@@ -386,6 +408,22 @@ def Wdg06P_batch(conn, coords, mat, device=False):
     return MeshBatch("CP", "Wdg06", conn, coords, mat) if device else _iso_batch("CP", 3, _shape_wdg, _WDG_PTS, conn, coords, mat)
 
 
+def ASTria_batch(conn, coords, mat):  # elasticelements.jl:235-252
+    b = _tria_batch("CP", conn, coords, mat)   # N = [1,1,1]/3, Nx, Ny, A as in Tria
+    X = np.asarray(coords, dtype=np.float64)[b.nodes - 1]
+    X0 = ((X[:, 0, 0] + X[:, 1, 0] + X[:, 2, 0]) / 3)[:, None]
+    A = b.wgt
+    return ElemBatch("CAS", 2, b.nodes, b.gradN, A * 2 * np.pi * X0, mat, b.Nval, V=A[:, 0], X0=X0)
+
+
+def ASQuad_batch(conn, coords, mat):  # elasticelements.jl:253-285 (2x2 rule, wgt = detJ·2π·r, V = Σ wgt)
+    b = _iso_batch("CP", 2, _shape_quad, _tensor_points(2, GP2), conn, coords, mat)
+    X = np.asarray(coords, dtype=np.float64)[b.nodes - 1]
+    X0 = np.einsum("epa,ea->ep", b.Nval, X[:, :, 0])   # p[1].v = Σ_a N_a x_a, accumulated in node order
+    wgt = b.wgt * 2 * np.pi * X0
+    return ElemBatch("CAS", 2, b.nodes, b.gradN, wgt, mat, b.Nval, V=wgt.sum(axis=1), X0=X0)
+
+
 def _single(batch_ctor, nodes, p0, **kw):
     nodes = np.asarray(nodes, dtype=np.int64)
     p0 = np.asarray(p0, dtype=np.float64)
@@ -402,6 +440,14 @@ def _default_mat(mat):
 # reference signatures: Ctor(nodes, p0; mat=..., GP=...)
 def Tria(nodes, p0, mat=None):
     return _single(Tria_batch, nodes, p0, mat=_default_mat(mat))
+
+
+def ASTria(nodes, p0, mat=None):
+    return _single(ASTria_batch, nodes, p0, mat=_default_mat(mat))
+
+
+def ASQuad(nodes, p0, mat=None):
+    return _single(ASQuad_batch, nodes, p0, mat=_default_mat(mat))
 
 
 def Quad(nodes, p0, GP=GP2, mat=None):
@@ -517,9 +563,10 @@ def as_batches(elems):
         es = [elems[i] for i in idx]
         out.append(ElemBatch(kind, D, np.stack([e.nodes for e in es]), np.stack([e.gradN for e in es]),
                              np.stack([e.wgt for e in es]), es[0].mat,
-                             np.stack([e.N for e in es]) if kind == "CP" else None,
+                             np.stack([e.N for e in es]) if kind != "CE" else None,
                              V=np.array([e.V for e in es]),
-                             orig_index=None if single else np.asarray(idx, dtype=np.int64)))
+                             orig_index=None if single else np.asarray(idx, dtype=np.int64),
+                             X0=np.stack([e.X0 for e in es]) if kind == "CAS" else None))
     return out
 
 
@@ -539,7 +586,7 @@ class Plan:
         for i, b in enumerate(self.batches):
             kind, base, flags, params = material_descriptor(b.mat, pf_grad_term, nh2d_extension)
             s = arr[i]
-            s.elem_kind = capi.ELEM_CE if b.kind == "CE" else capi.ELEM_CP
+            s.elem_kind = {"CE": capi.ELEM_CE, "CP": capi.ELEM_CP, "CAS": capi.ELEM_CAS}[b.kind]
             s.dim, s.n_gauss, s.n_elem_nodes = b.D, b.P, b.N
             s.mat_kind, s.mat_base, s.mat_flags = kind, base, flags
             for k in range(8):
@@ -553,7 +600,12 @@ class Plan:
                 s.mesh = C.pointer(m)
             s.gradN = b.gradN.ctypes.data if b.gradN is not None else None
             s.wgt = b.wgt.ctypes.data if b.wgt is not None else None
-            s.Nval = b.Nval.ctypes.data if b.Nval is not None else None
+            if b.kind == "CAS" and not b.halo:   # the C ABI takes the hoop row N / X0
+                hr = b.hoop_row()
+                self._keep.append(hr)
+                s.Nval = hr.ctypes.data
+            else:
+                s.Nval = b.Nval.ctypes.data if b.Nval is not None else None
             if b.orig_index is not None:
                 oi = np.ascontiguousarray(b.orig_index, dtype=np.int64)
                 self._keep.append(oi)

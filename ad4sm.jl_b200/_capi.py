@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AD4SM_B200_LIB") or os.path.join(_HERE, "lib", "libad4sm_b200.so")
 
 OK, EINVAL, ENODEV, ENOMEM, ESTATE, ENCCL = 0, -1, -2, -3, -4, -5
-ELEM_CE, ELEM_CP = 0, 1
+ELEM_CE, ELEM_CP, ELEM_CAS = 0, 1, 2
 MAT_HOOKE, MAT_HOOKE2D, MAT_NEOHOOKE, MAT_MOONEYRIVLIN, MAT_OGDEN, MAT_PHASEFIELD = 1, 2, 3, 4, 5, 6
 F_SMALL, F_PLANE_STRESS, F_DHN, F_PF_GRAD_INTENDED, F_NH2D_EXT = 1, 2, 4, 8, 16
 FIELD_U, FIELD_D = 0, 1

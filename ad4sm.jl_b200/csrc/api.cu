@@ -173,6 +173,16 @@ template <class T> static int dev_upload(ad4sm_plan* p, T** ptr, const T* host, 
 
 static int mat_family(const ad4sm_batch& b, int* mf, std::string* why) {
   const int kind = b.mat_kind;
+  if (b.elem_kind == AD4SM_ELEM_CAS) {  // 3x3 F (in-plane block + hoop stretch): the 3-D elastic materials
+    switch (kind) {
+      case AD4SM_MAT_HOOKE: *mf = MF_HOOKE; return 0;
+      case AD4SM_MAT_NEOHOOKE: *mf = MF_NEO; return 0;
+      case AD4SM_MAT_MOONEYRIVLIN: *mf = MF_MOONEY; return 0;
+      case AD4SM_MAT_OGDEN: *mf = MF_OGDEN; return 0;
+    }
+    *why = "CAS (axisymmetric) elements evaluate a 3x3 F: the material must be Hooke, NeoHooke, MooneyRivlin or Ogden";
+    return -1;
+  }
   if (kind == AD4SM_MAT_PHASEFIELD) {
     const int base = b.mat_base;
     const bool dhn = b.mat_flags & AD4SM_F_DHN;
@@ -458,13 +468,19 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       return fail(AD4SM_EINVAL, "batch arrays missing");
     if (B.elem_kind == AD4SM_ELEM_CP && B.n_elems > 0 && !halo && !B.mesh && !B.Nval)
       return fail(AD4SM_EINVAL, "CPElem batch needs Nval");
+    if (B.elem_kind == AD4SM_ELEM_CAS) {
+      if (B.dim != 2 || (B.n_elem_nodes != 3 && B.n_elem_nodes != 4)) return fail(AD4SM_EINVAL, "CAS batches are 2-D with 3 or 4 nodes (ASTria / ASQuad)");
+      if (B.mesh) return fail(AD4SM_EINVAL, "CAS batches have no device constructor: pass gradN, wgt and the hoop row N/X0");
+      if (B.n_elems > 0 && !halo && !B.Nval) return fail(AD4SM_EINVAL, "CAS batch needs Nval = N / X0 (the hoop row)");
+    }
     if (B.mesh && !halo) {  // constructed on the device from the coordinates: the declared shape must be the mesh's
       int mD, mN, mP;
       if (shape_dims(B.mesh->shape, B.mesh->n_gp_1d, &mD, &mN, &mP) || mD != B.dim || mN != B.n_elem_nodes || mP != B.n_gauss)
         return fail(AD4SM_EINVAL, "batch.mesh: shape / rule do not match dim, n_elem_nodes, n_gauss of the batch");
       if (B.mesh->n_nodes != n_nodes) return fail(AD4SM_EINVAL, "batch.mesh: n_nodes differs from the plan's");
     }
-    if (B.elem_kind != AD4SM_ELEM_CE && B.elem_kind != AD4SM_ELEM_CP) return fail(AD4SM_EINVAL, "unknown elem_kind");
+    if (B.elem_kind != AD4SM_ELEM_CE && B.elem_kind != AD4SM_ELEM_CP && B.elem_kind != AD4SM_ELEM_CAS)
+      return fail(AD4SM_EINVAL, "unknown elem_kind");
     std::string why;
     if (mat_family(B, &mfs[b], &why)) return fail(AD4SM_EINVAL, why);
     const char* r = k1_unsupported_reason(B.dim, B.n_elem_nodes, B.n_gauss, mfs[b], 0);
@@ -719,6 +735,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       bp.k.P = B.n_gauss;
       bp.k.mf = mfs[b];
       bp.k.dpn = dofs_per_node;
+      bp.k.cas = B.elem_kind == AD4SM_ELEM_CAS;
       bp.hist_off = h0;
       bp.halo = (B.batch_flags & AD4SM_BATCH_HALO) != 0;
       if (!bp.halo) {
@@ -740,7 +757,7 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
           bp.k.gradN = x;
           TRY(dev_upload(p, &x, B.wgt, (size_t)B.n_elems * B.n_gauss));
           bp.k.wgt = x;
-          if (B.elem_kind == AD4SM_ELEM_CP) {
+          if (B.elem_kind == AD4SM_ELEM_CP || B.elem_kind == AD4SM_ELEM_CAS) {
             TRY(dev_upload(p, &x, B.Nval, (size_t)B.n_elems * B.n_gauss * N));
             bp.k.Nval = x;
           }
@@ -1354,6 +1371,14 @@ int ad4sm_peer_attach(ad4sm_plan* p, int32_t n_links, const ad4sm_peer_link* lin
     p->n_xr = n_links;
     p->n_xr_local = n_links;
     p->push_end = std::min<long long>(p->n_own_sorted, (end + 31) & ~31ll);
+    {  // the first K1 slice ends on a whole wave of the persistent kernel (all warps of all SMs busy to its end)
+      K1Config c;
+      const BatchPlan& b0 = p->batches[0];
+      if (k1_config(p->D, p->N, b0.k.P, false, b0.k.ne, &c) && c.persistent) {
+        const long long wave = (long long)c.grid * c.warps * c.EW;
+        if (wave > 0) p->push_end = std::min<long long>(p->n_own_sorted, (p->push_end + wave - 1) / wave * wave);
+      }
+    }
     p->parity = 0;
     p->push_pending = false;
     p->dist_aware = true;
@@ -2015,6 +2040,7 @@ int ad4sm_post_device(ad4sm_plan* p, const double* u_dev, double* F, double* det
   if (!u_dev) return fail(AD4SM_EINVAL, "u is NULL");
   for (const BatchPlan& b : p->batches) {
     if (b.halo) return fail(AD4SM_EINVAL, "post-processing on a plan with HALO batches: evaluate each rank's own elements with its own plan");
+    if (b.k.cas) return fail(AD4SM_EINVAL, "post-processing of CAS batches is not defined (the reference has no getF for them)");
     if ((sigma || Pk) && b.k.mat.kind == MAT_PHASEFIELD)
       return fail(AD4SM_EINVAL, "getσ / getP need an elastic material: the reference has no getϕ(F, ::PhaseField) (phasefieldmaterials.jl:20)");
   }

@@ -208,6 +208,101 @@ AD4SM_DI void gauss_point_d(const MatDev& m, const double* G, const double* Nv, 
   for (int k = 0; k < D; k++) rec[4 + k] = gd[k];
 }
 
+// ---- CAS: axisymmetric continuum element (EXTENSION: the reference has the constructors ASTria / ASQuad,
+// elasticelements.jl:235-284, but neither the struct nor its getϕ -- SURVEY §9-7) ---------------------------------------
+// Energy  Φ_e = Σ_gp wgt ϕ(F),  F = [1+u_r,r  u_r,z  0;  u_z,r  1+u_z,z  0;  0  0  1 + u_r/r]  with the 3-D material ϕ;
+// dofs (u_r, u_z) per node; wgt carries 2π r (elasticelements.jl:249, 279).  F is linear in u, so -- as for the other
+// elements -- gradient and Hessian are the exact chain of the material tangent (P, A) through  ∂F/∂u:
+//   ∂F_(k,j)/∂u_(a,j) = ∇N_a,k (k, j in {r, z}),   ∂F_33/∂u_(a,r) = N_a / r =: H_a   (the "hoop row", K1Args.Nval).
+// One thread per element; Kf = full (2N)x(2N) tangent [row dof][col dof], dof = 2*node + comp.
+template <int N, int MF>
+AD4SM_DI void cas_element(const MatDev& m, int P, const double* gN, const double* wg, const double* Hr, const double* ue,
+                          bool want_K, double* Kf, double* r, double& phi) {
+  constexpr int ND = 2 * N;
+  constexpr int I5[5] = {0, 1, 3, 4, 8};  // the F components that depend on u, as linear indices k*3 + j of the 3x3 F
+  phi = 0.0;
+#pragma unroll
+  for (int i = 0; i < ND; i++) r[i] = 0.0;
+  if (want_K) {
+#pragma unroll
+    for (int i = 0; i < ND * ND; i++) Kf[i] = 0.0;
+  }
+  for (int gp = 0; gp < P; gp++) {
+    double G[2 * N], H[N];
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+      for (int a = 0; a < N; a++) G[k * N + a] = gN[(k * P + gp) * N + a];
+#pragma unroll
+    for (int a = 0; a < N; a++) H[a] = Hr[gp * N + a];
+    double F2[4];
+    deformation_gradient<2, N>(G, ue, F2);
+    double hoop = 0.0;
+#pragma unroll
+    for (int a = 0; a < N; a++) hoop += H[a] * ue[a * 2];
+    double F[9] = {F2[0], F2[1], 0.0, F2[2], F2[3], 0.0, 0.0, 0.0, hoop + 1.0};
+    Tangent<3> t;
+    material_tangent<3, MF>(m, F, nullptr, t);
+    const double w = wg[gp];
+    phi += w * t.psi;
+    // B_(a,j)[I]: the derivative of F component I5[I] with respect to dof (a, j)
+    auto Bv = [&](int a, int j, int I) -> double {
+      return I < 4 ? ((I & 1) == j ? G[(I >> 1) * N + a] : 0.0) : (j == 0 ? H[a] : 0.0);
+    };
+#pragma unroll
+    for (int a = 0; a < N; a++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int I = 0; I < 5; I++) s += Bv(a, j, I) * t.P[I5[I]];
+        r[a * 2 + j] += w * s;
+      }
+    if (want_K) {
+#pragma unroll
+      for (int b = 0; b < N; b++)
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+          double T[5];  // T[I] = Σ_J A_(I,J) B_(b,l)[J]
+#pragma unroll
+          for (int I = 0; I < 5; I++) {
+            double s = 0.0;
+#pragma unroll
+            for (int J = 0; J < 5; J++) s += t.A[pk(I5[I], I5[J])] * Bv(b, l, J);
+            T[I] = w * s;
+          }
+#pragma unroll
+          for (int a = 0; a < N; a++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              double s = Kf[(a * 2 + j) * ND + b * 2 + l];
+#pragma unroll
+              for (int I = 0; I < 5; I++) s += Bv(a, j, I) * T[I];
+              Kf[(a * 2 + j) * ND + b * 2 + l] = s;
+            }
+        }
+    }
+  }
+}
+// the full element tangent into the cyclic block storage Ke [NPB][2*2]; diagonal node blocks mirrored like column_u_acc
+template <int N> AD4SM_DI void cas_store(const double* Kf, double* Ke) {
+  constexpr int ND = 2 * N;
+#pragma unroll
+  for (int q = 0; q < N; q++)
+#pragma unroll
+    for (int o = 0; o <= N / 2; o++)
+      if (o < n_offsets(N, q)) {
+        const int a = (q + o) % N;
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int l = 0; l < 2; l++) {
+            const int jj = (o == 0 && j > l) ? l : j, ll = (o == 0 && j > l) ? j : l;  // lower entry := upper entry
+            Ke[(o * N + q) * 4 + j * 2 + l] = Kf[(a * 2 + jj) * ND + q * 2 + ll];
+          }
+      }
+}
+
 // T[(k,j)][l] = Σ_m A_(kj)(ml) ∇N_b,m  from the packed symmetric A (81 FMAs for D = 3)
 template <int D, class Mem> AD4SM_DI void tangent_times_gradient(const Mem& A, const double* gb, double (*T)[D]) {
   constexpr int DD = D * D;

@@ -52,6 +52,7 @@ struct K1Args {
   int mf;               // MatFamily
   int dpn;              // rows of u (dofs per node of the displacement field)
   int want_K;           // 0: ϕ and r only (makeϕr)
+  int cas;              // 1: axisymmetric CAS batch (D = 2; Nval = N / X0, the hoop row; 3-D material on a 3x3 F)
   const int* nodes;     // [ne][N] 0-based
   const double* gradN;  // [ne][D][P][N]
   const double* wgt;    // [ne][P]

@@ -669,6 +669,46 @@ template <int D, int N, int MF, bool PF> __global__ void __launch_bounds__(K1_TH
 }
 
 
+// ---- K1 for CAS batches (axisymmetric extension, element.cuh: cas_element): one thread per element, element-major
+// staging (D = 2: the K2 gather assembles it like any 2-D element) ------------------------------------------------------
+template <int N, int MF> __global__ void __launch_bounds__(64) k1_cas_kernel(const K1Args a) {
+  const long long e = (long long)blockIdx.x * 64 + threadIdx.x;
+  if (e >= a.ne) return;
+  constexpr int ND = 2 * N;
+  double ue[ND];
+#pragma unroll
+  for (int n = 0; n < N; n++) {
+    const long long nd = __ldg(a.nodes + e * N + n);
+#pragma unroll
+    for (int j = 0; j < 2; j++) ue[n * 2 + j] = __ldg(a.u + nd * a.dpn + j);
+  }
+  double Kf[ND * ND], r[ND], phi;
+  cas_element<N, MF>(a.mat, a.P, a.gradN + e * (long long)(2 * a.P * N), a.wgt + e * a.P, a.Nval + e * (long long)(a.P * N), ue,
+                     a.want_K != 0, Kf, r, phi);
+  const long long slot = a.slot0 + e;
+  if (a.want_K) cas_store<N>(Kf, a.Ke + slot * (long long)(n_pair_blocks(N) * 4));
+#pragma unroll
+  for (int i = 0; i < ND; i++) a.re[slot * ND + i] = r[i];
+  a.phie[slot] = phi;
+}
+template <int N> static cudaError_t launch_cas_n(const K1Args& a, cudaStream_t s) {
+  const unsigned grid = (unsigned)((a.ne + 63) / 64);
+  switch (a.mf) {
+    case MF_HOOKE: k1_cas_kernel<N, MF_HOOKE><<<grid, 64, 0, s>>>(a); break;
+    case MF_NEO: k1_cas_kernel<N, MF_NEO><<<grid, 64, 0, s>>>(a); break;
+    case MF_MOONEY: k1_cas_kernel<N, MF_MOONEY><<<grid, 64, 0, s>>>(a); break;
+    case MF_OGDEN: k1_cas_kernel<N, MF_OGDEN><<<grid, 64, 0, s>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+static cudaError_t launch_cas(const K1Args& a, cudaStream_t s) {
+  if (a.D != 2 || !a.Nval || a.cpos) return cudaErrorInvalidValue;
+  if (a.N == 3) return launch_cas_n<3>(a, s);
+  if (a.N == 4) return launch_cas_n<4>(a, s);
+  return cudaErrorInvalidValue;
+}
+
 // ---- K1, u-dual, one thread per element (P == 1), warp-cooperative output ------------------------------------------
 // The thread-per-element kernel above leaves every store to the owning thread: 102 STG.64 per Tet4 element at a lane
 // stride of 720 B, i.e. 32 cache lines per instruction -- the LSU's one-line-per-cycle front end, not DRAM, bounds it
@@ -1009,6 +1049,7 @@ cudaError_t launch_k1(const K1Args& a, int mode, cudaStream_t s) {
   if (!lanes_for(a.D, a.N, a.P, LP)) return cudaErrorInvalidValue;
   const bool is_pf = a.mat.kind == MAT_PHASEFIELD;
   if ((mode == MODE_ELASTIC) == is_pf) return cudaErrorInvalidValue;  // PhaseField needs d; elastic has none
+  if (a.cas) return mode == MODE_ELASTIC ? launch_cas(a, s) : cudaErrorInvalidValue;
   const bool pf = (mode == MODE_PF_U);
 #define SHAPE(DD, NN, LL)                 \
   if (a.D == DD && a.N == NN && LP == LL) \

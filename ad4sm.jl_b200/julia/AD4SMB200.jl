@@ -26,7 +26,7 @@ using SparseArrays
 const lib = get(ENV, "AD4SM_B200_LIB", joinpath(@__DIR__, "..", "lib", "libad4sm_b200.so"))
 
 # ---- include/ad4sm_b200.h ---------------------------------------------------------------------------
-const ELEM_CE, ELEM_CP = Int32(0), Int32(1)
+const ELEM_CE, ELEM_CP, ELEM_CAS = Int32(0), Int32(1), Int32(2)
 const MAT_HOOKE, MAT_HOOKE2D, MAT_NEOHOOKE, MAT_MOONEYRIVLIN, MAT_OGDEN, MAT_PHASEFIELD = Int32.(1:6)
 const F_SMALL, F_PLANE_STRESS, F_DHN, F_PF_GRAD_INTENDED, F_NH2D_EXT = UInt32(1), UInt32(2), UInt32(4), UInt32(8), UInt32(16)
 
@@ -88,6 +88,48 @@ function pack(elems::AbstractVector{E}, idx::Vector{Int}; kw...) where {D,P,M,T,
   b = Batch(iscp ? ELEM_CP : ELEM_CE, D, P, N, kind, base, flags, 0, pad8(params...), ne,
             pointer(nodes), pointer(gradN), pointer(wgt), iscp ? pointer(Nval) : C_NULL, pointer(oi), C_NULL)
   Packed(b, Any[nodes, gradN, wgt, Nval, oi])
+end
+
+# ---- CAS: the axisymmetric element the reference constructs but never defines (elasticelements.jl:251, 284 call
+# `CAS(nodes, N, Nx, Ny, X0, wgt, V, mat)`; no struct, no getϕ -- SURVEY §9-7).  Defining it inside AD4SM.Elements makes
+# `ASTria` / `ASQuad` work as written; its energy exists only in this backend (3x3 F with the hoop stretch 1 + (N·u_r)/X0
+# and the 3-D materials; an extension, see include/ad4sm_b200.h AD4SM_ELEM_CAS).
+@eval AD4SM.Elements begin
+  struct CAS{P,M,T,N} <: AbstractCElem{2,P,M,T,N}
+    nodes::Vector{Int}
+    N::NTuple{P,Vector{T}}
+    Nx::NTuple{P,Vector{T}}
+    Ny::NTuple{P,Vector{T}}
+    X0::NTuple{P,T}
+    wgt::NTuple{P,T}
+    V::T
+    mat::M
+  end
+  CAS(nodes, N, Nx, Ny, X0, wgt, V, mat::M) where M =
+    CAS{length(wgt),M,typeof(float(V)),length(nodes)}(collect(Int, nodes), Tuple(N), Tuple(Nx), Tuple(Ny), Tuple(X0), Tuple(wgt), float(V), mat)
+end
+const CAS = AD4SM.Elements.CAS
+function pack(elems::AbstractVector{E}, idx::Vector{Int}; kw...) where {P,M,T,N,E<:CAS{P,M,T,N}}
+  ne = length(idx)
+  nodes = Matrix{Int64}(undef, N, ne)
+  gradN = Array{Float64}(undef, N, P, 2, ne)          # [ne][2][P][N] = (Nx, Ny)
+  wgt   = Matrix{Float64}(undef, P, ne)
+  hoop  = Array{Float64}(undef, N, P, ne)             # the C ABI's Nval for CAS: N[gp][a] / X0[gp]
+  for (k, ii) in enumerate(idx)
+    e = elems[ii]
+    nodes[:, k] .= e.nodes
+    for p in 1:P
+      gradN[:, p, 1, k] .= e.Nx[p]
+      gradN[:, p, 2, k] .= e.Ny[p]
+      hoop[:, p, k]     .= e.N[p] ./ e.X0[p]
+    end
+    wgt[:, k] .= e.wgt
+  end
+  kind, base, flags, params = matdesc(elems[idx[1]].mat)
+  oi = Int64.(idx .- 1)
+  b = Batch(ELEM_CAS, 2, P, N, kind, base, flags, 0, pad8(params...), ne,
+            pointer(nodes), pointer(gradN), pointer(wgt), pointer(hoop), pointer(oi), C_NULL)
+  Packed(b, Any[nodes, gradN, wgt, hoop, oi])
 end
 
 # ---- batched constructors on the device (ad4sm_construct; elasticelements.jl:35-197, phasefieldelements.jl:9-145) ---------

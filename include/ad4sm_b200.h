@@ -37,6 +37,13 @@ extern "C" {
 /* element kinds: CEElem{D,P,M,T,N} (elements.jl:71-77), CPElem (elements.jl:104-111) */
 #define AD4SM_ELEM_CE 0
 #define AD4SM_ELEM_CP 1
+/* CAS: the axisymmetric continuum element north_star names.  The reference only ships its constructors (ASTria / ASQuad,
+ * elasticelements.jl:235-284: N, Nx, Ny, the radius X0 and wgt = detJ*2π*X0 at every Gauss point); the struct `CAS` they
+ * call and its getϕ do not exist, so the energy is this library's EXTENSION (parity unpinned): a 3x3
+ * deformation gradient with the in-plane block I + ∇u (rows r, z) and the hoop stretch F33 = 1 + (N·u_r)/X0, fed to the
+ * 3-D materials (Hooke, NeoHooke, MooneyRivlin, Ogden), Φ_e = Σ_gp wgt ϕ(F).  dim = 2, dofs (u_r, u_z) per node; gradN holds
+ * (Nx, Ny) and `Nval` holds the HOOP ROW  N[gp][a] / X0[gp]. */
+#define AD4SM_ELEM_CAS 2
 
 /* material kinds (elasticmaterials.jl:25-120, phasefieldmaterials.jl:5-16) */
 #define AD4SM_MAT_HOOKE 1        /* params: E, nu                flags: SMALL */
@@ -100,7 +107,7 @@ typedef struct ad4sm_batch {
   const int64_t* nodes;      /* [n_elems][N]        elem.nodes, 1-based */
   const double* gradN;       /* [n_elems][D][P][N]  elem.∇N[d][gp][a] */
   const double* wgt;         /* [n_elems][P]        elem.wgt[gp] */
-  const double* Nval;        /* [n_elems][P][N]     elem.N[gp][a]   (CPElem; NULL for CEElem) */
+  const double* Nval;        /* [n_elems][P][N]     elem.N[gp][a]   (CPElem; NULL for CEElem; CAS: elem.N[gp][a] / elem.X0[gp]) */
   const int64_t* orig_index; /* [n_elems] 0-based position of each element in `elems` (fixes the
                                 summation order); NULL = the element's slot, i.e. its position in the
                                 concatenation of ALL batches in the order given (not "after the largest

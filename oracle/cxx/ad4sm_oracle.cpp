@@ -498,7 +498,7 @@ static R getphi_pf(const Mx<TF, D>& F, const TD& d, const TD* gd, const Mat& m, 
 // element layer
 // ------------------------------------------------------------------------------------------------
 struct Batch {
-  int kind;  // 0 = CEElem, 1 = CPElem
+  int kind;  // 0 = CEElem, 1 = CPElem, 2 = CAS (axisymmetric extension; Nval = N / X0)
   int D, P, N;
   Mat mat;
   i64 ne;
@@ -613,6 +613,20 @@ static void elem_u(const Batch& b, i64 e, int mode, const double* u, int dpn, co
         ue[a * D + j].g[a * D + j] = 1.0;
       }
     for (int gp = 0; gp < P; gp++) {
+      if (b.kind == 2) {
+        // CAS (axisymmetric; EXTENSION, no reference getϕ -- SURVEY §9-7, constructors elasticelements.jl:235-284):
+        // 3x3 F = in-plane block I + ∇u (rows r, z) and the hoop stretch 1 + (N·u_r)/X0; Nval holds N/X0 here
+        if constexpr (D == 2) {
+          Mx<D2<n>, 2> F2 = getF<D2<n>, 2, N>(gN, P, gp, ue);
+          Mx<D2<n>, 3> F3;
+          for (int k = 0; k < 9; k++) F3.a[k] = lift<n>(0.0);
+          for (int j = 0; j < 2; j++)
+            for (int k = 0; k < 2; k++) F3.at(j, k) = F2.at(j, k);
+          F3.at(2, 2) = edot<D2<n>, N>(Nv + gp * N, ue, D) + 1.0;
+          *phi = *phi + w[gp] * getphi<D2<n>>(F3, b.mat);
+        }
+        continue;
+      }
       Mx<D2<n>, D> F = getF<D2<n>, D, N>(gN, P, gp, ue);
       if (mode == M_PF_U) {
         double dv = edot<double, N>(Nv + gp * N, de, 1);

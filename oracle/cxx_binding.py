@@ -113,7 +113,7 @@ def elem_duals(kind, D, P, N, mat, nodes, gradN, wgt, Nval, mode, u, d=None, his
     ne = nodes.shape[0]
     n = N if mode == M_PF_D else D * N
     md, mp = mat_desc(mat, grad_term, nh2d_extension)
-    if type(mat).__name__ == "Ogden" and (D != 3 or float(mat.alpha) != int(mat.alpha) or not 1 <= mat.alpha <= 8):
+    if type(mat).__name__ == "Ogden" and ((D != 3 and kind != "CAS") or float(mat.alpha) != int(mat.alpha) or not 1 <= mat.alpha <= 8):
         # the C++ restatement differentiates Σλ^α = tr(U^α) through a matrix square root: 3-D, integer α only
         raise ValueError("oracle (C++): Ogden is restated for 3-D elements and integer alpha in 1..8; use oracle/materials.py otherwise")
     val = np.empty(ne)
@@ -121,7 +121,7 @@ def elem_duals(kind, D, P, N, mat, nodes, gradN, wgt, Nval, mode, u, d=None, his
     H = np.empty((ne, n, n))
     if hist is not None:
         assert hist.dtype == np.float64 and hist.flags.c_contiguous and hist.shape == (ne, P, 2)
-    rc = L.oracle_elem_duals(C.c_int(0 if kind == "CE" else 1), C.c_int(D), C.c_int(P), C.c_int(N), _ptr(md), _ptr(mp),
+    rc = L.oracle_elem_duals(C.c_int({"CE": 0, "CP": 1, "CAS": 2}[kind]), C.c_int(D), C.c_int(P), C.c_int(N), _ptr(md), _ptr(mp),
                              C.c_int64(ne), _ptr(nodes), _ptr(gradN), _ptr(wgt), _ptr(Nval), C.c_int(mode), _ptr(u),
                              C.c_int(dpn), _ptr(d), _ptr(hist), C.c_int(nthreads), _ptr(val), _ptr(g), _ptr(H))
     if rc != 0:
@@ -157,7 +157,10 @@ def make_phi_r_Kt(batches, u, mode=M_ELASTIC, d=None, hist=None, nthreads=0, tim
     vals, gs, Hs, nds = [], [], [], []
     for i, b in enumerate(batches):
         h = None if hist is None else hist[i]
-        v, g, H = elem_duals(b.kind, b.D, b.P, b.N, b.mat, b.nodes, b.gradN, b.wgt, b.Nval, mode, u, d, h, nthreads, **kw)
+        Nv = b.Nval
+        if b.kind == "CAS":   # axisymmetric extension: the C++ side takes the hoop row N[gp][a] / X0[gp]
+            Nv = np.ascontiguousarray(np.asarray(b.Nval) / np.asarray(b.X0)[:, :, None])
+        v, g, H = elem_duals(b.kind, b.D, b.P, b.N, b.mat, b.nodes, b.gradN, b.wgt, Nv, mode, u, d, h, nthreads, **kw)
         if mode != M_PF_D and u.shape[0] > b.D:
             # the reference seeds every row of u[:, nodes] (elasticelements.jl:217) but getF reads rows 1:D only
             # (toolkit:13): the extra dofs carry exact-zero derivatives.  Expand (D*N) -> (dpn*N).

@@ -38,7 +38,8 @@ class Elem:
     wgt: np.ndarray  # [P]
     V: float
     mat: object
-    Nval: np.ndarray | None = None  # [P][N]  (CPElem only)
+    Nval: np.ndarray | None = None  # [P][N]  (CPElem; CAS: the shape-function values N)
+    X0: np.ndarray | None = None  # [P]  radius at the Gauss points (kind='CAS' only, elasticelements.jl:247, 273)
 
     @property
     def P(self):
@@ -195,6 +196,68 @@ def TriaP(nodes, p0, mat):  # phasefieldelements.jl:9-24
                 np.array([[1 / 3, 1 / 3, 1 / 3]]))
 
 
+# ---- axisymmetric constructors (elasticelements.jl:235-284).  They end in `CAS(nodes, N, Nx, Ny, X0, wgt, V, mat)`, a
+# struct that does not exist upstream: only this data recipe is the reference's; kind='CAS' holds it.
+def ASTria(nodes, p0, mat):  # elasticelements.jl:235-252
+    (x1, x2, x3) = (p0[0][0], p0[1][0], p0[2][0])
+    (y1, y2, y3) = (p0[0][1], p0[1][1], p0[2][1])
+    Delta = x1 * y2 - x2 * y1 - x1 * y3 + x3 * y1 + x2 * y3 - x3 * y2
+    N = np.array([1, 1, 1]) / 3
+    Nx = np.array([y2 - y3, y3 - y1, y1 - y2]) / Delta
+    Ny = np.array([x3 - x2, x1 - x3, x2 - x1]) / Delta
+    A = abs(Delta) / 2
+    X0 = (x1 + x2 + x3) / 3
+    wgt = A * 2 * np.pi * X0
+    return Elem("CAS", 2, np.asarray(nodes, dtype=np.int64), np.stack([Nx[None], Ny[None]]), np.array([wgt]), A, mat,
+                N[None], np.array([X0]))
+
+
+def ASQuad(nodes, p0, mat):  # elasticelements.jl:253-285
+    r = np.array([-1, 1]) * 0.577350269189626
+    p0 = np.asarray(p0, dtype=float)
+    N0 = np.empty((2, 2), dtype=object)
+    Nx = np.empty((2, 2), dtype=object)
+    Ny = np.empty((2, 2), dtype=object)
+    X0 = np.empty((2, 2))
+    wgt = np.empty((2, 2))
+    V = 0
+    for ii, xi in enumerate(r):  # `for (ii, ξ) in enumerate(r), (jj, η) in enumerate(r)`: ii outer
+        for jj, eta in enumerate(r):
+            Nij = _quad_shape(*adiff.seed_D1(np.array([xi, eta])))
+            p = [None, None]
+            for i in range(2):
+                s_ = Nij[0] * p0[0][i]
+                for a in range(1, 4):
+                    s_ = s_ + Nij[a] * p0[a][i]
+                p[i] = s_
+            J = np.array([[p[i].g[j] for i in range(2)] for j in range(2)])  # J[jj,ii] = p[ii].g[jj]
+            Nxy = np.linalg.solve(J, np.stack([adiff.grad(n) for n in Nij], axis=1))
+            N0[ii, jj] = np.array([n.v for n in Nij])
+            Nx[ii, jj] = Nxy[0, :]
+            Ny[ii, jj] = Nxy[1, :]
+            X0[ii, jj] = p[0].v
+            wgt[ii, jj] = _det2(J) * 2 * np.pi * p[0].v
+            V += wgt[ii, jj]
+    flat = lambda A: [A[ii, jj] for jj in range(2) for ii in range(2)]  # tuple(A...): column-major, ii fastest
+    gradN = np.stack([np.stack(flat(Nx)), np.stack(flat(Ny))])
+    return Elem("CAS", 2, np.asarray(nodes, dtype=np.int64), gradN, np.array(flat(wgt)), V, mat, np.stack(flat(N0)),
+                np.array(flat(X0)))
+
+
+def getF_cas(elem: Elem, u, gp: int):
+    """EXTENSION (no reference counterpart): 3x3 F of an axisymmetric element, rows/columns (r, z, θ):
+    in-plane block I + ∇u from (Nx, Ny), hoop stretch F33 = 1 + (N·u_r)/X0."""
+    F = np.empty((3, 3), dtype=object)
+    F[:, :] = 0.0
+    for j in range(2):
+        for k in range(2):
+            F[j, k] = _dot(elem.gradN[k, gp], u[j, :])
+    for j in range(2):
+        F[j, j] = F[j, j] + 1
+    F[2, 2] = _dot(elem.Nval[gp], u[0, :]) / elem.X0[gp] + 1
+    return F
+
+
 def _tet_data(p0):  # elasticelements.jl:85-94
     A = np.ones((4, 4))
     for i in range(4):
@@ -278,7 +341,7 @@ def chain(phi: D2, F) -> D2:
 def _integrate(elem: Elem, u):  # elasticelements.jl:199-206
     phi = 0.0
     for gp in range(elem.P):
-        F = getF(elem, u, gp)
+        F = getF_cas(elem, u, gp) if elem.kind == "CAS" else getF(elem, u, gp)
         phi = phi + elem.wgt[gp] * M.getphi(F, elem.mat)
     return phi
 

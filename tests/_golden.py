@@ -39,6 +39,7 @@ def load(path):
     for k in ("nodes", "gradN", "wgt", "u", "phi", "r", "colptr", "rowval", "nzval"):
         setattr(c, k, z[k])
     c.Nval = z["Nval"] if "Nval" in z.files else None
+    c.X0 = z["X0"] if "X0" in z.files else None
     c.d = z["d"] if "d" in z.files else None
     c.hist_in = z["hist_in"] if "hist_in" in z.files else None
     c.hist_out = z["hist_out"] if "hist_out" in z.files else None
@@ -61,7 +62,7 @@ def run_oracle(c):
 def run_product(c):
     """The CUDA path through the C ABI on the golden inputs."""
     from ad4sm_b200 import Elements as El, Materials as Ma
-    b = El.ElemBatch(c.kind, c.D, c.nodes, c.gradN, c.wgt, _mat(Ma, c.meta["mat"]), c.Nval)
+    b = El.ElemBatch(c.kind, c.D, c.nodes, c.gradN, c.wgt, _mat(Ma, c.meta["mat"]), c.Nval, X0=c.X0)
     popts = {}
     if "grad_term" in c.opts:
         popts["pf_grad_term"] = c.opts["grad_term"]

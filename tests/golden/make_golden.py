@@ -36,6 +36,8 @@ def save(name, elems, u, mode="elastic", d=None, hist=None, **opts):
                nodes=b.nodes, gradN=b.gradN, wgt=b.wgt, u=np.asfortranarray(u), phi=phi, r=r, colptr=cp, rowval=rv, nzval=nz)
     if b.Nval is not None:
         out["Nval"] = b.Nval
+    if getattr(b, "X0", None) is not None:
+        out["X0"] = b.X0
     if d is not None:
         out["d"] = d
     if hist is not None:
@@ -73,6 +75,13 @@ def main():
     u, d = T._u(X0, 3, amp=0.05, seed=29), np.random.default_rng(30).uniform(0, 0.5, len(X0))
     save("hex8p_pf_neohooke_u", e, u, "pf_u", d)
     save("hex8p_pf_neohooke_d", e, u, "pf_d", d, grad_term="intended")
+    # axisymmetric CAS (extension): meshes shifted off the axis (r in [0.7, 1.7])
+    e, X0 = T.quad_mesh((3, 3), NH, seed=31, ctor=E.ASQuad, shift=(0.7, 0.0))
+    save("asquad_neohooke", e, T._u(X0, 2, seed=32))
+    e, X0 = T.quad_mesh((3, 2), M.Hooke(210000.0, 0.3), seed=33, ctor=E.ASQuad, shift=(0.7, 0.0))
+    save("asquad_hooke_gl", e, T._u(X0, 2, seed=34))
+    e, X0 = T.tri_mesh((3, 3), MR, seed=35, ctor=E.ASTria, shift=(0.7, 0.0))
+    save("astria_mooney", e, T._u(X0, 2, seed=36))
 
 
 if __name__ == "__main__":

@@ -481,3 +481,55 @@ def test_ragged_element_list_is_rejected():
     bt = El.Tet04_batch(conn, coords, K.nh())
     with pytest.raises(capi.AD4SMError):
         El.Plan([bh, bt], max(u.shape[1], len(coords)), 3)
+
+
+# ---- CAS: axisymmetric continuum elements (extension; oracle pins: tests/test_oracle_pins.py §6) ----------
+def _cas_case(ctor, n, mat, seed):
+    from ad4sm_b200 import mesh
+    grid = mesh.quad_grid if ctor is El.ASQuad_batch else mesh.tri_grid
+    coords, conn = grid(*n, jitter=0.1, seed=seed)
+    coords = coords + np.array([0.6, 0.0])   # off the axis
+    b = ctor(conn, coords, mat)
+    u = mesh.random_u(len(coords), 2, 1.0 / max(n), a=0.03, seed=seed + 100)
+    return b, u, coords
+
+
+@pytest.mark.parametrize("ctor,mat", [
+    (El.ASQuad_batch, K.nh()), (El.ASQuad_batch, Ma.Hooke(210000.0, 0.3)), (El.ASQuad_batch, Ma.Hooke(210000.0, 0.3, small=True)),
+    (El.ASQuad_batch, Ma.MooneyRivlin(800.0, 200.0, 5000.0)), (El.ASTria_batch, K.nh()),
+    (El.ASTria_batch, Ma.MooneyRivlin(800.0, 200.0, 5000.0)), (El.ASQuad_batch, Ma.Ogden(3.0, 1000.0, 5000.0))],
+    ids=["asquad-nh", "asquad-hooke-gl", "asquad-hooke-small", "asquad-mr", "astria-nh", "astria-mr", "asquad-ogden"])
+def test_cas_parity(ctor, mat):
+    b, u, _ = _cas_case(ctor, (11, 9), mat, seed=51)
+    plan = El.Plan(b, u.shape[1], 2)
+    got = plan.makeϕrKt(u)
+    tol = 1e-11 if type(mat).__name__ == "Ogden" else K.TOL   # Ogden: two formulations
+    K.assert_parity(got, K.oracle_eval(b, u), tol=tol)
+    Kd = got[2].to_scipy()
+    assert abs(Kd - Kd.T).max() == 0.0
+    phi2, r2 = plan.makeϕr(u)
+    assert phi2 == got[0] and np.array_equal(r2, got[1])
+    again = plan.makeϕrKt(u)
+    assert again[0] == got[0] and np.array_equal(again[1], got[1]) and np.array_equal(again[2].nzval, got[2].nzval)
+
+
+def test_cas_known_answers_and_errors():
+    """homogeneous expansion u_r = ε r, u_z = γ z: ϕ = ϕ(diag(1+ε, 1+γ, 1+ε)) · 2π∫r dA on the GPU; element objects built
+    with the reference's constructor names group into the same plan; unsupported combinations are rejected."""
+    mat = K.nh()
+    b, _, coords = _cas_case(El.ASQuad_batch, (6, 5), mat, seed=52)
+    eps, gam = 0.03, -0.02
+    u = np.asfortranarray(np.stack([eps * coords[:, 0], gam * coords[:, 1]]))
+    phi, r, Kt = El.Plan(b, len(coords), 2).makeϕrKt(u)
+    J = (1 + eps) ** 2 * (1 + gam)
+    I1 = 2 * (1 + eps) ** 2 + (1 + gam) ** 2
+    psi = mat.C1 * (I1 * J ** (-2.0 / 3.0) - 3) + mat.K * (J - 1) ** 2   # elasticmaterials.jl:186-197
+    assert abs(phi - psi * b.wgt.sum()) <= 1e-12 * abs(phi)
+    elems = [El.ASQuad(b.nodes[i], coords[b.nodes[i] - 1], mat=mat) for i in range(b.ne)]
+    assert all(type(e).__name__ == "CAS" for e in elems)
+    phi2, r2, Kt2 = El.Plan(elems, len(coords), 2).makeϕrKt(u)
+    assert phi2 == phi and np.array_equal(r2, r) and np.array_equal(Kt2.nzval, Kt.nzval)
+    with pytest.raises(capi.AD4SMError):   # a 2-D material on the 3x3 F of an axisymmetric element
+        El.Plan(El.ASQuad_batch(b.nodes, coords, Ma.Hooke2D(210000.0, 0.3)), len(coords), 2)
+    with pytest.raises(capi.AD4SMError):   # no post-processing for CAS
+        El.Plan(b, len(coords), 2).post(u, F=True)

@@ -52,14 +52,31 @@ def hex_mesh(n=(2, 2, 1), mat=NH, jitter=0.1, seed=0, ctor=E.Hex08):
     return elems, X0
 
 
-def quad_mesh(n=(3, 2), mat=None, jitter=0.1, seed=0, ctor=E.Quad):
+def quad_mesh(n=(3, 2), mat=None, jitter=0.1, seed=0, ctor=E.Quad, shift=None):
     mat = mat or M.Hooke2D(210000.0, 0.3, plane_stress=False)
     ids, X0 = _grid(n, 2, jitter, seed)
+    if shift is not None:   # axisymmetric meshes: away from the axis r = 0
+        X0 = X0 + np.asarray(shift)
     elems = []
     for j in range(n[1]):
         for i in range(n[0]):
             nd = np.array([ids[i, j], ids[i + 1, j], ids[i + 1, j + 1], ids[i, j + 1]]) + 1
             elems.append(ctor(nd, X0[nd - 1], mat))
+    return elems, X0
+
+
+def tri_mesh(n=(3, 2), mat=None, jitter=0.1, seed=0, ctor=E.Tria, shift=None):
+    """every quad of the grid split along its (0,2) diagonal into two counter-clockwise triangles"""
+    mat = mat or M.Hooke2D(210000.0, 0.3, plane_stress=False)
+    ids, X0 = _grid(n, 2, jitter, seed)
+    if shift is not None:
+        X0 = X0 + np.asarray(shift)
+    elems = []
+    for j in range(n[1]):
+        for i in range(n[0]):
+            q = np.array([ids[i, j], ids[i + 1, j], ids[i + 1, j + 1], ids[i, j + 1]]) + 1
+            for nd in (q[[0, 1, 2]], q[[0, 2, 3]]):
+                elems.append(ctor(nd, X0[nd - 1], mat))
     return elems, X0
 
 
@@ -93,7 +110,8 @@ class _Batch:
         self.nodes = np.stack([e.nodes for e in elems]).astype(np.int64)
         self.gradN = np.stack([e.gradN for e in elems])
         self.wgt = np.stack([e.wgt for e in elems])
-        self.Nval = np.stack([e.Nval for e in elems]) if e0.kind == "CP" else None
+        self.Nval = np.stack([e.Nval for e in elems]) if e0.kind != "CE" else None
+        self.X0 = np.stack([e.X0 for e in elems]) if e0.kind == "CAS" else None
 
 
 def _u(X0, dpn, amp=0.02, seed=5):
@@ -409,3 +427,73 @@ def test_cxx_oracle_reproduces_golden_vectors(path):
 
 def test_golden_vectors_exist():
     assert len(GOLDEN) >= 8, "run tests/golden/make_golden.py"
+
+
+# ---------------------------------------------------------------------------------------------------
+# 6. CAS (axisymmetric extension): the reference only has the constructors; the energy is pinned by
+#    closed forms and independent differentiation
+# ---------------------------------------------------------------------------------------------------
+def _cas_case(ctor=E.ASQuad, mat=NH, n=(3, 2), seed=41):
+    mesh_fn = quad_mesh if ctor is E.ASQuad else tri_mesh
+    return mesh_fn(n, mat, seed=seed, ctor=ctor, shift=(0.7, 0.0))
+
+
+@pytest.mark.parametrize("ctor", [E.ASQuad, E.ASTria], ids=["asquad", "astria"])
+@pytest.mark.parametrize("mat", [NH, MR, M.Hooke(210000.0, 0.3)], ids=["neohooke", "mooney", "hooke"])
+def test_cas_homogeneous_expansion_closed_form(ctor, mat):
+    """u_r = ε r, u_z = γ z  =>  F = diag(1+ε, 1+γ, 1+ε) everywhere (the hoop stretch equals the radial one), so
+    ϕ = ϕ(F) · Σ wgt exactly (both shape-function sets reproduce linear fields) and Σ wgt = 2π ∫ r dA."""
+    elems, X0 = _cas_case(ctor, mat)
+    eps, gam = 0.03, -0.02
+    u = np.asfortranarray(np.stack([eps * X0[:, 0], gam * X0[:, 1]]))
+    phi, r, _ = E.make_phi_r_Kt(elems, u)
+    F = np.diag([1 + eps, 1 + gam, 1 + eps]).astype(object)
+    V = sum(float(e.wgt.sum()) for e in elems)
+    assert abs(phi - M.getphi(F, mat) * V) <= 1e-12 * abs(phi)
+
+
+def test_cas_volume_of_revolution():
+    """wgt = detJ·2π·r (elasticelements.jl:249, 279): for a straight-sided quad mesh Σ wgt = 2π ∫ r dA is integrated exactly
+    by the 2x2 rule; compare with the shoelace/Pappus value of the mesh outline."""
+    elems, X0 = quad_mesh((3, 2), NH, jitter=0.0, seed=1, ctor=E.ASQuad, shift=(0.7, 0.0))
+    V = sum(float(e.wgt.sum()) for e in elems)
+    r0, r1, h = X0[:, 0].min(), X0[:, 0].max(), X0[:, 1].max() - X0[:, 1].min()
+    assert abs(V - np.pi * (r1 ** 2 - r0 ** 2) * h) <= 1e-13 * V
+
+
+@pytest.mark.parametrize("ctor", [E.ASQuad, E.ASTria], ids=["asquad", "astria"])
+def test_cas_axial_translation_and_central_differences(ctor):
+    """a rigid axial translation costs nothing (ϕ = 0, r = 0, Kt·t = 0 at any u); r and Kt are the derivatives of ϕ
+    (4th-order central differences), Kt symmetric."""
+    elems, X0 = _cas_case(ctor, NH)
+    nn = len(X0)
+    t = np.zeros((2, nn))
+    t[1] = 1.0
+    phi, r, _ = E.make_phi_r_Kt(elems, 0.37 * t)
+    assert abs(phi) <= 1e-12 and np.abs(r).max() <= 1e-9
+    u = _u(X0, 2, seed=43)
+    phi, r, csc = E.make_phi_r_Kt(elems, u)
+    Kd = _dense(csc, 2 * nn)
+    assert np.abs(Kd - Kd.T).max() == 0.0
+    assert np.abs(Kd @ t.reshape(-1, order="F")).max() <= 1e-9 * np.abs(Kd).max()
+    h = 1e-4
+    rng = np.random.default_rng(44)
+    for _ in range(3):
+        dvec = rng.uniform(-1, 1, u.shape)
+        f = lambda s: E.make_phi_r_Kt(elems, u + s * h * dvec)  # noqa: E731
+        (pm2, rm2, _), (pm1, rm1, _), (pp1, rp1, _), (pp2, rp2, _) = f(-2), f(-1), f(1), f(2)
+        dphi = (pm2 - 8 * pm1 + 8 * pp1 - pp2) / (12 * h)
+        assert abs(dphi - r @ dvec.reshape(-1, order="F")) <= 1e-9 * max(1.0, abs(dphi))
+        dr = (rm2 - 8 * rm1 + 8 * rp1 - rp2) / (12 * h)
+        assert np.abs(dr - Kd @ dvec.reshape(-1, order="F")).max() <= 1e-8 * np.abs(dr).max()
+
+
+def test_cas_python_and_cxx_restatements_agree():
+    for ctor, mat in ((E.ASQuad, NH), (E.ASQuad, M.Hooke(210000.0, 0.3, small=True)), (E.ASTria, MR)):
+        elems, X0 = _cas_case(ctor, mat, seed=45)
+        u = _u(X0, 2, seed=46)
+        phi, r, (cp, rv, nz) = E.make_phi_r_Kt(elems, u)
+        phi2, r2, (cp2, rv2, nz2) = X.make_phi_r_Kt([_Batch(elems)], u)
+        assert np.array_equal(cp, cp2) and np.array_equal(rv, rv2)
+        assert abs(phi - phi2) <= 1e-13 * abs(phi) and np.abs(r - r2).max() <= 1e-13 * np.abs(r).max()
+        assert np.abs(nz - nz2).max() <= 1e-13 * np.abs(nz).max()
