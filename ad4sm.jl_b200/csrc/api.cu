@@ -669,7 +669,11 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
       return fail(AD4SM_ENODEV, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     p->stream = p->own_stream;
-    if (cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // the copy stream also carries the interface exchange of ad4sm_dist_eval*, whose few CTAs must not queue behind the
+    // interior assembly running on the main stream: highest priority
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&p->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_r_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_copied, cudaEventDisableTiming) != cudaSuccess) {
       ad4sm_plan_destroy(p);

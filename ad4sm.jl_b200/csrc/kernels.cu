@@ -898,7 +898,10 @@ template <int D, int N> __global__ void __launch_bounds__(K1_THREADS) k1_d_kerne
 // ---- K1 dispatch ---------------------------------------------------------------------------------
 static bool lanes_for(int D, int N, int P, int& LP) {
   if ((D == 2 && N == 3) || (D == 3 && N == 4)) {
-    LP = (P == 1) ? 1 : 4;
+    // experiment knob: AD4SM_P1_PERSISTENT=1 runs one-Gauss-point simplices through the persistent 4-lanes-per-element
+    // kernel (TMA-staged inputs, asynchronous u gather) instead of the thread-per-element one
+    static const bool p1_persistent = getenv("AD4SM_P1_PERSISTENT") && atoi(getenv("AD4SM_P1_PERSISTENT")) != 0;
+    LP = (P == 1 && !p1_persistent) ? 1 : 4;
     return true;
   }
   if (D == 2 && N == 4) {

@@ -401,7 +401,9 @@ class DistPlan:
         split = phi.is_cuda and hasattr(self.b, "assemble_interior")   # (the CPU stand-in of the gloo tests has no streams)
         if self._allphi is None:
             self._allphi = torch.empty(self.part.world, dtype=phi.dtype, device=phi.device)
-            self._side = torch.cuda.Stream() if split else None
+            # high priority: the collective's few CTAs must not queue behind the thousands of CTAs of the interior
+            # assembly launched right after it on the main stream
+            self._side = torch.cuda.Stream(priority=-1) if split else None
 
         def exchange():
             if not peer:
