@@ -722,7 +722,8 @@ template <int D, int N> struct W1Layout {
   static constexpr int OS0 = KW + RW;
   static constexpr int OS = (OS0 % 2) ? OS0 + 1 : (((OS0 / 2) % 2) ? OS0 : OS0 + 2);  // even, OS/2 odd
   static constexpr int WARPS = 4;
-  static constexpr size_t BYTES = (size_t)WARPS * 32 * OS * sizeof(double);
+  static constexpr size_t ROWS_BYTES = (size_t)WARPS * 32 * OS * sizeof(double);
+  static constexpr size_t BYTES = ROWS_BYTES + (size_t)WARPS * 32 * NPB * sizeof(unsigned);  // + the warp's sorted positions
 };
 template <int D, int N, int MF, bool PF>
 __global__ void __launch_bounds__(128) k1_u_kernel_w1(const __grid_constant__ K1Args a) {
@@ -738,6 +739,18 @@ __global__ void __launch_bounds__(128) k1_u_kernel_w1(const __grid_constant__ K1
   double* row = ws + (size_t)lane * OS;
   const long long e = e0 + lane;
   const bool valid = lane < cnt;
+  // destination-sorted staging: the positions of the warp's cnt * NPB blocks (contiguous in cpos) start travelling into
+  // shared memory now (cp.async, no registers held), so that the store loop at the end does not wait on them
+  if (a.cpos && a.want_K) {
+    const unsigned* cp = a.cpos + (a.slot0 + e0) * (long long)NPB;
+    const unsigned dst = smem_u32(reinterpret_cast<unsigned char*>(smw) + L::ROWS_BYTES) + (unsigned)(warp * 32 * NPB * 4);
+#pragma unroll
+    for (int k = 0; k < NPB; k++) {
+      const int i = lane + 32 * k;
+      if (i < cnt * NPB) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * i), "l"(cp + i) : "memory");
+    }
+    cp_async_commit();
+  }
   if (valid) {
     int nd[N];
 #pragma unroll
@@ -777,11 +790,14 @@ __global__ void __launch_bounds__(128) k1_u_kernel_w1(const __grid_constant__ K1
   if (!a.want_K) return;
   if (a.cpos) {  // destination-sorted staging (D == 3): block b of element el -> C[cpos >> 1], 5 x 16 bytes
     if constexpr (D == 3) {
-      const unsigned* cp = a.cpos + slot_w * (long long)NPB;
+      cp_async_wait_all();
+      __syncwarp();
+      const unsigned* cps =
+          reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(smw) + L::ROWS_BYTES) + (size_t)warp * 32 * NPB;
       for (int c = lane; c < cnt * NPB * 5; c += 32) {
         const int eb = c / 5, t = c - eb * 5;  // eb = el * NPB + b
         const int el = eb / NPB, b = eb - el * NPB;
-        const unsigned code = __ldg(cp + eb);
+        const unsigned code = cps[eb];
         const double* src = ws + (size_t)el * OS + b * 9 + 2 * t;
         const double v0 = src[0];
         const double v1 = t < 4 ? src[1] : ((code & 1u) ? 1.0 : 0.0);  // 10th double: "stored transposed" (K2s flips it)
