@@ -179,7 +179,7 @@ class Workload:
             self.plan_opts = {"nh2d_extension": True}   # C4 as named needs the plane-strain embedding
             self.d = np.random.default_rng(seed + 3).uniform(0.0, 0.5, len(coords))
         self._host_ctor = lambda: ctor(conn, coords, m)
-        self._host_batch = None
+        self._host_batch = self._oracle_batch = None
         self.batch = ctor(conn, coords, m, device=True) if device_ctor else self.host_batch
         if self.shape == "quadp":
             self.hist = np.zeros((self.batch.ne, self.batch.P, 2))
@@ -195,10 +195,23 @@ class Workload:
             self._host_batch = self._host_ctor()
         return self._host_batch
 
+    @property
+    def oracle_batch(self):
+        """The element arrays the oracle evaluates: EXACTLY the ∇N / wgt / N the product's plan holds.  With device
+        constructors that is the device-built arrays read back (`materialize`), not the host constructors' -- the two differ
+        by the conditioning of J (coordinates O(1), differences O(h): 1e-16 / h relative, 2e-14 at h = 1/200), which is a
+        property of the constructors (tests/test_gpu_construct.py), not of makeϕrKt."""
+        from ad4sm_b200 import Elements as El
+        if isinstance(self.batch, El.MeshBatch):
+            if self._oracle_batch is None:
+                self._oracle_batch = self.batch.materialize()
+            return self._oracle_batch
+        return self.batch
+
     def oracle(self, nthreads=0):
         """the reference-algorithm restatement on this workload: list of (ϕ, r, (colptr, rowval, nzval)) and seconds"""
         from oracle import cxx_binding as X
-        hb = self.host_batch
+        hb = self.oracle_batch
         t0 = time.perf_counter()
         if self.shape == "quadp":
             kw = dict(nh2d_extension=True)
@@ -665,10 +678,10 @@ def bench_newton(plan, w, u_np, timed, ne_total, torch):
     from ad4sm_b200 import _capi as capi
     L = capi.lib()
     nn = w.n_nodes
-    npl = (w.dims[0] + 1) * (w.dims[1] + 1)
+    npl = int(np.prod([k + 1 for k in w.dims[:w.D - 1]]))   # nodes of one plane (3-D) / one row (2-D)
     bfree = np.ones((w.D, nn), dtype=np.uint8, order="F")
-    bfree[:, :npl] = 0            # bottom plane (nodes are numbered x-fastest, z-slowest): clamped
-    bfree[2, nn - npl:] = 0       # top plane: driven in z
+    bfree[:, :npl] = 0               # bottom plane / row (nodes are numbered x-fastest, last direction slowest): clamped
+    bfree[w.D - 1, nn - npl:] = 0    # top plane / row: driven in the last direction
     t0 = time.perf_counter()
     nfree, ncnst, nnz_ff = plan.newton_setup(bfree)
     plan.newton_pattern()
