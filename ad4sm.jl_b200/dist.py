@@ -364,6 +364,30 @@ class DistPlan:
         self._tok = None
         self._allphi = self._side = None
 
+    def _prof_events(self):
+        """developer tool (AD4SM_DIST_PROF=1): CUDA events after K1 / after the exchange (side stream) / after the interior
+        assembly / at the end of every step; `prof_report()` averages the intervals"""
+        import os
+        import torch
+        if not os.environ.get("AD4SM_DIST_PROF"):
+            return None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        self._prof_log = getattr(self, "_prof_log", [])
+        self._prof_log.append(ev)
+        return ev
+
+    def prof_report(self, skip=5):
+        import torch
+        torch.cuda.synchronize()
+        log = getattr(self, "_prof_log", [])[skip:]
+        if not log:
+            return None
+        n = len(log)
+        return {"steps": n, "k1_end_to_exchange_done_ms": sum(e[0].elapsed_time(e[1]) for e in log) / n,
+                "k1_end_to_interior_done_ms": sum(e[0].elapsed_time(e[2]) for e in log) / n,
+                "k1_end_to_step_end_ms": sum(e[0].elapsed_time(e[3]) for e in log) / n,
+                "cpu_enqueue_ms_per_step": 1e3 * sum(self._prof_cpu[skip:]) / max(1, len(self._prof_cpu[skip:]))}
+
     def step_host(self, u_host, r_host, d_host=None):
         """One evaluation with host-resident u (in) and r (out, this rank's local dofs): the upload overlaps K1, the
         download of r overlaps the Kt assembly.  Returns the global ϕ as a 0-d tensor; r_host is valid after
@@ -377,8 +401,10 @@ class DistPlan:
         interface exchange (send/recv, or the barrier that follows the copy-engine pushes) and the all-gather of the
         per-rank ϕ -- which doubles as that barrier -- run on a side stream while the main stream assembles the interior
         rows and pairs (`ad4sm_eval_assemble_split_device`); only the interface part of the assembly waits for them."""
+        import time
         import torch
         import torch.distributed as D
+        t_cpu0 = time.perf_counter()
         if hasattr(self.b, "bind_current_stream"):
             self.b.bind_current_stream()   # no-op unless the caller switched torch streams since the last step
         peer = getattr(self.b, "peer", False)
@@ -414,14 +440,25 @@ class DistPlan:
 
         if split:
             main = torch.cuda.current_stream()
+            prof = self._prof_events()
+            if prof:
+                prof[0].record(main)
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 exchange()
+                if prof:
+                    prof[1].record(self._side)
             self.b.assemble_interior()
+            if prof:
+                prof[2].record(main)
             main.wait_stream(self._side)
         else:
             exchange()
         self.b.assemble()
+        if split and prof:
+            prof[3].record(main)
+            self._prof_cpu = getattr(self, "_prof_cpu", [])
+            self._prof_cpu.append(time.perf_counter() - t_cpu0)
         if host is not None:
             self.b.fetch_r_async(host[1])
         return self._allphi.sum()   # one fixed reduction over `world` values: run-to-run reproducible

@@ -467,6 +467,8 @@ def run_ours(args):
         e1.record(stream)
         barrier()
         ms_total = e0.elapsed_time(e1)
+        if runner is not None and getattr(runner, "dplan", None) is not None and os.environ.get("AD4SM_DIST_PROF"):
+            print(f"DISTPROF rank {rank}: {runner.dplan.prof_report(skip=max(args.warmup, 3) + 1)}", file=sys.stderr)   # developer tool
         prof_ms, prof_n = plan.profile_read()
         plan.profile_enable(False)
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
