@@ -309,4 +309,58 @@ function newton_reduce(elems, u, bfree, kind; fe=nothing, Δucnst=nothing)
   (res, SparseMatrixCSC{Float64,Int64}(s.nfree, s.nfree, copy(s.colptr), copy(s.rowval), nz), norms[1], norms[2])
 end
 
+# ---- mesh-partitioned evaluation, one Julia process per GPU (ad4sm_dist_*: NCCL inside the library) ----------------------
+# The reference has no multi-device path.  Every rank holds its own elements `own` (LOCAL node ids) and the connectivity
+# `halo_nodes` (N x nHalo, local ids) of the foreign elements that touch nodes it owns; `peers` lists, per neighbour, the
+# own slots (0-based) whose staged rows that neighbour needs and the range of HALO slots it fills (see
+# include/ad4sm_b200.h: ad4sm_dist_peer; ad4sm.jl_b200/dist.py: build_partition computes exactly these from a global
+# connectivity and an element -> rank map).  `bcast(bytes_or_nothing)` must hand rank 0's 128-byte NCCL id to every rank
+# (MPI.bcast, a shared file, Distributed.remotecall_fetch, ...).
+struct DistPeer                    # struct ad4sm_dist_peer
+  rank::Int32; n_send::Int64; send_slots::Ptr{Int64}; recv_first_slot::Int64; n_recv::Int64
+end
+mutable struct DistPlan
+  plan::Plan
+  comm::Ptr{Cvoid}
+  keep::Vector{Any}
+end
+function dist_plan(own::AbstractVector{<:AbstractCElem}, halo_nodes::Matrix{Int64}, own_index::Vector{Int64}, halo_index::Vector{Int64},
+                   n_local_nodes::Int, dofs_per_node::Int, nranks::Int, rank::Int, device::Int,
+                   peers::Vector{Tuple{Int,Vector{Int64},Int,Int}}, bcast)
+  packed = pack(own, collect(1:length(own)))
+  oi = copy(own_index)                                 # global positions in `elems`: fixes the summation order across ranks
+  b  = packed.batch
+  ob = Batch(b.elem_kind, b.dim, b.n_gauss, b.n_elem_nodes, b.mat_kind, b.mat_base, b.mat_flags, 0, b.mat_params, b.n_elems,
+             b.nodes, b.gradN, b.wgt, b.Nval, pointer(oi), C_NULL)
+  hb = Batch(b.elem_kind, b.dim, b.n_gauss, b.n_elem_nodes, b.mat_kind, b.mat_base, b.mat_flags, 1 #= AD4SM_BATCH_HALO =#, b.mat_params,
+             size(halo_nodes, 2), pointer(halo_nodes), C_NULL, C_NULL, C_NULL, pointer(halo_index), C_NULL)
+  batches = size(halo_nodes, 2) > 0 ? [ob, hb] : [ob]
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve packed oi halo_nodes halo_index batches begin
+    check(ccall((:ad4sm_plan_create, lib), Cint, (Ptr{Batch}, Int32, Int64, Int32, Int32, Ref{Ptr{Cvoid}}),
+                batches, length(batches), n_local_nodes, dofs_per_node, device, h))
+  end
+  plan = Plan(h[], length(own), (dofs_per_node, n_local_nodes), [collect(1:length(own))], [Int(b.n_gauss)])
+  finalizer(destroy!, plan)
+  id = Vector{UInt8}(undef, 128)
+  rank == 0 && check(ccall((:ad4sm_dist_unique_id, lib), Cint, (Ptr{UInt8},), id))
+  id = bcast(rank == 0 ? id : nothing)
+  comm = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ad4sm_dist_init, lib), Cint, (Int32, Int32, Ptr{UInt8}, Int32, Ref{Ptr{Cvoid}}), nranks, rank, id, device, comm))
+  n_own = length(own)
+  dp = [DistPeer(pr, length(send), pointer(send), n_own + first, cnt) for (pr, send, first, cnt) in peers]
+  GC.@preserve peers dp check(ccall((:ad4sm_dist_attach, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{DistPeer}), plan.h, comm[], length(dp), dp))
+  DistPlan(plan, comm[], Any[packed, oi, halo_nodes, halo_index, peers])
+end
+"""One partitioned evaluation: `u` is this rank's D x nLocalNodes block.  Returns the GLOBAL ϕ and this rank's r; the rows
+of Kt this rank owns stay on the device (`fetch(dp.plan, ...)` / `newton_reduce` read them) and are bitwise those of a
+single-GPU evaluation of the whole mesh."""
+function dist_makeϕrKt(dp::DistPlan, u::Matrix{Float64})
+  ϕ = Ref(0.0); r = Vector{Float64}(undef, length(u))
+  check(ccall((:ad4sm_dist_eval, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
+              dp.plan.h, 0, u, C_NULL, ϕ, r))
+  (ϕ[], r)
+end
+dist_close!(dp::DistPlan) = (dp.comm != C_NULL && ccall((:ad4sm_dist_destroy, lib), Cvoid, (Ptr{Cvoid},), dp.comm); dp.comm = C_NULL; nothing)
+
 end # module
