@@ -45,6 +45,7 @@ BATCH_HALO = 1
 OPT_SORTED, OPT_PEER_PUSH = 3, 4
 INFO_SORTED = 3
 INFO_SPLIT_PAIRS = 4
+INFO_DIST_TRANSPORT = 5
 
 
 class StagingView(C.Structure):

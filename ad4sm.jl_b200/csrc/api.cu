@@ -147,6 +147,7 @@ struct ad4sm_plan {
   };
   ad4sm_dist* dcomm = nullptr;
   std::vector<DistPeer> dpeers;
+  std::vector<cudaEvent_t> dprof;  // developer tool (AD4SM_DIST_PROF): 4 timing events per partitioned evaluation
   int* xmap = nullptr;
   double *xke = nullptr, *xre = nullptr, *allphi = nullptr, *phi_local = nullptr;
   long long n_export = 0;
@@ -439,6 +440,20 @@ void ad4sm_plan_destroy(ad4sm_plan* p) {
   if (p->ev_r_ready) cudaEventDestroy(p->ev_r_ready);
   if (p->ev_copied) cudaEventDestroy(p->ev_copied);
   if (p->ev_start) cudaEventDestroy(p->ev_start);
+  if (!p->dprof.empty()) {  // AD4SM_DIST_PROF: average intervals from the end of the element stage, last half of the evaluations
+    cudaDeviceSynchronize();
+    const size_t n = p->dprof.size() / 4, k0 = n / 2;
+    double a[3] = {0, 0, 0};
+    for (size_t k = k0; k < n; k++)
+      for (int j = 0; j < 3; j++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p->dprof[4 * k], p->dprof[4 * k + 1 + j]);
+        a[j] += ms;
+      }
+    fprintf(stderr, "DISTPROF(lib) %zu evaluations: element stage end -> exchange done %.4f ms, -> interior done %.4f ms, -> step end %.4f ms\n",
+            n - k0, a[0] / (n - k0), a[1] / (n - k0), a[2] / (n - k0));
+    for (cudaEvent_t e : p->dprof) cudaEventDestroy(e);
+  }
   if (p->ev_exports) cudaEventDestroy(p->ev_exports);
   if (p->ev_pushed) cudaEventDestroy(p->ev_pushed);
   for (cudaEvent_t e : p->ev_h2d)
@@ -673,6 +688,8 @@ int ad4sm_plan_create(const ad4sm_batch* batches, int32_t n_batches, int64_t n_n
     // interior assembly running on the main stream: highest priority
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char* e = getenv("AD4SM_COPY_PRIO"))  // experiment knob: 0 = default priority
+      if (atoi(e) == 0) prio_hi = 0;
     if (cudaStreamCreateWithPriority(&p->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_r_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_copied, cudaEventDisableTiming) != cudaSuccess) {
@@ -1122,7 +1139,7 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
         for (int x = 0; x < p->n_xr; x++) a.xr[x] = p->xr[x];
       }
     }
-    if (p->xmap && sorted && !internal && b.k.slot0 == 0) {
+    if (p->xmap && sorted && !internal && b.k.slot0 == 0 && !p->push_mode) {  // (push transport: the linked ranges above are what leaves)
       a.xmap = p->xmap;
       a.xke = p->xke;
       a.xre = p->xre;
@@ -1319,6 +1336,7 @@ int ad4sm_get_info(ad4sm_plan* p, int32_t what, int64_t* value) {
   if (!p || !value) return fail(AD4SM_EINVAL, "plan or value is NULL");
   switch (what) {
     case AD4SM_INFO_SORTED: *value = p->sorted_built ? (p->sorted_on ? 2 : 1) : 0; return AD4SM_OK;
+    case AD4SM_INFO_DIST_TRANSPORT: *value = p->dcomm ? (p->push_mode ? 2 : 1) : 0; return AD4SM_OK;
     case AD4SM_INFO_SPLIT_PAIRS: *value = (p->sorted_built && p->n_own_sorted < p->ne) ? p->split_pair : 0; return AD4SM_OK;
   }
   return fail(AD4SM_EINVAL, "unknown info id");
@@ -1883,6 +1901,107 @@ void ad4sm_dist_destroy(ad4sm_dist* comm) {
   delete comm;
 }
 
+// Copy-engine push transport for the in-library partitioned evaluation: when EVERY rank's send lists are contiguous slot
+// ranges (z-slabs and other contiguous partitions), the plans are destination-sorted, and CUDA IPC works between the ranks,
+// the interface rows travel like in dist.py's default transport -- K1 evaluates them first, the copy engine pushes them into
+// the owner's double-buffered HALO rows over NVLink while the rest of K1 runs -- and ncclSend/ncclRecv (a few channels per
+// peer: ~0.14 ms per 28 MB interface, measured) is not used at all; the ϕ all-gather is the barrier.  Collective: every
+// rank all-gathers (IPC handles, n_own, n_slots, its receive ranges, "I can push") and all take the same decision.
+// AD4SM_DIST_PUSH=0 keeps the send/recv exchange.
+static int dist_try_push(ad4sm_plan* p, ad4sm_dist* comm, int n_peers, const ad4sm_dist_peer* peers) {
+  const int nranks = dist_comm_size(comm->c), me = dist_comm_rank(comm->c);
+  constexpr int REC = 32;  // 8-byte words per rank: [0,16) handles, 16 n_own, 17 n_slots, 18 can_push, 19 n_entries, 20.. (rank, first, count) x 4
+  const char* env = getenv("AD4SM_DIST_PUSH");
+  bool can = !(env && atoi(env) == 0) && p->sorted_built && p->n_own_batches == 1 && n_peers <= AD4SM_MAX_PEER_LINKS;
+  for (const ad4sm_plan::DistPeer& d : p->dpeers)
+    if (d.n_send && d.first_s < 0) can = false;
+  std::vector<long long> mine(REC, 0), all((size_t)REC * nranks, 0);
+  if (can) {
+    cudaIpcMemHandle_t h[2];
+    if (cudaIpcGetMemHandle(&h[0], p->Ke) != cudaSuccess || cudaIpcGetMemHandle(&h[1], p->re) != cudaSuccess) {
+      cudaGetLastError();
+      can = false;
+    } else {
+      memcpy(mine.data(), h, sizeof(h));
+    }
+  }
+  mine[16] = p->batches[0].k.ne;
+  mine[17] = p->ne;
+  mine[18] = can ? 1 : 0;
+  int ne_ = 0;
+  for (int i = 0; i < n_peers && ne_ < 4; i++)
+    if (peers[i].n_recv > 0) {
+      mine[20 + 3 * ne_] = peers[i].rank;
+      mine[21 + 3 * ne_] = peers[i].recv_first_slot;
+      mine[22 + 3 * ne_] = peers[i].n_recv;
+      ne_++;
+    }
+  mine[19] = ne_;
+  double *d_mine = nullptr, *d_all = nullptr;
+  std::string err;
+  auto gather = [&]() -> int {  // all ranks' records (a tiny collective on the plan's stream)
+    if (!d_mine) {
+      CK(cudaMalloc(&d_mine, REC * 8));
+      CK(cudaMalloc(&d_all, (size_t)REC * 8 * nranks));
+    }
+    CK(cudaMemcpyAsync(d_mine, mine.data(), REC * 8, cudaMemcpyHostToDevice, p->stream));
+    if (dist_allgather(comm->c, d_mine, d_all, REC, p->stream, &err)) return fail(AD4SM_ENCCL, err);
+    CK(cudaMemcpyAsync(all.data(), d_all, (size_t)REC * 8 * nranks, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+  };
+  auto done = [&](int rc) {
+    cudaFree(d_mine);
+    cudaFree(d_all);
+    return rc;
+  };
+  int rc = gather();
+  if (rc) return done(rc);
+  bool everyone = true;
+  for (int g = 0; g < nranks; g++) everyone = everyone && all[(size_t)REC * g + 18] != 0;
+  if (!everyone) return done(AD4SM_OK);  // send/recv exchange
+  // links: my contiguous send ranges -> the receive ranges the owners announced for me
+  ad4sm_peer_link links[AD4SM_MAX_PEER_LINKS];
+  int nl = 0;
+  bool ok = true;
+  for (const ad4sm_plan::DistPeer& d : p->dpeers) {
+    if (!d.n_send) continue;
+    const long long* R = all.data() + (size_t)REC * d.rank;
+    long long first = -1;
+    for (int k = 0; k < (int)R[19]; k++)
+      if (R[20 + 3 * k] == me && R[22 + 3 * k] == d.n_send) first = R[21 + 3 * k];
+    if (first < 0) {
+      ok = false;
+      break;
+    }
+    links[nl].first_slot = d.first_s;
+    links[nl].count = d.n_send;
+    links[nl].remote_first_slot = first;
+    links[nl].peer_handles = R;  // the first 128 bytes of the record
+    links[nl].remote_first_slot_b = R[17] + (first - R[16]);
+    nl++;
+  }
+  if (ok) {
+    p->push_opt = true;
+    ok = ad4sm_peer_attach(p, nl, links) == AD4SM_OK;
+  }
+  // second round: did every rank attach?  otherwise all fall back together
+  mine[18] = ok ? 1 : 0;
+  rc = gather();
+  if (rc) return done(rc);
+  everyone = true;
+  for (int g = 0; g < nranks; g++) everyone = everyone && all[(size_t)REC * g + 18] != 0;
+  if (!everyone) {
+    p->push_opt = false;
+    ad4sm_peer_attach(p, 0, nullptr);
+    p->dist_aware = true;
+    p->n_xr = 0;
+    p->n_xr_local = 0;
+    p->push_mode = false;
+  }
+  return done(AD4SM_OK);
+}
+
 int ad4sm_dist_attach(ad4sm_plan* p, ad4sm_dist* comm, int32_t n_peers, const ad4sm_dist_peer* peers) {
   if (!p || !comm) return fail(AD4SM_EINVAL, "plan or comm is NULL");
   if (n_peers < 0 || (n_peers && !peers)) return fail(AD4SM_EINVAL, "bad peer list");
@@ -1951,14 +2070,21 @@ int ad4sm_dist_attach(ad4sm_plan* p, ad4sm_dist* comm, int32_t n_peers, const ad
   p->n_xr = 0;
   p->n_xr_local = 0;
   p->push_mode = false;
-  return AD4SM_OK;
+  return dist_try_push(p, comm, n_peers, peers);
 }
 
 // element stage -> grouped neighbour exchange -> assembly -> ϕ all-gather + rank-ordered sum, all on the plan's stream
 static int dist_eval_stages(ad4sm_plan* p, int32_t mode, const double* u_dev, const double* d_dev, double* hist_dev) {
   if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
   if (!p->dcomm) return fail(AD4SM_ESTATE, "ad4sm_dist_eval before ad4sm_dist_attach");
+  // the push transport serves the Kt evaluations on the sorted path (modes 0, 1); ϕ,r-only and d-phase evaluations of the
+  // same plan take the send/recv exchange of the element-major rows
+  const bool pushable = mode == MODE_ELASTIC || mode == MODE_PF_U;
+  const bool push_saved = p->push_mode;
+  if (!pushable) p->push_mode = false;
   int rc = eval_elements_impl(p, mode, u_dev, d_dev, hist_dev, false);
+  const bool pushed = p->push_mode && p->push_pending;
+  p->push_mode = push_saved;
   if (rc) return rc;
   const int DB = mode == MODE_PF_D ? 1 : p->D;
   const long long kw = (long long)n_pair_blocks(p->N) * DB * DB, rw = (long long)p->N * DB;
@@ -1967,6 +2093,7 @@ static int dist_eval_stages(ad4sm_plan* p, int32_t mode, const double* u_dev, co
   cudaStream_t s = p->stream;
   std::vector<DistXfer> xf;
   for (ad4sm_plan::DistPeer& d : p->dpeers) {
+    if (pushed) break;  // the copy engine has pushed the interface rows during K1 (dist_try_push)
     if (d.n_send) {
       const double* kbase = from_x ? p->xke : p->Ke;
       const double* rbase = from_x ? p->xre : p->re;
@@ -2005,13 +2132,25 @@ static int dist_eval_stages(ad4sm_plan* p, int32_t mode, const double* u_dev, co
   if (!xf.empty() && dist_exchange(p->dcomm->c, (int)xf.size(), xf.data(), xs, &err)) return fail(AD4SM_ENCCL, err);
   if (dist_allgather(p->dcomm->c, p->phi_local, p->allphi, 1, xs, &err)) return fail(AD4SM_ENCCL, err);
   CK(cudaEventRecord(p->ev_pushed, xs));
+  static const bool dprof = getenv("AD4SM_DIST_PROF") != nullptr;
+  cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (dprof && p->dprof.size() < 4 * 4096) {
+    for (int k = 0; k < 4; k++) {
+      CK(cudaEventCreate(&pe[k]));
+      p->dprof.push_back(pe[k]);
+    }
+    CK(cudaEventRecord(pe[0], s));   // (after the element stage and the enqueue of the exchange)
+    CK(cudaEventRecord(pe[1], xs));  // exchange + all-gather complete
+  }
   rc = ad4sm_eval_assemble_split_device(p, mode);
   if (rc) return rc;
+  if (pe[2]) CK(cudaEventRecord(pe[2], s));  // interior assembled
   CK(cudaStreamWaitEvent(s, p->ev_pushed, 0));
   rc = ad4sm_eval_assemble_device(p, mode);
   if (rc) return rc;
   // ϕ: the partials of all ranks, summed in rank order, into phi_dev (the global ϕ)
   CK(launch_phi_rank_sum(p->allphi, nranks, p->phi_dev, s));
+  if (pe[3]) CK(cudaEventRecord(pe[3], s));
   return AD4SM_OK;
 }
 

@@ -317,7 +317,11 @@ int ad4sm_export_ranges(ad4sm_plan* plan, int32_t n_ranges, const int64_t* first
  * are packed by a gather kernel) and the range of this rank's HALO slots that neighbour fills.  ad4sm_dist_eval* then runs
  * element stage -> grouped ncclSend/ncclRecv of the staged rows on the plan's stream -> assembly -> ncclAllGather of the
  * per-rank ϕ, summed in rank order (run-to-run reproducible).  Owned rows of Kt and r are bitwise those of a single-GPU
- * evaluation of the whole mesh.  libnccl.so.2 is bound at run time (dlopen; AD4SM_NCCL_LIB overrides the name). */
+ * evaluation of the whole mesh.  libnccl.so.2 is bound at run time (dlopen; AD4SM_NCCL_LIB overrides the name).
+ * The exchange and the ϕ all-gather run on a side stream while the interior of the assembly (ad4sm_eval_assemble_split_device)
+ * proceeds.  When every rank's send lists are contiguous slot ranges (z-slabs etc.) and CUDA IPC works between the ranks,
+ * ad4sm_dist_attach -- a collective call -- sets up the copy-engine push transport of ad4sm_peer_attach by itself
+ * (IPC handles and receive ranges all-gathered over NCCL) and ncclSend/ncclRecv is not used; AD4SM_DIST_PUSH=0 disables it. */
 #define AD4SM_NCCL_ID_BYTES 128
 typedef struct ad4sm_dist ad4sm_dist;
 typedef struct ad4sm_dist_peer {
@@ -353,6 +357,7 @@ int ad4sm_sync(ad4sm_plan* plan);
 #define AD4SM_OPT_PEER_PUSH 4    /* 1: ad4sm_peer_attach sets up copy-engine pushes instead of K1 peer stores (see there) */
 #define AD4SM_INFO_SORTED 3       /* 0 = not available for this plan, 1 = available but off, 2 = on */
 #define AD4SM_INFO_SPLIT_PAIRS 4  /* node pairs ad4sm_eval_assemble_split_device assembles ahead of the exchange (0: none) */
+#define AD4SM_INFO_DIST_TRANSPORT 5 /* after ad4sm_dist_attach: 1 = ncclSend/ncclRecv of the staged rows, 2 = copy-engine push (CUDA IPC); 0 = not attached */
 int ad4sm_set_option(ad4sm_plan* plan, int32_t option, int64_t value);
 int ad4sm_get_info(ad4sm_plan* plan, int32_t what, int64_t* value);
 

@@ -114,6 +114,9 @@ def _lib_worker(rank, world, port, out):
             own = El.ElemBatch("CE", 3, p.local_conn(conn[p.own_elems]), b.gradN[p.own_elems], b.wgt[p.own_elems], b.mat)
             lp = AD.LibDistPlan(own, p.local_conn(conn[p.halo_elems]), p, 3, AD.torch_share_id, device=rank)
             assert lp.plan.info(capi.INFO_SORTED) == 2
+            # slabs: contiguous interface ranges -> the copy-engine push transport set up inside ad4sm_dist_attach;
+            # checkerboard: general partition -> packed ncclSend/ncclRecv
+            assert lp.plan.info(capi.INFO_DIST_TRANSPORT) == (2 if name == "slab" else 1)
             ul = np.asfortranarray(u[:, p.local_nodes - 1])
             r_host = np.empty(ul.size)
             for f in (0.5, 1.0):                       # host entry point: u in, global ϕ and local r out
@@ -126,6 +129,13 @@ def _lib_worker(rank, world, port, out):
             lp.plan.sync()
             Kt2 = lp.plan.fetch_csc()
             assert np.array_equal(Kt.nzval, Kt2.nzval)
+            # ϕ, r only (makeϕr) through the same plan: not a push evaluation -> send/recv of the element-major rows
+            capi.check(capi.lib().ad4sm_dist_eval_device(lp.plan._h, capi.MODE_PHI_R, ud.data_ptr(), None, None))
+            lp.plan.sync()
+            v = lp.plan.device_view()
+            r3 = AD._wrap(torch, v.r_dev, (v.n_dof,)).cpu().numpy()
+            own3 = np.repeat(p.owned, 3)
+            assert np.array_equal(r3[own3], r_host[own3])
             res[name] = (phi, r_host.copy(), Kt, p)
             lp.close()
         np.savez(os.path.join(out, f"lib{rank}.npz"),
