@@ -966,10 +966,15 @@ bool k1_config(int D, int N, int P, bool pf, long long ne, K1Config* c) {
     const int w = atoi(e);
     if (w >= 1 && w < warps) warps = w;
   }
+  // 2-D shapes need 140-190 registers and a few KB of shared memory per warp: two CTAs of 6 warps per SM (12 warps) instead
+  // of one of 8 hide more of their latencies (the 3-D kernels fill the register file with 8 warps).  AD4SM_K1_CTAS overrides.
+  int ctas = (D == 2) ? 2 : 1;
+  if (const char* e = getenv("AD4SM_K1_CTAS")) ctas = atoi(e) >= 1 ? atoi(e) : ctas;
+  if (ctas > 1 && warps > 6) warps = 6;
   const long long n_groups = (ne + c->EW - 1) / c->EW;
   if (n_groups < warps) warps = (int)(n_groups > 0 ? n_groups : 1);
   long long grid = (n_groups + warps - 1) / warps;
-  if (grid > sm_count()) grid = sm_count();  // persistent: one CTA per SM, each warp strides over the element groups
+  if (grid > (long long)ctas * sm_count()) grid = (long long)ctas * sm_count();  // persistent: each warp strides over the element groups
   if (grid < 1) grid = 1;
   c->warps = warps;
   c->grid = (int)grid;
