@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(128) k1_u_kernel_w1(const __grid_constant__ K1
 
 // ---- K1, d-dual (makeϕrKt_d) -----------------------------------------------------------------------
 template <int D, int N, int LP>
-__global__ void __launch_bounds__(K1_THREADS, 2) k1_d_kernel(const K1Args a, const SmemLayout L) {
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_d_kernel(const K1Args a, const SmemLayout L) {
   constexpr int EPC = K1_THREADS / LP;
   extern __shared__ __align__(16) double sm[];
   const int el = threadIdx.x / LP, q = threadIdx.x % LP;
