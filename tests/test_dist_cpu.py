@@ -75,15 +75,11 @@ def _worker(rank, world, port, out):
         b, conn, u = _mesh()
         part = AD.build_partition(conn, AD.contiguous_elem_ranks(len(conn), world), rank, world)
         be = OracleBackend(b, conn, part, u)
-        be.eval_elements()
-        AD.exchange_staging(part, be.n_own, be.staging())
-        be.assemble()
-        phi = be.phi_tensor()
-        allphi = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
-        dist.all_gather(allphi, phi)
+        # the product's step logic (element stage -> exchange + ϕ all-gather -> assembly) with the oracle as kernel stand-in
+        phi_total = float(AD.DistPlan(be, part).step())
         phi_r, r, (cp, rv, nz) = be.result
         np.savez(os.path.join(out, f"rank{rank}.npz"), r=r, cp=cp, rv=rv, nz=nz, local_nodes=part.local_nodes, owned=part.owned,
-                 phi=sum(float(x) for x in allphi), n_halo=len(part.halo_elems),
+                 phi=phi_total, n_halo=len(part.halo_elems),
                  n_send=sum(len(v) for v in part.send.values()))
     finally:
         dist.destroy_process_group()
