@@ -869,6 +869,11 @@ class Plan:
         slot contributes to; may run while the interface rows are still in flight.  `eval_assemble_device` then finishes."""
         capi.check(self._L.ad4sm_eval_assemble_split_device(self._h, mode))
 
+    def eval_halo_prepare_device(self, mode, cuda_stream):
+        """Behind the interface exchange, on its stream: HALO rows into the sorted staging + the interface rows of r
+        (ad4sm_eval_halo_prepare_device), overlapping the interior assembly on the plan's stream."""
+        capi.check(self._L.ad4sm_eval_halo_prepare_device(self._h, mode, C.c_void_p(cuda_stream)))
+
     def staging_view(self, field=capi.FIELD_U):
         v = capi.StagingView()
         capi.check(self._L.ad4sm_staging_view_get(self._h, field, C.byref(v)))

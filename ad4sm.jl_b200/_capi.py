@@ -120,6 +120,7 @@ SIGNATURES = {
     "ad4sm_fetch_phi_r_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ad4sm_eval_assemble_device": (C.c_int, [C.c_void_p, C.c_int32]),
     "ad4sm_eval_assemble_split_device": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ad4sm_eval_halo_prepare_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "ad4sm_staging_view_get": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(StagingView)]),
     "ad4sm_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ad4sm_peer_attach": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(PeerLink)]),

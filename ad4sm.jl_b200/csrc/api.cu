@@ -131,6 +131,7 @@ struct ad4sm_plan {
   // [0, split_pair) -- receive no HALO contribution and can be assembled before the interface exchange has completed
   long long split_node = 0, split_pair = 0;
   int split_done = 0;          // 1: the interior part of the pending evaluation has been assembled
+  bool halo_prepared = false;  // the HALO scatter and the interface rows of r have been done on the exchange stream
   int n_own_batches = 0;       // evaluated (non-HALO) batches; the partitioned-run features (export ranges, peer links) know one
   bool dist_aware = false;     // the caller declared its export ranges / peer links (ad4sm_peer_attach / ad4sm_export_ranges)
   // peer staging / export ranges
@@ -1227,6 +1228,7 @@ static int eval_elements_impl(ad4sm_plan* p, int32_t mode, const double* u_dev, 
   }
   p->elements_mode = mode;
   p->split_done = 0;
+  p->halo_prepared = false;
   return AD4SM_OK;
 }
 
@@ -1264,11 +1266,12 @@ static int assemble_impl(ad4sm_plan* p, int32_t mode, int part) {
     a.pair0 = p->split_pair;
     a.keep_zero_count = 1;
   }
-  CK(launch_k3(a, p->stream));
+  const bool prepared = rest && p->halo_prepared;  // ad4sm_eval_halo_prepare_device ran behind the exchange
+  if (!prepared) CK(launch_k3(a, p->stream));
   CK(cudaEventRecord(p->ev_r_ready, p->stream));
   if (want_K) {
     if (p->sorted_last) {
-      if (p->n_own_sorted < p->ne) {
+      if (p->n_own_sorted < p->ne && !prepared) {
         const long long kw = (long long)n_pair_blocks(p->N) * p->D * p->D;
         const double* rows = p->Ke + ((p->push_pending && p->parity) ? p->n_halo * kw : 0);  // receive buffer in use (peer push)
         CK(launch_halo_scatter(rows, p->cpos, p->C, p->n_own_sorted, p->ne - p->n_own_sorted, n_pair_blocks(p->N), p->stream));
@@ -1283,6 +1286,7 @@ static int assemble_impl(ad4sm_plan* p, int32_t mode, int part) {
     p->prof_launches[AD4SM_PROF_ASSEMBLE] += want_K ? 2 : 1;
   }
   p->split_done = 0;
+  p->halo_prepared = false;
   p->ev_cur = nullptr;
   p->elements_mode = -1;
   if (p->push_pending) {  // the next evaluation's pushes land in the other receive buffer
@@ -1295,6 +1299,27 @@ static int assemble_impl(ad4sm_plan* p, int32_t mode, int part) {
   f.dz_valid = false;
   f.n_zero = -1;
   p->last_field = field;
+  return AD4SM_OK;
+}
+// After ad4sm_eval_assemble_split_device and once the interface rows have arrived: the HALO scatter into the sorted staging
+// and the interface rows of r, on `stream` (the stream the exchange ran on) -- off the main stream, which is still busy with
+// the interior.  The caller orders `stream` behind the exchange and the main stream behind `stream`.
+int ad4sm_eval_halo_prepare_device(ad4sm_plan* p, int32_t mode, void* cuda_stream) {
+  if (!p) return fail(AD4SM_EINVAL, "plan is NULL");
+  if (p->elements_mode != mode || mode < 0 || mode > 3) return fail(AD4SM_ESTATE, "ad4sm_eval_halo_prepare_device: no element evaluation of this mode pending");
+  if (p->split_done != 2 || p->halo_prepared) return AD4SM_OK;  // nothing was split off (or already done): the assembly does it all
+  CK(cudaSetDevice(p->device));
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : p->copy_stream;
+  const int field = mode == MODE_PF_D ? AD4SM_FIELD_D : AD4SM_FIELD_U;
+  AsmArgs a = asm_args(p, field);
+  a.node0 = p->split_node;
+  CK(launch_k3(a, s));
+  if (p->sorted_last && p->n_own_sorted < p->ne) {
+    const long long kw = (long long)n_pair_blocks(p->N) * p->D * p->D;
+    const double* rows = p->Ke + ((p->push_pending && p->parity) ? p->n_halo * kw : 0);
+    CK(launch_halo_scatter(rows, p->cpos, p->C, p->n_own_sorted, p->ne - p->n_own_sorted, n_pair_blocks(p->N), s));
+  }
+  p->halo_prepared = true;
   return AD4SM_OK;
 }
 int ad4sm_eval_assemble_device(ad4sm_plan* p, int32_t mode) { return assemble_impl(p, mode, 0); }
@@ -2131,7 +2156,6 @@ static int dist_eval_stages(ad4sm_plan* p, int32_t mode, const double* u_dev, co
   CK(cudaStreamWaitEvent(xs, p->ev_exports, 0));
   if (!xf.empty() && dist_exchange(p->dcomm->c, (int)xf.size(), xf.data(), xs, &err)) return fail(AD4SM_ENCCL, err);
   if (dist_allgather(p->dcomm->c, p->phi_local, p->allphi, 1, xs, &err)) return fail(AD4SM_ENCCL, err);
-  CK(cudaEventRecord(p->ev_pushed, xs));
   static const bool dprof = getenv("AD4SM_DIST_PROF") != nullptr;
   cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
   if (dprof && p->dprof.size() < 4 * 4096) {
@@ -2145,6 +2169,10 @@ static int dist_eval_stages(ad4sm_plan* p, int32_t mode, const double* u_dev, co
   rc = ad4sm_eval_assemble_split_device(p, mode);
   if (rc) return rc;
   if (pe[2]) CK(cudaEventRecord(pe[2], s));  // interior assembled
+  // behind the exchange, still on its stream: HALO scatter + the interface rows of r (the main stream is busy with the interior)
+  rc = ad4sm_eval_halo_prepare_device(p, mode, xs);
+  if (rc) return rc;
+  CK(cudaEventRecord(p->ev_pushed, xs));
   CK(cudaStreamWaitEvent(s, p->ev_pushed, 0));
   rc = ad4sm_eval_assemble_device(p, mode);
   if (rc) return rc;

@@ -232,6 +232,9 @@ class GpuBackend:
     def assemble_interior(self):
         self.plan.eval_assemble_interior_device(self.mode)
 
+    def halo_prepare(self, cuda_stream):
+        self.plan.eval_halo_prepare_device(self.mode, cuda_stream)
+
     def phi_tensor(self):
         if self._phi_t is None:   # library-owned device memory: the views are made once
             v = self.plan.device_view(self.field_id)
@@ -451,6 +454,8 @@ class DistPlan:
             self.b.assemble_interior()
             if prof:
                 prof[2].record(main)
+            # behind the exchange, on its stream: HALO rows into the sorted staging + the interface rows of r
+            self.b.halo_prepare(self._side.cuda_stream)
             main.wait_stream(self._side)
         else:
             exchange()

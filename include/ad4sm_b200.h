@@ -273,6 +273,12 @@ int ad4sm_eval_assemble_device(ad4sm_plan* plan, int32_t mode);
  * one-call assembly.  (ϕ, which needs no exchange either, is reduced at the end of the element stage.)  On plans without
  * destination-sorted staging or without HALO batch it does nothing. */
 int ad4sm_eval_assemble_split_device(ad4sm_plan* plan, int32_t mode);
+/* Optional, after ad4sm_eval_assemble_split_device and once the interface rows have arrived: moves the HALO rows into the
+ * sorted staging and assembles the interface rows of r on `cuda_stream` (cudaStream_t; the stream the exchange ran on, NULL =
+ * the plan's copy stream), so that this work overlaps the interior assembly still running on the plan's stream.  The caller
+ * orders `cuda_stream` behind the exchange and the plan's stream behind `cuda_stream` before ad4sm_eval_assemble_device,
+ * which then only assembles the interface pairs of Kt.  A no-op when nothing was split off. */
+int ad4sm_eval_halo_prepare_device(ad4sm_plan* plan, int32_t mode, void* cuda_stream);
 /* The same two stages for callers whose u / r live in host memory (what makeϕrKt's arguments are, elasticelements.jl:
  * 356-358): elements_host uploads u (d, hist) and runs the element stage -- on large single-batch plans the upload goes
  * in node chunks and K1 starts on the element slice whose nodes have arrived; fetch_phi_r_async enqueues the copy of

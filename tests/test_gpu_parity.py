@@ -178,7 +178,7 @@ def test_cuda_path_reproduces_golden_vectors(path):
     _golden.compare(_golden.run_product(case), case, tol=K.TOL)
 
 
-@pytest.mark.parametrize("shape,split", [("hex8", False), ("tet4", False), ("hex8", True), ("tet4", True)])
+@pytest.mark.parametrize("shape,split", [("hex8", False), ("tet4", False), ("hex8", True), ("tet4", True), ("hex8", "prepare")])
 def test_two_rank_halo_exchange_single_gpu(shape, split):
     """Mesh-partitioned evaluation (dist.py) emulated on ONE GPU: two in-process plans with HALO batches, the
     interface staging copied between them where NCCL send/recv would carry it.  Owned rows must be BITWISE equal to
@@ -225,6 +225,9 @@ def test_two_rank_halo_exchange_single_gpu(shape, split):
     torch.cuda.synchronize()
     phis, seen = [], np.zeros(u.shape[1], dtype=int)
     for p, be in zip(parts, backs):
+        if split == "prepare":   # HALO scatter + interface rows of r on the plan's copy stream (ad4sm_eval_halo_prepare_device)
+            be.halo_prepare(None)
+            be.plan.sync()
         be.assemble()
         be.plan.sync()
         phis.append(float(be.phi_tensor().cpu()[0]))
