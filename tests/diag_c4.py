@@ -1,11 +1,12 @@
-"""diagnostic: C4 sample (200x200 QuadP PhaseField(NeoHooke), plane-strain extension) on the GPU against the oracle: error
+"""TEST INFRASTRUCTURE (a script, not collected by pytest; it is the only place outside test_*.py / bench.py that touches the oracle).
+Diagnostic: C4 sample (200x200 QuadP PhaseField(NeoHooke), plane-strain extension) on the GPU against the oracle: error
 distribution relative to the natural scale of each entry, reproducibility, and independence of the K1 launch shape"""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from oracle.check import entry_scales  # noqa: E402

@@ -2,7 +2,7 @@
 # round-2 GPU call 23: C4 parity diagnostic with the oracle fed the arrays the product holds; C1 / C4 bench lines (all legs)
 set -x
 mkdir -p gpurun_out
-python tools/gpu/diag_c4.py 200 200 > gpurun_out/r2_diag23_c4.txt 2>&1
+python tests/diag_c4.py 200 200 > gpurun_out/r2_diag23_c4.txt 2>&1
 grep -E "phase|violations|percentiles" -A1 gpurun_out/r2_diag23_c4.txt | head -20
 for c in C1 C4; do
 python bench.py --config $c --steps 20 --warmup 5 > gpurun_out/r2_final_$c.json 2> gpurun_out/r2_final_$c.err
